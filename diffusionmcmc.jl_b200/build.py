@@ -1,0 +1,45 @@
+"""Build the C-ABI shared library (hand-written CUDA for sm_100a) in-tree with nvcc."""
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libdmcmc_b200.so")
+SOURCES = ["dmcmc_capi.cu", "dmcmc_solve.cu", "dmcmc_bf.cu"]
+HEADERS = ["dmcmc_device.cuh", "dmcmc_internal.h", "dmcmc_models.cuh",
+           os.path.join("..", "..", "include", "dmcmc.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU.  Returns the library path."""
+    if not force and not _stale():
+        return LIB_PATH
+    objs = []
+    procs = []
+    for src in SOURCES:  # compile translation units in parallel
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = ["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", "-o", obj,
+                                                                      os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
+        objs.append(obj)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB_PATH] + objs +
+                          ["-gencode", "arch=compute_100a,code=sm_100a"], cwd=CSRC)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,295 @@
+// dmcmc_bf.cu -- a8: the backward filter (backward_filter!, /root/reference
+// src/run!_alterations.jl:203; recompute_guiding_term!, src/workspaces.jl:428) as a batched
+// small-matrix recursion, one thread per layout block.
+//
+// The ODEs  H' = -B'H - HB + H a~ H,  F' = -B'F + H a~ F + H beta,  c' = beta'F + F'a~F/2 - tr(H a~)/2
+// with (B, beta, a~) constant on an interval have the exact one-step flow
+//     K = (I + H+ Q)^-1,  H* = K H+,  F* = K F+,
+//     H = Phi' H* Phi,    F = Phi'(F* - H* m),
+//     c = c+ + log det(I + H+ Q)/2 + m'H* m/2 - m'F* - F+' Q F*/2
+// where x(t+dt) | x(t) ~ N(Phi x + m, Q) is the aux law's transition.  For pinned blocks the
+// dependence on the pinned end point x_b is carried as F = F0 + Psi x_b, c = c0 + g'x_b + x_b'Qc x_b/2
+// so that one table serves every chain.  Same operation order as oracle/dmcmc_oracle.c.
+#include <cmath>
+
+#include "dmcmc_device.cuh"
+#include "dmcmc_internal.h"
+
+namespace dmcmc {
+
+template <int D>
+struct SmallMat {
+    __device__ static void mm(const double *A, const double *B, double *C) {
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < D; ++k) s += A[i * D + k] * B[k * D + j];
+                C[i * D + j] = s;
+            }
+    }
+    __device__ static void mmT(const double *A, const double *B, double *C) {
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < D; ++k) s += A[i * D + k] * B[j * D + k];
+                C[i * D + j] = s;
+            }
+    }
+    __device__ static void mTm(const double *A, const double *B, double *C) {
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < D; ++k) s += A[k * D + i] * B[k * D + j];
+                C[i * D + j] = s;
+            }
+    }
+    __device__ static void mv(const double *A, const double *x, double *y) {
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[i * D + k] * x[k];
+            y[i] = s;
+        }
+    }
+    __device__ static void mTv(const double *A, const double *x, double *y) {
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[k * D + i] * x[k];
+            y[i] = s;
+        }
+    }
+    __device__ static double dot(const double *a, const double *b) {
+        double s = 0.0;
+        for (int i = 0; i < D; ++i) s += a[i] * b[i];
+        return s;
+    }
+    __device__ static void sym(double *A) {
+        for (int i = 0; i < D; ++i)
+            for (int j = i + 1; j < D; ++j) {
+                const double s = 0.5 * (A[i * D + j] + A[j * D + i]);
+                A[i * D + j] = s;
+                A[j * D + i] = s;
+            }
+    }
+    __device__ static void lu(double *A, int *piv, double &lad) {
+        lad = 0.0;
+        for (int k = 0; k < D; ++k) {
+            int p = k;
+            double best = fabs(A[k * D + k]);
+            for (int i = k + 1; i < D; ++i)
+                if (fabs(A[i * D + k]) > best) { best = fabs(A[i * D + k]); p = i; }
+            piv[k] = p;
+            if (p != k)
+                for (int j = 0; j < D; ++j) {
+                    const double t = A[k * D + j]; A[k * D + j] = A[p * D + j]; A[p * D + j] = t;
+                }
+            lad += log(fabs(A[k * D + k]));
+            const double inv = 1.0 / A[k * D + k];
+            for (int i = k + 1; i < D; ++i) {
+                const double l = A[i * D + k] * inv;
+                A[i * D + k] = l;
+                for (int j = k + 1; j < D; ++j) A[i * D + j] -= l * A[k * D + j];
+            }
+        }
+    }
+    template <int NR>
+    __device__ static void solve(const double *LU, const int *piv, double *Bm) {
+        for (int k = 0; k < D; ++k) {
+            const int p = piv[k];
+            if (p != k)
+                for (int j = 0; j < NR; ++j) {
+                    const double t = Bm[k * NR + j]; Bm[k * NR + j] = Bm[p * NR + j]; Bm[p * NR + j] = t;
+                }
+            for (int i = k + 1; i < D; ++i) {
+                const double l = LU[i * D + k];
+                for (int j = 0; j < NR; ++j) Bm[i * NR + j] -= l * Bm[k * NR + j];
+            }
+        }
+        for (int k = D - 1; k >= 0; --k) {
+            const double inv = 1.0 / LU[k * D + k];
+            for (int j = 0; j < NR; ++j) {
+                double s = Bm[k * NR + j];
+                for (int i = k + 1; i < D; ++i) s -= LU[k * D + i] * Bm[i * NR + j];
+                Bm[k * NR + j] = s * inv;
+            }
+        }
+    }
+};
+
+constexpr int TAYLOR_TERMS = 16;
+
+// transition (Phi, Q, m) of dx = (Bx + beta)dt + sigma~ dW over dt: Taylor series of
+// Phi = e^{B dt}, m = int_0^dt e^{Bs} beta ds, Q = int_0^dt e^{Bs} a~ e^{B's} ds with
+// scaling-and-doubling.  Mirrors orc_transition.
+template <int D>
+__device__ void transition(const double *B, const double *beta, const double *atil, double dt,
+                           double *Phi, double *Q, double *mvec) {
+    using S = SmallMat<D>;
+    double nrm = 0.0;
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < D; ++j) s += fabs(B[i * D + j]);
+        if (s > nrm) nrm = s;
+    }
+    int sq = 0;
+    double h = dt;
+    while (nrm * h > 0.25 && sq < 40) { h *= 0.5; ++sq; }
+    double Pn[D * D], An[D * D], T1[D * D], T2[D * D], bn[D], tv[D];
+    for (int i = 0; i < D * D; ++i) { Phi[i] = 0.0; Pn[i] = 0.0; }
+    for (int i = 0; i < D; ++i) { Phi[i * D + i] = 1.0; Pn[i * D + i] = 1.0; }
+    for (int i = 0; i < D * D; ++i) An[i] = atil[i];
+    for (int i = 0; i < D; ++i) bn[i] = beta[i];
+    double coef = h;
+    for (int i = 0; i < D * D; ++i) Q[i] = coef * An[i];
+    for (int i = 0; i < D; ++i) mvec[i] = coef * bn[i];
+    for (int n = 1; n <= TAYLOR_TERMS; ++n) {
+        S::mm(B, Pn, T1);
+        for (int i = 0; i < D * D; ++i) { Pn[i] = T1[i] * (h / n); Phi[i] += Pn[i]; }
+        S::mm(B, An, T1);
+        S::mmT(An, B, T2);
+        for (int i = 0; i < D * D; ++i) An[i] = T1[i] + T2[i];
+        S::mv(B, bn, tv);
+        for (int i = 0; i < D; ++i) bn[i] = tv[i];
+        coef = coef * h / (n + 1);
+        for (int i = 0; i < D * D; ++i) Q[i] += coef * An[i];
+        for (int i = 0; i < D; ++i) mvec[i] += coef * bn[i];
+    }
+    for (int s = 0; s < sq; ++s) {
+        S::mm(Phi, Q, T1);
+        S::mmT(T1, Phi, T2);
+        for (int i = 0; i < D * D; ++i) Q[i] += T2[i];
+        S::mv(Phi, mvec, tv);
+        for (int i = 0; i < D; ++i) mvec[i] += tv[i];
+        S::mm(Phi, Phi, T1);
+        for (int i = 0; i < D * D; ++i) Phi[i] = T1[i];
+    }
+    S::sym(Q);
+}
+
+template <int D>
+struct BFState {
+    double H[D * D], F0[D], Psi[D * D], c0, g[D], Qc[D * D];
+};
+
+template <int D>
+__device__ void bf_step(bool pinned, const double *Phi, const double *Q, const double *mvec,
+                        BFState<D> &s) {
+    using S = SmallMat<D>;
+    double A[D * D], Hs[D * D], T1[D * D], Psis[D * D], Fs[D], tv[D], tv2[D];
+    int piv[D];
+    double lad;
+    S::mm(s.H, Q, A);
+    for (int i = 0; i < D; ++i) A[i * D + i] += 1.0;
+    S::lu(A, piv, lad);
+    for (int i = 0; i < D * D; ++i) Hs[i] = s.H[i];
+    S::template solve<D>(A, piv, Hs);
+    S::sym(Hs);
+    for (int i = 0; i < D; ++i) Fs[i] = s.F0[i];
+    S::template solve<1>(A, piv, Fs);
+    S::mv(Hs, mvec, tv);
+    S::mv(Q, Fs, tv2);
+    s.c0 = s.c0 + 0.5 * lad + 0.5 * S::dot(mvec, tv) - S::dot(mvec, Fs) - 0.5 * S::dot(s.F0, tv2);
+    if (pinned) {
+        for (int i = 0; i < D * D; ++i) Psis[i] = s.Psi[i];
+        S::template solve<D>(A, piv, Psis);
+        double a1[D], a2[D];
+        S::mTv(Psis, mvec, a1);
+        S::mTv(s.Psi, tv2, a2);
+        for (int i = 0; i < D; ++i) s.g[i] = s.g[i] - a1[i] - a2[i];
+        S::mm(Q, Psis, T1);
+        S::mTm(s.Psi, T1, A);
+        for (int i = 0; i < D * D; ++i) s.Qc[i] -= A[i];
+        S::sym(s.Qc);
+        S::mTm(Phi, Psis, s.Psi);
+    }
+    for (int i = 0; i < D; ++i) tv2[i] = Fs[i] - tv[i];
+    S::mTv(Phi, tv2, s.F0);
+    S::mm(Hs, Phi, T1);
+    S::mTm(Phi, T1, s.H);
+    S::sym(s.H);
+}
+
+template <int D>
+__device__ void store_point(const BFParams &b, const BFState<D> &s, size_t pt) {
+    if (b.ptH)
+        for (int i = 0; i < D * D; ++i) b.ptH[pt * D * D + i] = s.H[i];
+    if (b.ptF0)
+        for (int i = 0; i < D; ++i) b.ptF0[pt * D + i] = s.F0[i];
+    if (b.ptPsi)
+        for (int i = 0; i < D * D; ++i) b.ptPsi[pt * D * D + i] = s.Psi[i];
+    if (b.ptc0) b.ptc0[pt] = s.c0;
+}
+
+template <int D>
+__device__ void store_rec(const BFParams &b, const BFState<D> &s, size_t step, double dt) {
+    double *r = b.table + step * b.rec;
+    r[0] = dt;
+    r[1] = sqrt(dt);
+    int o = 2;
+    for (int i = 0; i < D; ++i)
+        for (int k = i; k < D; ++k) r[o++] = s.H[i * D + k];
+    for (int i = 0; i < D; ++i) r[o++] = s.F0[i];
+    if (b.has_psi)
+        for (int i = 0; i < D * D; ++i) r[o++] = s.Psi[i];
+}
+
+template <int D>
+__global__ void bf_kernel(const BFParams b) {
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= b.nblk) return;
+    BFState<D> s;
+    for (int i = 0; i < D * D; ++i) { s.H[i] = 0.0; s.Psi[i] = 0.0; s.Qc[i] = 0.0; }
+    for (int i = 0; i < D; ++i) { s.F0[i] = 0.0; s.g[i] = 0.0; }
+    s.c0 = 0.0;
+    const bool pinned = b.blk_pinned[blk] != 0;
+    const int i1 = b.blk_i1[blk], i2 = b.blk_i2[blk];
+    double Phi[D * D], Q[D * D], mvec[D];
+    for (int j = i2; j >= i1; --j) {
+        if (j == i2 && pinned) {
+            const double ie = 1.0 / b.pin_eps;
+            for (int i = 0; i < D; ++i) { s.H[i * D + i] = ie; s.Psi[i * D + i] = ie; s.Qc[i * D + i] = ie; }
+            s.c0 = 0.5 * D * log(2.0 * M_PI * b.pin_eps);
+        } else {
+            for (int i = 0; i < D * D; ++i) s.H[i] += b.Hobs[(size_t)j * D * D + i];
+            for (int i = 0; i < D; ++i) s.F0[i] += b.Fobs[(size_t)j * D + i];
+            s.c0 += b.cobs[j];
+        }
+        const int N = b.iv_N[j];
+        const size_t base = (size_t)b.iv_pt_off[j];
+        const size_t sbase = (size_t)b.iv_tile_off[j] * TILE;
+        store_point<D>(b, s, base + N);
+        double dt_cached = -1.0;
+        for (int k = N - 1; k >= 0; --k) {
+            const double dt = b.t[base + k + 1] - b.t[base + k];
+            if (!(fabs(dt - dt_cached) <= 1e-12 * fabs(dt_cached))) {
+                transition<D>(b.auxB + (size_t)j * D * D, b.auxbeta + (size_t)j * D,
+                              b.auxatil + (size_t)j * D * D, dt, Phi, Q, mvec);
+                dt_cached = dt;
+            }
+            bf_step<D>(pinned, Phi, Q, mvec, s);
+            store_point<D>(b, s, base + k);
+            store_rec<D>(b, s, sbase + k, dt);
+        }
+        // pad slots of the interval's last tile: benign record (dt = 0)
+        for (int k = N; k < ((N + TILE - 1) / TILE) * TILE; ++k) {
+            double *r = b.table + (sbase + k) * b.rec;
+            for (int i = 0; i < b.rec; ++i) r[i] = 0.0;
+        }
+    }
+    b.blk_c0[blk] = s.c0;
+    for (int i = 0; i < D; ++i) b.blk_g[(size_t)blk * D + i] = s.g[i];
+    for (int i = 0; i < D * D; ++i) b.blk_Qc[(size_t)blk * D * D + i] = s.Qc[i];
+}
+
+cudaError_t launch_backward_filter(const BFParams &b, cudaStream_t s) {
+    if (b.nblk == 0) return cudaSuccess;
+    const int threads = 32;
+    const unsigned grid = (unsigned)((b.nblk + threads - 1) / threads);
+    switch (b.D) {
+    case 2: bf_kernel<2><<<grid, threads, 0, s>>>(b); break;
+    case 3: bf_kernel<3><<<grid, threads, 0, s>>>(b); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dmcmc

@@ -1,0 +1,1056 @@
+// dmcmc_capi.cu -- the C ABI of include/dmcmc.h: context, problem upload, launches, read-outs.
+// Host-side logic only; the arithmetic of the hot path is in dmcmc_solve.cu / dmcmc_bf.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/dmcmc.h"
+#include "dmcmc_device.cuh"
+#include "dmcmc_internal.h"
+
+using namespace dmcmc;
+
+namespace {
+std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// tables and block constants of one (law, layout) pair
+struct Tables {
+    DevBuf<double> table, blk_c0, blk_g, blk_Qc;
+    DevBuf<double> ptH, ptF0, ptPsi, ptc0;  // per grid point, for download / parity
+    bool valid = false;
+};
+
+struct Layout {
+    std::vector<int32_t> i1, i2, pinned, iv_blk;
+    int32_t nblk = 0;
+    bool has_psi = false;
+    DevBuf<int32_t> d_i1, d_i2, d_pinned, d_iv_blk;
+    Tables tab[2];  // per law slot
+    uint64_t last_used = 0;
+    bool used = false;
+};
+
+struct Law {
+    double theta[DMCMC_MAX_THETA] = {0};
+    std::vector<double> auxB, auxbeta, auxsig, auxatil;
+    DevBuf<double> d_auxB, d_auxbeta, d_auxatil;
+    bool have_theta = false, custom_aux = false;
+};
+}  // namespace
+
+struct dmcmc_ctx {
+    dmcmc_config cfg{};
+    int d = 0, m = 0, nth = 0, C = 0, R = 0, J = 0, p = 0;
+    int64_t P = 0, S = 0, TT = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> ev;  // pairs (start, stop) of timed solve launches
+    size_t ev_used = 0;
+    bool timing = true;
+    // host copies
+    std::vector<int32_t> rec_nobs, N, pt_off, st_off, tile_off, iv_first, iv_rec;
+    std::vector<double> t, L, Sigma, v, Hobs, Fobs, cobs, rho, x0;
+    bool have_grid = false, have_obs = false, have_start = false;
+    Law law[2];
+    int law_cur = 0;
+    Layout layout[2];
+    int lay_cur = -1;
+    uint64_t lay_clock = 0;
+    // device
+    DevBuf<int32_t> d_N, d_tile_off, d_first, d_rec, d_pt_off;
+    DevBuf<double> d_t, d_rho, d_Hobs, d_Fobs, d_cobs, d_x0, d_ll, d_Z, d_E;
+    DevBuf<double> d_X[2], d_W[2];
+    DevBuf<uint8_t> d_selX[2], d_selW[2], d_mask, d_out_acc;
+    int sel_cur = 0;
+    DevBuf<double> d_out_llprop, d_out_ll, d_param_llprop;
+    DevBuf<unsigned long long> d_counts;  // [2][J]: accepted, proposed
+    std::vector<double> h_param_llprop;
+    bool param_pending = false;
+    int threads = 64;
+};
+
+namespace {
+
+int fail(dmcmc_ctx *c, const std::string &msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return -1;
+}
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+#define REQUIRE(cond, msg)                 \
+    do {                                   \
+        if (!(cond)) return fail(ctx, msg); \
+    } while (0)
+
+template <class T>
+int upload(dmcmc_ctx *ctx, DevBuf<T> &b, const T *src, size_t n) {
+    CK(b.ensure(n));
+    if (n) CK(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+template <class T>
+int upload(dmcmc_ctx *ctx, DevBuf<T> &b, const std::vector<T> &v) {
+    return upload(ctx, b, v.data(), v.size());
+}
+
+int sync(dmcmc_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// LU helpers for the (tiny) observation algebra on the host
+bool lu_factor(int n, std::vector<double> &A, std::vector<int> &piv, double &lad) {
+    lad = 0.0;
+    piv.assign(n, 0);
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        double best = std::fabs(A[k * n + k]);
+        for (int i = k + 1; i < n; ++i)
+            if (std::fabs(A[i * n + k]) > best) { best = std::fabs(A[i * n + k]); p = i; }
+        piv[k] = p;
+        if (best == 0.0) return false;
+        if (p != k)
+            for (int j = 0; j < n; ++j) std::swap(A[k * n + j], A[p * n + j]);
+        lad += std::log(std::fabs(A[k * n + k]));
+        const double inv = 1.0 / A[k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            const double l = A[i * n + k] * inv;
+            A[i * n + k] = l;
+            for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
+        }
+    }
+    return true;
+}
+void lu_solve(int n, const std::vector<double> &LU, const std::vector<int> &piv, double *B, int nrhs) {
+    for (int k = 0; k < n; ++k) {
+        const int p = piv[k];
+        if (p != k)
+            for (int j = 0; j < nrhs; ++j) std::swap(B[k * nrhs + j], B[p * nrhs + j]);
+        for (int i = k + 1; i < n; ++i) {
+            const double l = LU[i * n + k];
+            for (int j = 0; j < nrhs; ++j) B[i * nrhs + j] -= l * B[k * nrhs + j];
+        }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        const double inv = 1.0 / LU[k * n + k];
+        for (int j = 0; j < nrhs; ++j) {
+            double s = B[k * nrhs + j];
+            for (int i = k + 1; i < n; ++i) s -= LU[k * n + i] * B[i * nrhs + j];
+            B[k * nrhs + j] = s * inv;
+        }
+    }
+}
+
+// H += L'S^-1 L, F += L'S^-1 v, c += v'S^-1 v/2 + log det(2 pi S)/2 at every observation
+int compute_obs_terms(dmcmc_ctx *ctx) {
+    const int d = ctx->d, p = ctx->p, J = ctx->J;
+    ctx->Hobs.assign((size_t)J * d * d, 0.0);
+    ctx->Fobs.assign((size_t)J * d, 0.0);
+    ctx->cobs.assign(J, 0.0);
+    std::vector<double> S, SiL, Siv;
+    std::vector<int> piv;
+    for (int j = 0; j < J; ++j) {
+        const double *L = &ctx->L[(size_t)j * p * d], *v = &ctx->v[(size_t)j * p];
+        S.assign(&ctx->Sigma[(size_t)j * p * p], &ctx->Sigma[(size_t)j * p * p] + p * p);
+        double lad;
+        REQUIRE(lu_factor(p, S, piv, lad), "dmcmc_set_obs: singular observation covariance");
+        SiL.assign(L, L + p * d);
+        lu_solve(p, S, piv, SiL.data(), d);
+        Siv.assign(v, v + p);
+        lu_solve(p, S, piv, Siv.data(), 1);
+        double *H = &ctx->Hobs[(size_t)j * d * d], *F = &ctx->Fobs[(size_t)j * d];
+        for (int i = 0; i < d; ++i) {
+            for (int k = 0; k < d; ++k) {
+                double s = 0.0;
+                for (int q = 0; q < p; ++q) s += L[q * d + i] * SiL[q * d + k];
+                H[i * d + k] = s;
+            }
+            double s = 0.0;
+            for (int q = 0; q < p; ++q) s += L[q * d + i] * Siv[q];
+            F[i] = s;
+        }
+        for (int i = 0; i < d; ++i)
+            for (int k = i + 1; k < d; ++k) {
+                const double s = 0.5 * (H[i * d + k] + H[k * d + i]);
+                H[i * d + k] = H[k * d + i] = s;
+            }
+        double vs = 0.0;
+        for (int q = 0; q < p; ++q) vs += v[q] * Siv[q];
+        ctx->cobs[j] = 0.5 * vs + 0.5 * (p * std::log(2.0 * M_PI) + lad);
+    }
+    if (upload(ctx, ctx->d_Hobs, ctx->Hobs)) return -1;
+    if (upload(ctx, ctx->d_Fobs, ctx->Fobs)) return -1;
+    if (upload(ctx, ctx->d_cobs, ctx->cobs)) return -1;
+    return 0;
+}
+
+int build_aux(dmcmc_ctx *ctx, int slot) {
+    Law &law = ctx->law[slot];
+    const int d = ctx->d, m = ctx->m, J = ctx->J;
+    if (!law.custom_aux) {
+        REQUIRE(ctx->have_obs, "auxiliary laws need the observations: call dmcmc_set_obs first");
+        law.auxB.assign((size_t)J * d * d, 0.0);
+        law.auxbeta.assign((size_t)J * d, 0.0);
+        law.auxsig.assign((size_t)J * d * m, 0.0);
+        for (int j = 0; j < J; ++j)
+            aux_build_host(ctx->cfg.model, d, m, law.theta, &ctx->v[(size_t)j * ctx->p], ctx->p,
+                           &law.auxB[(size_t)j * d * d], &law.auxbeta[(size_t)j * d],
+                           &law.auxsig[(size_t)j * d * m]);
+    }
+    law.auxatil.assign((size_t)J * d * d, 0.0);
+    for (int j = 0; j < J; ++j)
+        for (int i = 0; i < d; ++i)
+            for (int k = 0; k < d; ++k) {
+                double s = 0.0;
+                for (int c = 0; c < m; ++c)
+                    s += law.auxsig[((size_t)j * d + i) * m + c] * law.auxsig[((size_t)j * d + k) * m + c];
+                law.auxatil[((size_t)j * d + i) * d + k] = s;
+            }
+    if (upload(ctx, law.d_auxB, law.auxB)) return -1;
+    if (upload(ctx, law.d_auxbeta, law.auxbeta)) return -1;
+    if (upload(ctx, law.d_auxatil, law.auxatil)) return -1;
+    for (auto &lay : ctx->layout) lay.tab[slot].valid = false;
+    return 0;
+}
+
+int ensure_tables_alloc(dmcmc_ctx *ctx, Layout &lay, int slot) {
+    Tables &tb = lay.tab[slot];
+    const int d = ctx->d;
+    const size_t rec = rec_size(d, lay.has_psi);
+    CK(tb.table.ensure((size_t)ctx->TT * TILE * rec));
+    CK(tb.blk_c0.ensure(lay.nblk));
+    CK(tb.blk_g.ensure((size_t)lay.nblk * d));
+    CK(tb.blk_Qc.ensure((size_t)lay.nblk * d * d));
+    CK(tb.ptH.ensure((size_t)ctx->P * d * d));
+    CK(tb.ptF0.ensure((size_t)ctx->P * d));
+    CK(tb.ptPsi.ensure((size_t)ctx->P * d * d));
+    CK(tb.ptc0.ensure((size_t)ctx->P));
+    return 0;
+}
+
+int run_backward_filter(dmcmc_ctx *ctx, int slot) {
+    REQUIRE(ctx->lay_cur >= 0, "no layout set");
+    REQUIRE(ctx->have_obs && ctx->have_grid, "grid/observations missing");
+    REQUIRE(ctx->law[slot].have_theta || ctx->law[slot].custom_aux, "law has no parameters");
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    if (ensure_tables_alloc(ctx, lay, slot)) return -1;
+    Tables &tb = lay.tab[slot];
+    Law &law = ctx->law[slot];
+    BFParams b{};
+    b.D = ctx->d; b.J = ctx->J; b.nblk = lay.nblk;
+    b.blk_i1 = lay.d_i1.p; b.blk_i2 = lay.d_i2.p; b.blk_pinned = lay.d_pinned.p;
+    b.iv_N = ctx->d_N.p; b.iv_tile_off = ctx->d_tile_off.p; b.iv_pt_off = ctx->d_pt_off.p;
+    b.t = ctx->d_t.p;
+    b.auxB = law.d_auxB.p; b.auxbeta = law.d_auxbeta.p; b.auxatil = law.d_auxatil.p;
+    b.Hobs = ctx->d_Hobs.p; b.Fobs = ctx->d_Fobs.p; b.cobs = ctx->d_cobs.p;
+    b.pin_eps = ctx->cfg.pin_eps;
+    b.has_psi = lay.has_psi; b.rec = rec_size(ctx->d, lay.has_psi);
+    b.table = tb.table.p;
+    b.ptH = tb.ptH.p; b.ptF0 = tb.ptF0.p; b.ptPsi = tb.ptPsi.p; b.ptc0 = tb.ptc0.p;
+    b.blk_c0 = tb.blk_c0.p; b.blk_g = tb.blk_g.p; b.blk_Qc = tb.blk_Qc.p;
+    CK(launch_backward_filter(b, ctx->stream));
+    tb.valid = true;
+    return 0;
+}
+
+int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
+    REQUIRE(ctx->lay_cur >= 0, "no layout set");
+    REQUIRE(ctx->have_grid && ctx->have_start, "grid / starting points missing");
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    Tables &tb = lay.tab[slot];
+    REQUIRE(tb.valid, "backward-filter tables missing: call dmcmc_backward_filter / dmcmc_upload_tables");
+    Law &law = ctx->law[slot];
+    sp = SolveParams{};
+    sp.C = ctx->C; sp.nblk = lay.nblk; sp.J = ctx->J; sp.chain_offset = ctx->cfg.chain_offset;
+    sp.TT = ctx->TT;
+    sp.blk_i1 = lay.d_i1.p; sp.blk_i2 = lay.d_i2.p; sp.blk_pinned = lay.d_pinned.p;
+    sp.iv_N = ctx->d_N.p; sp.iv_tile_off = ctx->d_tile_off.p; sp.iv_first = ctx->d_first.p;
+    sp.iv_rec = ctx->d_rec.p;
+    sp.rho = ctx->d_rho.p;
+    sp.auxB = law.d_auxB.p; sp.auxbeta = law.d_auxbeta.p; sp.auxatil = law.d_auxatil.p;
+    sp.table = tb.table.p; sp.blk_c0 = tb.blk_c0.p; sp.blk_g = tb.blk_g.p; sp.blk_Qc = tb.blk_Qc.p;
+    sp.has_psi = lay.has_psi;
+    for (int b = 0; b < 2; ++b) { sp.X[b] = ctx->d_X[b].p; sp.W[b] = ctx->d_W[b].p; }
+    sp.selX_in = ctx->d_selX[ctx->sel_cur].p; sp.selW_in = ctx->d_selW[ctx->sel_cur].p;
+    sp.selX_out = ctx->d_selX[1 - ctx->sel_cur].p; sp.selW_out = ctx->d_selW[1 - ctx->sel_cur].p;
+    sp.x0 = ctx->d_x0.p; sp.ll = ctx->d_ll.p;
+    sp.seed = ctx->cfg.seed;
+    for (int i = 0; i < DMCMC_MAX_THETA; ++i) sp.th.v[i] = law.theta[i];
+    return 0;
+}
+
+int timed_launch(dmcmc_ctx *ctx, int mode, const SolveParams &sp) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->timing) {
+        if (ctx->ev_used + 2 > ctx->ev.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                ctx->ev.push_back(e);
+            }
+        }
+        e0 = ctx->ev[ctx->ev_used];
+        e1 = ctx->ev[ctx->ev_used + 1];
+        ctx->ev_used += 2;
+        CK(cudaEventRecord(e0, ctx->stream));
+    }
+    CK(launch_solve(ctx->cfg.model, mode, sp, ctx->threads, ctx->stream));
+    if (ctx->timing) CK(cudaEventRecord(e1, ctx->stream));
+    return 0;
+}
+
+// [C][S][m] host normals -> [m][TT][C][8] device tiles
+int stage_noise(dmcmc_ctx *ctx, const double *Z) {
+    const int C = ctx->C, m = ctx->m, J = ctx->J;
+    const size_t n = (size_t)m * ctx->TT * C * TILE;
+    std::vector<double> buf(n, 0.0);
+    for (int c = 0; c < C; ++c)
+        for (int j = 0; j < J; ++j)
+            for (int k = 0; k < ctx->N[j]; ++k) {
+                const size_t tile = (size_t)ctx->tile_off[j] + (k >> 3);
+                for (int w = 0; w < m; ++w)
+                    buf[(((size_t)w * ctx->TT + tile) * C + c) * TILE + (k & 7)] =
+                        Z[((size_t)c * ctx->S + ctx->st_off[j] + k) * m + w];
+            }
+    CK(ctx->d_Z.ensure(n));
+    CK(cudaMemcpy(ctx->d_Z.p, buf.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int alloc_state(dmcmc_ctx *ctx) {
+    const size_t nx = (size_t)ctx->d * ctx->TT * ctx->C * TILE, nw = (size_t)ctx->m * ctx->TT * ctx->C * TILE;
+    const size_t ns = (size_t)ctx->J * ctx->C;
+    for (int b = 0; b < 2; ++b) {
+        CK(ctx->d_X[b].ensure(nx));
+        CK(ctx->d_W[b].ensure(nw));
+        CK(cudaMemsetAsync(ctx->d_X[b].p, 0, nx * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_W[b].p, 0, nw * sizeof(double), ctx->stream));
+        CK(ctx->d_selX[b].ensure(ns));
+        CK(ctx->d_selW[b].ensure(ns));
+        CK(cudaMemsetAsync(ctx->d_selX[b].p, 0, ns, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_selW[b].p, 0, ns, ctx->stream));
+    }
+    ctx->sel_cur = 0;
+    CK(ctx->d_counts.ensure((size_t)2 * ctx->J));
+    CK(cudaMemsetAsync(ctx->d_counts.p, 0, ctx->d_counts.bytes(), ctx->stream));
+    return 0;
+}
+
+int ensure_unit_buffers(dmcmc_ctx *ctx) {
+    const size_t n = (size_t)ctx->C * ctx->layout[ctx->lay_cur].nblk;
+    CK(ctx->d_out_llprop.ensure(n));
+    CK(ctx->d_out_ll.ensure(n));
+    CK(ctx->d_out_acc.ensure(n));
+    CK(ctx->d_E.ensure(n));
+    CK(ctx->d_mask.ensure(n));
+    return 0;
+}
+
+int select_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
+                  const int32_t *pinned) {
+    REQUIRE(ctx->have_grid, "dmcmc_set_layout: call dmcmc_set_grid first");
+    REQUIRE(nblk > 0, "dmcmc_set_layout: empty layout");
+    // validate: blocks tile [0, J) in order, never straddle recordings
+    int expect = 0;
+    for (int b = 0; b < nblk; ++b) {
+        REQUIRE(i1[b] == expect && i2[b] >= i1[b] && i2[b] < ctx->J, "dmcmc_set_layout: blocks must partition the intervals in order");
+        REQUIRE(ctx->iv_rec[i1[b]] == ctx->iv_rec[i2[b]], "dmcmc_set_layout: a block straddles two recordings");
+        const bool last_of_rec = (i2[b] == ctx->J - 1) || ctx->iv_first[i2[b] + 1];
+        REQUIRE(!(pinned[b] && last_of_rec) , "dmcmc_set_layout: the last block of a recording cannot be pinned");
+        REQUIRE(pinned[b] || last_of_rec, "dmcmc_set_layout: an interior block must be pinned");
+        expect = i2[b] + 1;
+    }
+    REQUIRE(expect == ctx->J, "dmcmc_set_layout: blocks must cover every interval");
+    for (int s = 0; s < 2; ++s) {
+        Layout &l = ctx->layout[s];
+        if (l.used && l.nblk == nblk && std::equal(i1, i1 + nblk, l.i1.begin()) &&
+            std::equal(i2, i2 + nblk, l.i2.begin()) && std::equal(pinned, pinned + nblk, l.pinned.begin())) {
+            ctx->lay_cur = s;
+            l.last_used = ++ctx->lay_clock;
+            return 0;
+        }
+    }
+    int s = 0;
+    if (ctx->layout[0].used && (!ctx->layout[1].used || ctx->layout[1].last_used < ctx->layout[0].last_used)) s = 1;
+    Layout &l = ctx->layout[s];
+    l.used = true;
+    l.nblk = nblk;
+    l.i1.assign(i1, i1 + nblk);
+    l.i2.assign(i2, i2 + nblk);
+    l.pinned.assign(pinned, pinned + nblk);
+    l.has_psi = std::any_of(pinned, pinned + nblk, [](int32_t x) { return x != 0; });
+    l.iv_blk.assign(ctx->J, 0);
+    for (int b = 0; b < nblk; ++b)
+        for (int j = i1[b]; j <= i2[b]; ++j) l.iv_blk[j] = b;
+    if (upload(ctx, l.d_i1, l.i1) || upload(ctx, l.d_i2, l.i2) || upload(ctx, l.d_pinned, l.pinned) ||
+        upload(ctx, l.d_iv_blk, l.iv_blk))
+        return -1;
+    l.tab[0].valid = l.tab[1].valid = false;
+    l.last_used = ++ctx->lay_clock;
+    ctx->lay_cur = s;
+    return 0;
+}
+
+int resize_ll(dmcmc_ctx *ctx) {
+    const size_t n = (size_t)ctx->C * ctx->layout[ctx->lay_cur].nblk;
+    CK(ctx->d_ll.ensure(n));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int dmcmc_create(const dmcmc_config *cfg, dmcmc_ctx **out) {
+    dmcmc_ctx *ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, "dmcmc_create: null argument");
+    if (cfg->abi_version != DMCMC_ABI_VERSION) return fail(nullptr, "dmcmc_create: ABI version mismatch");
+    int d, m, nth;
+    if (model_dims(cfg->model, cfg->d, &d, &m, &nth)) return fail(nullptr, "dmcmc_create: unknown model / unsupported dimension");
+    if (cfg->n_chains <= 0) return fail(nullptr, "dmcmc_create: n_chains must be positive");
+    if (!(cfg->pin_eps > 0.0)) return fail(nullptr, "dmcmc_create: pin_eps must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, std::string("dmcmc_create: no CUDA device (") + cudaGetErrorString(e) +
+                                 "); this backend has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "dmcmc_create: bad device ordinal");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10)
+        return fail(nullptr, "dmcmc_create: kernels are built for sm_100a (B200) only; found sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+    ctx = new dmcmc_ctx();
+    ctx->cfg = *cfg;
+    ctx->d = d; ctx->m = m; ctx->nth = nth; ctx->C = cfg->n_chains;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return 0;
+}
+
+void dmcmc_destroy(dmcmc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto e : ctx->ev) cudaEventDestroy(e);
+    auto rel_law = [](Law &l) { l.d_auxB.release(); l.d_auxbeta.release(); l.d_auxatil.release(); };
+    rel_law(ctx->law[0]);
+    rel_law(ctx->law[1]);
+    for (auto &l : ctx->layout) {
+        l.d_i1.release(); l.d_i2.release(); l.d_pinned.release(); l.d_iv_blk.release();
+        for (auto &t : l.tab) {
+            t.table.release(); t.blk_c0.release(); t.blk_g.release(); t.blk_Qc.release();
+            t.ptH.release(); t.ptF0.release(); t.ptPsi.release(); t.ptc0.release();
+        }
+    }
+    ctx->d_N.release(); ctx->d_tile_off.release(); ctx->d_first.release(); ctx->d_rec.release();
+    ctx->d_pt_off.release(); ctx->d_t.release(); ctx->d_rho.release(); ctx->d_Hobs.release();
+    ctx->d_Fobs.release(); ctx->d_cobs.release(); ctx->d_x0.release(); ctx->d_ll.release();
+    ctx->d_Z.release(); ctx->d_E.release();
+    for (int b = 0; b < 2; ++b) {
+        ctx->d_X[b].release(); ctx->d_W[b].release(); ctx->d_selX[b].release(); ctx->d_selW[b].release();
+    }
+    ctx->d_mask.release(); ctx->d_out_acc.release(); ctx->d_out_llprop.release();
+    ctx->d_out_ll.release(); ctx->d_param_llprop.release(); ctx->d_counts.release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *dmcmc_last_error(const dmcmc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs,
+                   const int32_t *n_steps, const double *t) {
+    REQUIRE(ctx && rec_nobs && n_steps && t && n_recordings > 0, "dmcmc_set_grid: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->R = n_recordings;
+    ctx->rec_nobs.assign(rec_nobs, rec_nobs + n_recordings);
+    int J = 0;
+    for (int r = 0; r < n_recordings; ++r) {
+        REQUIRE(rec_nobs[r] > 0, "dmcmc_set_grid: a recording has no observations");
+        J += rec_nobs[r];
+    }
+    ctx->J = J;
+    ctx->N.assign(n_steps, n_steps + J);
+    ctx->pt_off.assign(J + 1, 0);
+    ctx->st_off.assign(J + 1, 0);
+    ctx->tile_off.assign(J + 1, 0);
+    ctx->iv_first.assign(J, 0);
+    ctx->iv_rec.assign(J, 0);
+    int j = 0;
+    for (int r = 0; r < n_recordings; ++r)
+        for (int i = 0; i < rec_nobs[r]; ++i, ++j) {
+            ctx->iv_first[j] = (i == 0);
+            ctx->iv_rec[j] = r;
+        }
+    for (j = 0; j < J; ++j) {
+        REQUIRE(n_steps[j] > 0 && n_steps[j] < (1 << 24), "dmcmc_set_grid: n_steps out of range");
+        ctx->pt_off[j + 1] = ctx->pt_off[j] + n_steps[j] + 1;
+        ctx->st_off[j + 1] = ctx->st_off[j] + n_steps[j];
+        ctx->tile_off[j + 1] = ctx->tile_off[j] + (n_steps[j] + TILE - 1) / TILE;
+    }
+    ctx->P = ctx->pt_off[J];
+    ctx->S = ctx->st_off[J];
+    ctx->TT = ctx->tile_off[J];
+    ctx->t.assign(t, t + ctx->P);
+    for (j = 0; j < J; ++j)
+        for (int k = 0; k < n_steps[j]; ++k)
+            REQUIRE(t[ctx->pt_off[j] + k + 1] > t[ctx->pt_off[j] + k], "dmcmc_set_grid: grid times must increase");
+    if (upload(ctx, ctx->d_N, ctx->N) || upload(ctx, ctx->d_tile_off, ctx->tile_off) ||
+        upload(ctx, ctx->d_first, ctx->iv_first) || upload(ctx, ctx->d_rec, ctx->iv_rec) ||
+        upload(ctx, ctx->d_pt_off, ctx->pt_off) || upload(ctx, ctx->d_t, ctx->t))
+        return -1;
+    ctx->rho.assign(J, 0.0);
+    if (upload(ctx, ctx->d_rho, ctx->rho)) return -1;
+    ctx->have_grid = true;
+    ctx->have_obs = ctx->have_start = false;
+    ctx->lay_cur = -1;
+    ctx->layout[0].used = ctx->layout[1].used = false;
+    if (alloc_state(ctx)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_set_obs(dmcmc_ctx *ctx, int32_t p, const double *L, const double *Sigma, const double *v) {
+    REQUIRE(ctx && L && Sigma && v && p > 0, "dmcmc_set_obs: bad argument");
+    REQUIRE(ctx->have_grid, "dmcmc_set_obs: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->p = p;
+    const size_t J = ctx->J;
+    ctx->L.assign(L, L + J * p * ctx->d);
+    ctx->Sigma.assign(Sigma, Sigma + J * p * p);
+    ctx->v.assign(v, v + J * p);
+    if (compute_obs_terms(ctx)) return -1;
+    ctx->have_obs = true;
+    for (int s = 0; s < 2; ++s)
+        if (ctx->law[s].have_theta && build_aux(ctx, s)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_set_start(dmcmc_ctx *ctx, const double *x0) {
+    REQUIRE(ctx && x0, "dmcmc_set_start: bad argument");
+    REQUIRE(ctx->have_grid, "dmcmc_set_start: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int C = ctx->C, R = ctx->R, d = ctx->d;
+    ctx->x0.assign(x0, x0 + (size_t)C * R * d);
+    std::vector<double> tr((size_t)R * d * C);
+    for (int c = 0; c < C; ++c)
+        for (int r = 0; r < R; ++r)
+            for (int i = 0; i < d; ++i) tr[((size_t)r * d + i) * C + c] = x0[((size_t)c * R + r) * d + i];
+    if (upload(ctx, ctx->d_x0, tr)) return -1;
+    ctx->have_start = true;
+    return sync(ctx);
+}
+
+int dmcmc_set_theta(dmcmc_ctx *ctx, const double *theta, int32_t ntheta) {
+    REQUIRE(ctx && theta, "dmcmc_set_theta: bad argument");
+    REQUIRE(ntheta == ctx->nth, "dmcmc_set_theta: wrong number of parameters for this model");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Law &law = ctx->law[ctx->law_cur];
+    std::copy(theta, theta + ntheta, law.theta);
+    law.have_theta = true;
+    if (ctx->have_obs && build_aux(ctx, ctx->law_cur)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_set_aux(dmcmc_ctx *ctx, int32_t which, const double *B, const double *beta, const double *sigma_aux) {
+    REQUIRE(ctx && B && beta && sigma_aux && (which == 0 || which == 1), "dmcmc_set_aux: bad argument");
+    REQUIRE(ctx->have_grid, "dmcmc_set_aux: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int slot = ctx->law_cur ^ which;
+    Law &law = ctx->law[slot];
+    const size_t J = ctx->J, d = ctx->d, m = ctx->m;
+    law.auxB.assign(B, B + J * d * d);
+    law.auxbeta.assign(beta, beta + J * d);
+    law.auxsig.assign(sigma_aux, sigma_aux + J * d * m);
+    law.custom_aux = true;
+    if (build_aux(ctx, slot)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_chequerboard_layout(int32_t R, const int32_t *rec_nobs, int32_t half_len, int32_t pattern,
+                              int32_t *i1, int32_t *i2, int32_t *pinned) {
+    if (!rec_nobs || !i1 || !i2 || !pinned || R <= 0) return -1;
+    int nb = 0, base = 0;
+    for (int r = 0; r < R; ++r) {
+        const int n = rec_nobs[r];
+        if (half_len <= 0) {
+            i1[nb] = base; i2[nb] = base + n - 1; pinned[nb] = 0; ++nb;
+        } else {
+            int start = 0, len = pattern ? half_len : 2 * half_len;
+            while (start < n) {
+                const int end = std::min(start + len, n);
+                i1[nb] = base + start; i2[nb] = base + end - 1; pinned[nb] = end < n; ++nb;
+                start = end;
+                len = 2 * half_len;
+            }
+        }
+        base += n;
+    }
+    return nb;
+}
+
+int dmcmc_set_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2, const int32_t *pinned) {
+    REQUIRE(ctx && i1 && i2 && pinned, "dmcmc_set_layout: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (select_layout(ctx, nblk, i1, i2, pinned)) return -1;
+    if (resize_ll(ctx)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_set_rho(dmcmc_ctx *ctx, const double *rho) {
+    REQUIRE(ctx && rho, "dmcmc_set_rho: bad argument");
+    REQUIRE(ctx->have_grid, "dmcmc_set_rho: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    for (int j = 0; j < ctx->J; ++j)
+        REQUIRE(rho[j] >= 0.0 && rho[j] <= 1.0, "dmcmc_set_rho: rho must lie in [0, 1]");
+    ctx->rho.assign(rho, rho + ctx->J);
+    if (upload(ctx, ctx->d_rho, ctx->rho)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_backward_filter(dmcmc_ctx *ctx, int32_t which) {
+    REQUIRE(ctx && (which == 0 || which == 1), "dmcmc_backward_filter: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (run_backward_filter(ctx, ctx->law_cur ^ which)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_upload_tables(dmcmc_ctx *ctx, int32_t which, const double *H, const double *F0,
+                        const double *Psi, const double *c0, const double *blk_g, const double *blk_Qc) {
+    REQUIRE(ctx && H && F0 && c0 && (which == 0 || which == 1), "dmcmc_upload_tables: bad argument");
+    REQUIRE(ctx->lay_cur >= 0, "dmcmc_upload_tables: no layout set");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    REQUIRE(!lay.has_psi || (Psi && blk_g && blk_Qc), "dmcmc_upload_tables: pinned layout needs Psi, g, Qc");
+    const int slot = ctx->law_cur ^ which;
+    if (ensure_tables_alloc(ctx, lay, slot)) return -1;
+    Tables &tb = lay.tab[slot];
+    const int d = ctx->d, rec = rec_size(d, lay.has_psi);
+    std::vector<double> tab((size_t)ctx->TT * TILE * rec, 0.0);
+    for (int j = 0; j < ctx->J; ++j)
+        for (int k = 0; k < ctx->N[j]; ++k) {
+            const size_t pt = (size_t)ctx->pt_off[j] + k;
+            double *r = &tab[((size_t)ctx->tile_off[j] * TILE + k) * rec];
+            const double dt = ctx->t[pt + 1] - ctx->t[pt];
+            r[0] = dt;
+            r[1] = std::sqrt(dt);
+            int o = 2;
+            for (int i = 0; i < d; ++i)
+                for (int q = i; q < d; ++q) r[o++] = H[pt * d * d + i * d + q];
+            for (int i = 0; i < d; ++i) r[o++] = F0[pt * d + i];
+            if (lay.has_psi)
+                for (int i = 0; i < d * d; ++i) r[o++] = Psi[pt * d * d + i];
+        }
+    std::vector<double> c0b(lay.nblk), g((size_t)lay.nblk * d, 0.0), Qc((size_t)lay.nblk * d * d, 0.0);
+    for (int b = 0; b < lay.nblk; ++b) c0b[b] = c0[ctx->pt_off[lay.i1[b]]];
+    if (blk_g) g.assign(blk_g, blk_g + (size_t)lay.nblk * d);
+    if (blk_Qc) Qc.assign(blk_Qc, blk_Qc + (size_t)lay.nblk * d * d);
+    CK(cudaMemcpy(tb.table.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tb.blk_c0.p, c0b.data(), c0b.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tb.blk_g.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tb.blk_Qc.p, Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tb.ptH.p, H, (size_t)ctx->P * d * d * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tb.ptF0.p, F0, (size_t)ctx->P * d * sizeof(double), cudaMemcpyHostToDevice));
+    if (Psi) CK(cudaMemcpy(tb.ptPsi.p, Psi, (size_t)ctx->P * d * d * sizeof(double), cudaMemcpyHostToDevice));
+    else CK(cudaMemset(tb.ptPsi.p, 0, (size_t)ctx->P * d * d * sizeof(double)));
+    CK(cudaMemcpy(tb.ptc0.p, c0, (size_t)ctx->P * sizeof(double), cudaMemcpyHostToDevice));
+    tb.valid = true;
+    return 0;
+}
+
+int dmcmc_download_tables(dmcmc_ctx *ctx, int32_t which, double *H, double *F0, double *Psi,
+                          double *c0, double *blk_g, double *blk_Qc) {
+    REQUIRE(ctx && (which == 0 || which == 1), "dmcmc_download_tables: bad argument");
+    REQUIRE(ctx->lay_cur >= 0, "dmcmc_download_tables: no layout set");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    Tables &tb = lay.tab[ctx->law_cur ^ which];
+    REQUIRE(tb.valid, "dmcmc_download_tables: tables not computed");
+    if (sync(ctx)) return -1;
+    const size_t d = ctx->d, P = ctx->P;
+    if (H) CK(cudaMemcpy(H, tb.ptH.p, P * d * d * sizeof(double), cudaMemcpyDeviceToHost));
+    if (F0) CK(cudaMemcpy(F0, tb.ptF0.p, P * d * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Psi) CK(cudaMemcpy(Psi, tb.ptPsi.p, P * d * d * sizeof(double), cudaMemcpyDeviceToHost));
+    if (c0) CK(cudaMemcpy(c0, tb.ptc0.p, P * sizeof(double), cudaMemcpyDeviceToHost));
+    if (blk_g) CK(cudaMemcpy(blk_g, tb.blk_g.p, lay.nblk * d * sizeof(double), cudaMemcpyDeviceToHost));
+    if (blk_Qc) CK(cudaMemcpy(blk_Qc, tb.blk_Qc.p, lay.nblk * d * d * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// one PathImputation update; internal form shared by impute / init_paths
+static int impute_once(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E,
+                       bool force_accept, const uint8_t *mask_host, bool zero_rho,
+                       double *out_ll_prop, double *out_ll, uint8_t *out_acc) {
+    SolveParams sp;
+    if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+    if (ensure_unit_buffers(ctx)) return -1;
+    const size_t n = (size_t)ctx->C * sp.nblk;
+    REQUIRE((Z == nullptr) == (E == nullptr) || force_accept, "dmcmc_impute: pass both Z and E, or neither");
+    if (Z) {
+        if (stage_noise(ctx, Z)) return -1;
+        sp.Z = ctx->d_Z.p;
+        if (E) {
+            CK(cudaMemcpyAsync(ctx->d_E.p, E, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CK(cudaMemsetAsync(ctx->d_E.p, 0, n * sizeof(double), ctx->stream));
+        }
+        sp.E = ctx->d_E.p;
+    }
+    if (mask_host) {
+        CK(cudaMemcpyAsync(ctx->d_mask.p, mask_host, n, cudaMemcpyHostToDevice, ctx->stream));
+        sp.unit_mask = ctx->d_mask.p;
+    }
+    DevBuf<double> zero_rho_buf;
+    if (zero_rho) {
+        CK(zero_rho_buf.ensure(ctx->J));
+        CK(cudaMemsetAsync(zero_rho_buf.p, 0, ctx->J * sizeof(double), ctx->stream));
+        sp.rho = zero_rho_buf.p;
+    }
+    sp.iter = iter;
+    sp.force_accept = force_accept;
+    sp.out_llprop = ctx->d_out_llprop.p;
+    sp.out_ll = ctx->d_out_ll.p;
+    sp.out_acc = ctx->d_out_acc.p;
+    if (!force_accept) {
+        sp.acc_count = ctx->d_counts.p;
+        sp.prop_count = ctx->d_counts.p + ctx->J;
+    }
+    if (mask_host) {  // masked-out units keep their previous outputs: clear first
+        CK(cudaMemsetAsync(ctx->d_out_acc.p, 0, n, ctx->stream));
+    }
+    if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
+    ctx->sel_cur ^= 1;
+    if (out_ll_prop) CK(cudaMemcpyAsync(out_ll_prop, ctx->d_out_llprop.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ll) CK(cudaMemcpyAsync(out_ll, ctx->d_out_ll.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_acc) CK(cudaMemcpyAsync(out_acc, ctx->d_out_acc.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    zero_rho_buf.release();
+    return 0;
+}
+
+int dmcmc_init_ll(dmcmc_ctx *ctx) {
+    REQUIRE(ctx, "dmcmc_init_ll: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    SolveParams sp;
+    if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+    if (timed_launch(ctx, MODE_LOGLIK, sp)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_init_paths(dmcmc_ctx *ctx, const double *Z) {
+    REQUIRE(ctx, "dmcmc_init_paths: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    REQUIRE(ctx->lay_cur >= 0, "dmcmc_init_paths: no layout set");
+    const size_t n = (size_t)ctx->C * ctx->layout[ctx->lay_cur].nblk;
+    std::vector<uint8_t> done(n, 0), mask(n, 1), acc(n, 0);
+    // init_paths!: un-preconditioned forward_guide! until success (src/workspaces.jl:86-90)
+    for (int tr = 0; tr < 100; ++tr) {
+        for (size_t i = 0; i < n; ++i) mask[i] = !done[i];
+        if (impute_once(ctx, 0xFFFF0000u + (uint32_t)tr, Z, nullptr, true, mask.data(), true, nullptr, nullptr, acc.data()))
+            return -1;
+        bool all = true;
+        for (size_t i = 0; i < n; ++i) {
+            done[i] = done[i] || (mask[i] && acc[i]);
+            all = all && done[i];
+        }
+        if (all) return dmcmc_init_ll(ctx);
+        REQUIRE(Z == nullptr, "dmcmc_init_paths: the supplied noise leaves the model's domain");
+    }
+    return fail(ctx, "dmcmc_init_paths: no admissible path after 100 tries");
+}
+
+int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E,
+                 double *out_ll_prop, double *out_ll, uint8_t *out_accepted) {
+    REQUIRE(ctx, "dmcmc_impute: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    REQUIRE((Z == nullptr) == (E == nullptr), "dmcmc_impute: pass both Z and E, or neither");
+    return impute_once(ctx, iter, Z, E, false, nullptr, false, out_ll_prop, out_ll, out_accepted);
+}
+
+int dmcmc_run_imputation(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_iters, double *hist_ll_prop,
+                         double *hist_ll, uint8_t *hist_accepted) {
+    REQUIRE(ctx && n_iters >= 0, "dmcmc_run_imputation: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    SolveParams sp;
+    if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+    const size_t n = (size_t)ctx->C * sp.nblk;
+    // device-side history ring so that the D2H copies overlap later sweeps
+    const int ring = 4;
+    DevBuf<double> h_llp, h_ll;
+    DevBuf<uint8_t> h_acc;
+    CK(h_llp.ensure(n * ring));
+    CK(h_ll.ensure(n * ring));
+    CK(h_acc.ensure(n * ring));
+    cudaStream_t cs;
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> done(ring), freed(ring);
+    for (int i = 0; i < ring; ++i) {
+        CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+    }
+    sp.acc_count = ctx->d_counts.p;
+    sp.prop_count = ctx->d_counts.p + ctx->J;
+    for (int it = 0; it < n_iters; ++it) {
+        const int slot = it % ring;
+        if (it >= ring) CK(cudaStreamWaitEvent(ctx->stream, freed[slot], 0));
+        sp.iter = iter0 + (uint32_t)it;
+        sp.selX_in = ctx->d_selX[ctx->sel_cur].p; sp.selW_in = ctx->d_selW[ctx->sel_cur].p;
+        sp.selX_out = ctx->d_selX[1 - ctx->sel_cur].p; sp.selW_out = ctx->d_selW[1 - ctx->sel_cur].p;
+        sp.out_llprop = hist_ll_prop ? h_llp.p + n * slot : nullptr;
+        sp.out_ll = hist_ll ? h_ll.p + n * slot : nullptr;
+        sp.out_acc = hist_accepted ? h_acc.p + n * slot : nullptr;
+        if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
+        ctx->sel_cur ^= 1;
+        CK(cudaEventRecord(done[slot], ctx->stream));
+        CK(cudaStreamWaitEvent(cs, done[slot], 0));
+        if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + n * it, h_llp.p + n * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (hist_ll) CK(cudaMemcpyAsync(hist_ll + n * it, h_ll.p + n * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + n * it, h_acc.p + n * slot, n, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(freed[slot], cs));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(cs));
+    for (int i = 0; i < ring; ++i) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
+    cudaStreamDestroy(cs);
+    h_llp.release(); h_ll.release(); h_acc.release();
+    return 0;
+}
+
+int dmcmc_relayout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2, const int32_t *pinned) {
+    REQUIRE(ctx && i1 && i2 && pinned, "dmcmc_relayout: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (select_layout(ctx, nblk, i1, i2, pinned)) return -1;
+    if (resize_ll(ctx)) return -1;
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    if (!lay.tab[ctx->law_cur].valid && run_backward_filter(ctx, ctx->law_cur)) return -1;
+    SolveParams sp;
+    if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+    if (timed_launch(ctx, MODE_RELAYOUT, sp)) return -1;
+    return sync(ctx);
+}
+
+int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical,
+                       double *out_ll_prop, uint8_t *out_success) {
+    REQUIRE(ctx && theta_prop, "dmcmc_param_loglik: bad argument");
+    REQUIRE(ntheta == ctx->nth, "dmcmc_param_loglik: wrong number of parameters for this model");
+    REQUIRE(ctx->lay_cur >= 0, "dmcmc_param_loglik: no layout set");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int cur = ctx->law_cur, prop = cur ^ 1;
+    Law &lp = ctx->law[prop];
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    std::copy(theta_prop, theta_prop + ntheta, lp.theta);
+    lp.have_theta = true;
+    if (critical) {
+        // critical_change && backward_filter!(ws deg.P[i])  (src/run!_alterations.jl:199-204)
+        lp.custom_aux = false;
+        if (build_aux(ctx, prop)) return -1;
+        if (run_backward_filter(ctx, prop)) return -1;
+    } else {
+        // non-critical: aux law and tables are those of the current law
+        Law &lc = ctx->law[cur];
+        lp.auxB = lc.auxB; lp.auxbeta = lc.auxbeta; lp.auxsig = lc.auxsig; lp.custom_aux = lc.custom_aux;
+        if (build_aux(ctx, prop)) return -1;
+        Tables &tc = lay.tab[cur], &tp = lay.tab[prop];
+        REQUIRE(tc.valid, "dmcmc_param_loglik: current tables missing");
+        if (ensure_tables_alloc(ctx, lay, prop)) return -1;
+        auto cp = [&](DevBuf<double> &dst, DevBuf<double> &src) {
+            return cudaMemcpyAsync(dst.p, src.p, src.bytes(), cudaMemcpyDeviceToDevice, ctx->stream);
+        };
+        CK(cp(tp.table, tc.table)); CK(cp(tp.blk_c0, tc.blk_c0)); CK(cp(tp.blk_g, tc.blk_g));
+        CK(cp(tp.blk_Qc, tc.blk_Qc)); CK(cp(tp.ptH, tc.ptH)); CK(cp(tp.ptF0, tc.ptF0));
+        CK(cp(tp.ptPsi, tc.ptPsi)); CK(cp(tp.ptc0, tc.ptc0));
+        tp.valid = true;
+    }
+    SolveParams sp;
+    if (fill_params(ctx, sp, prop)) return -1;
+    if (ensure_unit_buffers(ctx)) return -1;
+    const size_t n = (size_t)ctx->C * sp.nblk;
+    CK(ctx->d_param_llprop.ensure(n));
+    sp.out_llprop = ctx->d_param_llprop.p;
+    sp.out_acc = ctx->d_out_acc.p;
+    if (timed_launch(ctx, MODE_PARAM, sp)) return -1;
+    ctx->h_param_llprop.resize(n);
+    std::vector<uint8_t> okb(n);
+    CK(cudaMemcpyAsync(ctx->h_param_llprop.data(), ctx->d_param_llprop.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(okb.data(), ctx->d_out_acc.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    if (out_ll_prop) std::copy(ctx->h_param_llprop.begin(), ctx->h_param_llprop.end(), out_ll_prop);
+    if (out_success)
+        for (int c = 0; c < ctx->C; ++c) {
+            uint8_t ok = 1;
+            for (int b = 0; b < sp.nblk; ++b) ok &= okb[(size_t)c * sp.nblk + b];
+            out_success[c] = ok;
+        }
+    ctx->param_pending = true;
+    return 0;
+}
+
+__global__ void flip_sel_kernel(uint8_t *sel, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sel[i] ^= 1;
+}
+
+int dmcmc_param_commit(dmcmc_ctx *ctx, int32_t accepted) {
+    REQUIRE(ctx, "dmcmc_param_commit: null context");
+    REQUIRE(ctx->param_pending, "dmcmc_param_commit: no pending dmcmc_param_loglik");
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->param_pending = false;
+    if (!accepted) return 0;
+    // swap_laws_and_paths!: P deg <-> P, XX deg <-> XX, W kept  (src/run!_alterations.jl:328-334)
+    const size_t n = (size_t)ctx->J * ctx->C;
+    flip_sel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_selX[ctx->sel_cur].p, n);
+    CK(cudaGetLastError());
+    ctx->law_cur ^= 1;
+    const size_t nu = (size_t)ctx->C * ctx->layout[ctx->lay_cur].nblk;
+    CK(cudaMemcpyAsync(ctx->d_ll.p, ctx->d_param_llprop.p, nu * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    // tables of the other layout slot belong to the old law now
+    for (int s = 0; s < 2; ++s)
+        if (s != ctx->lay_cur) ctx->layout[s].tab[ctx->law_cur].valid = false;
+    return sync(ctx);
+}
+
+int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W) {
+    REQUIRE(ctx && X && W && (which == 0 || which == 1), "dmcmc_download_state: bad argument");
+    REQUIRE(ctx->lay_cur >= 0 && ctx->have_start, "dmcmc_download_state: context not initialised");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    DevBuf<double> oX, oW;
+    const size_t nX = (size_t)ctx->C * ctx->P * ctx->d, nW = (size_t)ctx->C * ctx->P * ctx->m;
+    CK(oX.ensure(nX));
+    CK(oW.ensure(nW));
+    GatherParams g{};
+    g.C = ctx->C; g.J = ctx->J; g.D = ctx->d; g.M = ctx->m; g.TT = ctx->TT; g.P = ctx->P;
+    g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_first = ctx->d_first.p;
+    g.iv_rec = ctx->d_rec.p; g.iv_pt_off = ctx->d_pt_off.p; g.iv_blk = lay.d_iv_blk.p;
+    g.blk_i1 = lay.d_i1.p;
+    for (int b = 0; b < 2; ++b) { g.X[b] = ctx->d_X[b].p; g.W[b] = ctx->d_W[b].p; }
+    g.selX = ctx->d_selX[ctx->sel_cur].p; g.selW = ctx->d_selW[ctx->sel_cur].p;
+    g.x0 = ctx->d_x0.p; g.which = which; g.outX = oX.p; g.outW = oW.p;
+    CK(launch_gather(g, ctx->stream));
+    CK(cudaMemcpyAsync(X, oX.p, nX * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(W, oW.p, nW * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    oX.release();
+    oW.release();
+    return 0;
+}
+
+int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_out) {
+    REQUIRE(ctx && x_out, "dmcmc_download_path: bad argument");
+    REQUIRE(chain >= 0 && chain < ctx->C && rec >= 0 && rec < ctx->R, "dmcmc_download_path: index out of range");
+    // glue: every interval's points but the last, then the final end point
+    // (_copy_path!, src/path_saving_buffer.jl:54-64)
+    std::vector<double> X((size_t)ctx->C * ctx->P * ctx->d), W((size_t)ctx->C * ctx->P * ctx->m);
+    if (dmcmc_download_state(ctx, 0, X.data(), W.data())) return -1;
+    int j0 = 0;
+    for (int r = 0; r < rec; ++r) j0 += ctx->rec_nobs[r];
+    const int j1 = j0 + ctx->rec_nobs[rec] - 1, d = ctx->d;
+    size_t off = 0;
+    for (int j = j0; j <= j1; ++j) {
+        const double *src = &X[((size_t)chain * ctx->P + ctx->pt_off[j]) * d];
+        std::copy(src, src + (size_t)ctx->N[j] * d, x_out + off * d);
+        off += ctx->N[j];
+    }
+    const double *last = &X[((size_t)chain * ctx->P + ctx->pt_off[j1] + ctx->N[j1]) * d];
+    std::copy(last, last + d, x_out + off * d);
+    return 0;
+}
+
+int dmcmc_get_ll(dmcmc_ctx *ctx, double *ll) {
+    REQUIRE(ctx && ll && ctx->lay_cur >= 0, "dmcmc_get_ll: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (sync(ctx)) return -1;
+    CK(cudaMemcpy(ll, ctx->d_ll.p, (size_t)ctx->C * ctx->layout[ctx->lay_cur].nblk * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll) {
+    REQUIRE(ctx && ll && ctx->lay_cur >= 0, "dmcmc_set_ll: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaMemcpy(ctx->d_ll.p, ll, (size_t)ctx->C * ctx->layout[ctx->lay_cur].nblk * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted, int64_t *proposed) {
+    REQUIRE(ctx && ctx->lay_cur >= 0, "dmcmc_accept_counts: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (sync(ctx)) return -1;
+    std::vector<unsigned long long> h((size_t)2 * ctx->J);
+    CK(cudaMemcpy(h.data(), ctx->d_counts.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const int nblk = ctx->layout[ctx->lay_cur].nblk;
+    for (int b = 0; b < nblk; ++b) {
+        if (accepted) accepted[b] = (int64_t)h[b];
+        if (proposed) proposed[b] = (int64_t)h[ctx->J + b];
+    }
+    CK(cudaMemset(ctx->d_counts.p, 0, ctx->d_counts.bytes()));
+    return 0;
+}
+
+int dmcmc_last_kernel_ms(dmcmc_ctx *ctx, double *ms, int64_t *launches) {
+    REQUIRE(ctx, "dmcmc_last_kernel_ms: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (sync(ctx)) return -1;
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float f = 0.f;
+        CK(cudaEventElapsedTime(&f, ctx->ev[i], ctx->ev[i + 1]));
+        tot += f;
+    }
+    if (ms) *ms = tot;
+    if (launches) *launches = (int64_t)(ctx->ev_used / 2);
+    ctx->ev_used = 0;
+    return 0;
+}
+
+int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t b = 0;
+    for (int i = 0; i < 2; ++i)
+        b += ctx->d_X[i].bytes() + ctx->d_W[i].bytes() + ctx->d_selX[i].bytes() + ctx->d_selW[i].bytes();
+    for (auto &l : ctx->layout)
+        for (auto &t : l.tab) b += t.table.bytes() + t.ptH.bytes() + t.ptF0.bytes() + t.ptPsi.bytes() + t.ptc0.bytes();
+    b += ctx->d_Z.bytes() + ctx->d_ll.bytes();
+    return b;
+}
+
+}  // extern "C"

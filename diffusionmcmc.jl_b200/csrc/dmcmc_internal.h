@@ -1,0 +1,99 @@
+// dmcmc_internal.h -- structures shared by the C-ABI layer (dmcmc_capi.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "dmcmc_models.cuh"
+
+namespace dmcmc {
+
+enum SolveMode {
+    MODE_IMPUTE = 0,    // a1-a7: pCN refresh + guided solve + ll + accept/swap
+    MODE_PARAM = 1,     // a9: solve with the fixed accepted noise under the proposal law
+    MODE_RELAYOUT = 2,  // layout switch: recover dW from the accepted X, recompute ll
+    MODE_LOGLIK = 3     // init_ll!: ll of the accepted path only
+};
+
+// Everything a solve kernel needs.  Pointers are device pointers.
+struct SolveParams {
+    int32_t C, nblk, J;
+    int32_t chain_offset;
+    int64_t TT;  // total tiles over all intervals
+    // layout
+    const int32_t *blk_i1, *blk_i2, *blk_pinned;
+    // intervals
+    const int32_t *iv_N, *iv_tile_off, *iv_first, *iv_rec;
+    const double *rho;      // [J]
+    const double *auxB;     // [J][D*D]
+    const double *auxbeta;  // [J][D]
+    const double *auxatil;  // [J][D*D]
+    // tables of the law the kernel solves under
+    const double *table;    // [TT*8][REC]
+    const double *blk_c0;   // [nblk] c0 at the block's first grid point
+    const double *blk_g;    // [nblk][D]
+    const double *blk_Qc;   // [nblk][D*D]
+    int32_t has_psi;
+    // state
+    double *X[2];           // [D][TT][C][8]
+    double *W[2];           // [M][TT][C][8]
+    // accepted-container selectors [J][C]: read from *_in, written (flipped on accept) to *_out;
+    // the two arrays are swapped by the host after the sweep, so no unit ever reads a selector
+    // that a neighbouring block's unit is flipping.
+    const uint8_t *selX_in, *selW_in;
+    uint8_t *selX_out, *selW_out;
+    const double *x0;       // [R][D][C]
+    double *ll;             // [C][nblk]
+    // noise
+    const double *Z;        // [M][TT][C][8] explicit normals or nullptr (Philox)
+    const double *E;        // [C][nblk] explicit Exp(1) or nullptr
+    uint64_t seed;
+    uint32_t iter;
+    int32_t force_accept;
+    const uint8_t *unit_mask;  // [C][nblk] or nullptr
+    // outputs
+    double *out_llprop, *out_ll;  // [C][nblk]
+    uint8_t *out_acc;             // [C][nblk]  (MODE_PARAM: per-unit success)
+    unsigned long long *acc_count, *prop_count;  // [nblk]
+    Theta th;
+};
+
+// launchers (dmcmc_solve.cu); return the CUDA error of the launch
+cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s);
+
+// state gather for read-outs (dmcmc_solve.cu)
+struct GatherParams {
+    int32_t C, J, D, M;
+    int64_t TT;
+    const int32_t *iv_N, *iv_tile_off, *iv_first, *iv_rec, *iv_pt_off, *iv_blk;
+    const int32_t *blk_i1;
+    const double *X[2], *W[2];
+    const uint8_t *selX, *selW;
+    const double *x0;
+    int32_t which;  // 0 accepted, 1 proposal
+    double *outX;   // [C][P][D]
+    double *outW;   // [C][P][M]
+    int64_t P;
+};
+cudaError_t launch_gather(const GatherParams &g, cudaStream_t s);
+
+// noise transposition [C][S][M] -> [M][TT][C][8] is done on the host in the C-ABI layer.
+
+// backward filter (dmcmc_bf.cu)
+struct BFParams {
+    int32_t D, J, nblk;
+    const int32_t *blk_i1, *blk_i2, *blk_pinned;
+    const int32_t *iv_N, *iv_tile_off, *iv_pt_off;
+    const double *t;        // [P]
+    const double *auxB, *auxbeta, *auxatil;
+    const double *Hobs;     // [J][D*D]
+    const double *Fobs;     // [J][D]
+    const double *cobs;     // [J]
+    double pin_eps;
+    int32_t has_psi, rec;
+    double *table;          // [TT*8][rec]
+    double *ptH, *ptF0, *ptPsi, *ptc0;  // per-grid-point copies (download / parity), may be null
+    double *blk_c0, *blk_g, *blk_Qc;
+};
+cudaError_t launch_backward_filter(const BFParams &b, cudaStream_t s);
+
+}  // namespace dmcmc

@@ -1,0 +1,212 @@
+"""NumPy-facing wrapper of the C ABI (include/dmcmc.h): one `Engine` = one `dmcmc_ctx` = the
+device-resident replacement of the reference's `DiffusionGlobalSubworkspace` pair
+(`sub_ws_diff`, `sub_ws_diff°`; /root/reference src/workspaces.jl:49-72, :119-127): accepted and
+proposal containers of X and W for every chain, the guided-proposal laws and their
+backward-filter tables.
+
+Everything numerical happens in libdmcmc_b200.so on the GPU; this class only marshals arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .problems import chequerboard_layout
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_lib._dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_lib._ip)
+
+
+def _bp(a):
+    return None if a is None else a.ctypes.data_as(_lib._bp)
+
+
+class DmcmcError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, spec, device=0, seed=0, chain_offset=0, n_chains=None):
+        self.lib = _lib.load()
+        self.spec = spec
+        self.model, self.d, self.m = int(spec["model"]), int(spec["d"]), int(spec["m"])
+        x0 = _f64(spec["x0"])
+        if n_chains is not None:
+            x0 = x0[chain_offset:chain_offset + n_chains] if x0.shape[0] >= chain_offset + n_chains \
+                else np.broadcast_to(x0[:1], (n_chains,) + x0.shape[1:]).copy()
+        self.C = x0.shape[0]
+        cfg = _lib.Config(_lib.ABI_VERSION, self.model, self.d, self.C, chain_offset, device,
+                          seed, float(spec.get("pin_eps", 1e-4)))
+        h = C.c_void_p()
+        if self.lib.dmcmc_create(C.byref(cfg), C.byref(h)) != 0:
+            raise DmcmcError(self.lib.dmcmc_last_error(None).decode())
+        self.h = h
+        self.N = _i32(spec["N"])
+        self.J = len(self.N)
+        self.pt_off = np.concatenate([[0], np.cumsum(self.N + 1)]).astype(np.int64)
+        self.st_off = np.concatenate([[0], np.cumsum(self.N)]).astype(np.int64)
+        self.P, self.S = int(self.pt_off[-1]), int(self.st_off[-1])
+        rec_first = _i32(spec["rec_first"])
+        self.rec_nobs = _i32(np.diff(np.concatenate([np.flatnonzero(rec_first), [self.J]])))
+        self.R = len(self.rec_nobs)
+        t = _f64(spec["t"])
+        self._ck(self.lib.dmcmc_set_grid(self.h, self.R, _ip(self.rec_nobs), _ip(self.N), _dp(t)))
+        L, Sg, v = _f64(spec["obs_L"]), _f64(spec["obs_Sigma"]), _f64(spec["obs_v"])
+        self.p = L.shape[1]
+        self._ck(self.lib.dmcmc_set_obs(self.h, self.p, _dp(L), _dp(Sg), _dp(v)))
+        self._ck(self.lib.dmcmc_set_start(self.h, _dp(x0)))
+        self.set_theta(spec["theta"])
+        self.set_rho(np.broadcast_to(spec["rho"], (self.J,)))
+        self.set_layout(*chequerboard_layout(self.rec_nobs, 0, 0))
+        self.backward_filter()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise DmcmcError(self.lib.dmcmc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dmcmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- problem ----------------------------------------------------------------------------
+    def set_theta(self, theta):
+        th = _f64(theta)
+        self._ck(self.lib.dmcmc_set_theta(self.h, _dp(th), len(th)))
+        self.theta = th
+
+    def set_aux(self, B, beta, sig, which=0):
+        B, beta, sig = _f64(B), _f64(beta), _f64(sig)
+        self._ck(self.lib.dmcmc_set_aux(self.h, which, _dp(B), _dp(beta), _dp(sig)))
+
+    def set_rho(self, rho):
+        rho = _f64(rho)
+        self._ck(self.lib.dmcmc_set_rho(self.h, _dp(rho)))
+        self.rho = rho
+
+    def set_layout(self, i1, i2, pinned):
+        self.blk_i1, self.blk_i2, self.blk_pinned = _i32(i1), _i32(i2), _i32(pinned)
+        self.nblk = len(self.blk_i1)
+        self._ck(self.lib.dmcmc_set_layout(self.h, self.nblk, _ip(self.blk_i1), _ip(self.blk_i2),
+                                           _ip(self.blk_pinned)))
+
+    def relayout(self, i1, i2, pinned):
+        self.blk_i1, self.blk_i2, self.blk_pinned = _i32(i1), _i32(i2), _i32(pinned)
+        self.nblk = len(self.blk_i1)
+        self._ck(self.lib.dmcmc_relayout(self.h, self.nblk, _ip(self.blk_i1), _ip(self.blk_i2),
+                                         _ip(self.blk_pinned)))
+
+    def backward_filter(self, which=0):
+        self._ck(self.lib.dmcmc_backward_filter(self.h, which))
+
+    def upload_tables(self, H, F0, Psi, c0, blk_g=None, blk_Qc=None, which=0):
+        H, F0, c0 = _f64(H), _f64(F0), _f64(c0)
+        Psi = None if Psi is None else _f64(Psi)
+        blk_g = None if blk_g is None else _f64(blk_g)
+        blk_Qc = None if blk_Qc is None else _f64(blk_Qc)
+        self._ck(self.lib.dmcmc_upload_tables(self.h, which, _dp(H), _dp(F0), _dp(Psi), _dp(c0),
+                                              _dp(blk_g), _dp(blk_Qc)))
+
+    def download_tables(self, which=0):
+        d, P, nb = self.d, self.P, self.nblk
+        H, F0, Psi = np.zeros((P, d, d)), np.zeros((P, d)), np.zeros((P, d, d))
+        c0, g, Qc = np.zeros(P), np.zeros((nb, d)), np.zeros((nb, d, d))
+        self._ck(self.lib.dmcmc_download_tables(self.h, which, _dp(H), _dp(F0), _dp(Psi), _dp(c0),
+                                                _dp(g), _dp(Qc)))
+        return dict(H=H, F0=F0, Psi=Psi, c0=c0, blk_g=g, blk_Qc=Qc)
+
+    # -- updates ----------------------------------------------------------------------------
+    def init_paths(self, Z=None):
+        Z = None if Z is None else _f64(Z)
+        self._ck(self.lib.dmcmc_init_paths(self.h, _dp(Z)))
+
+    def init_ll(self):
+        self._ck(self.lib.dmcmc_init_ll(self.h))
+
+    def impute(self, it=0, Z=None, E=None, want=True):
+        n = (self.C, self.nblk)
+        llp = np.empty(n) if want else None
+        ll = np.empty(n) if want else None
+        acc = np.empty(n, np.uint8) if want else None
+        if Z is not None:
+            Z, E = _f64(Z), _f64(E)
+            assert Z.shape == (self.C, self.S, self.m) and E.shape == n
+        self._ck(self.lib.dmcmc_impute(self.h, it, _dp(Z), _dp(E), _dp(llp), _dp(ll), _bp(acc)))
+        if want:
+            return llp, ll, acc.astype(bool)
+
+    def run_imputation(self, it0, n_iters, histories=True):
+        n = (n_iters, self.C, self.nblk)
+        if histories:
+            llp, ll, acc = np.empty(n), np.empty(n), np.empty(n, np.uint8)
+        else:
+            llp = ll = acc = None
+        self._ck(self.lib.dmcmc_run_imputation(self.h, it0, n_iters, _dp(llp), _dp(ll), _bp(acc)))
+        return llp, ll, acc
+
+    def param_loglik(self, theta_prop, critical=True):
+        th = _f64(theta_prop)
+        llp = np.empty((self.C, self.nblk))
+        ok = np.empty(self.C, np.uint8)
+        self._ck(self.lib.dmcmc_param_loglik(self.h, _dp(th), len(th), int(critical), _dp(llp), _bp(ok)))
+        return llp, ok.astype(bool)
+
+    def param_commit(self, accepted):
+        self._ck(self.lib.dmcmc_param_commit(self.h, int(bool(accepted))))
+
+    # -- read-outs --------------------------------------------------------------------------
+    def download_state(self, which=0):
+        X = np.empty((self.C, self.P, self.d))
+        W = np.empty((self.C, self.P, self.m))
+        self._ck(self.lib.dmcmc_download_state(self.h, which, _dp(X), _dp(W)))
+        return X, W
+
+    def download_path(self, chain, rec=0):
+        j0 = int(self.rec_nobs[:rec].sum())
+        npts = int(self.N[j0:j0 + self.rec_nobs[rec]].sum()) + 1
+        out = np.empty((npts, self.d))
+        self._ck(self.lib.dmcmc_download_path(self.h, chain, rec, _dp(out)))
+        return out
+
+    def get_ll(self):
+        ll = np.empty((self.C, self.nblk))
+        self._ck(self.lib.dmcmc_get_ll(self.h, _dp(ll)))
+        return ll
+
+    def set_ll(self, ll):
+        ll = _f64(ll)
+        assert ll.shape == (self.C, self.nblk)
+        self._ck(self.lib.dmcmc_set_ll(self.h, _dp(ll)))
+
+    def accept_counts(self):
+        a, p = np.zeros(self.nblk, np.int64), np.zeros(self.nblk, np.int64)
+        self._ck(self.lib.dmcmc_accept_counts(self.h, a.ctypes.data_as(_lib._lp), p.ctypes.data_as(_lib._lp)))
+        return a, p
+
+    def kernel_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.lib.dmcmc_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def device_bytes(self):
+        return int(self.lib.dmcmc_device_bytes(self.h))

@@ -1,0 +1,158 @@
+/*
+ * dmcmc.h -- C ABI of the B200-native path-imputation backend (libdmcmc_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of JuliaDiffusionBayes/DiffusionMCMC.jl: every entry point
+ * below is what the reference's Julia methods for that path would `ccall` instead of calling
+ * GuidedProposals.jl / DiffusionDefinition.jl.  File:line citations are relative to the
+ * reference checkout (/root/reference).  Plain pointers and sizes only; the caller owns every
+ * host buffer, the library copies in/out before returning unless stated otherwise; device
+ * memory is owned by the context.  All floating point is IEEE binary64.
+ *
+ * Return value: 0 on success, <0 on error (text via dmcmc_last_error).  A path that leaves the
+ * model's domain is NOT an error: it reports success = 0 and ll = -Inf for that (chain, block),
+ * mirroring the `(success, ll)` tuples at src/run!_alterations.jl:18 and :206-209.
+ *
+ * Index conventions: intervals are the inter-observation intervals of all recordings
+ * concatenated (0-based); interval j ends at observation j.  A layout block is an inclusive
+ * range [i1, i2] of intervals of one recording -- the `(rec_idx, obs_range)` tuples of
+ * src/schedule.jl:97-100.  Chains are a batch axis that the reference does not have
+ * (SURVEY.md section 0): every chain owns a full copy of the path/noise state.
+ */
+#ifndef DMCMC_H
+#define DMCMC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMCMC_ABI_VERSION 1
+
+/* Built-in diffusion laws (DiffusionDefinition.jl `@load_diffusion`, src/DiffusionMCMC.jl:4). */
+enum dmcmc_model {
+    DMCMC_MODEL_FHN = 0,  /* FitzHugh-Nagumo           d=2  m=1  theta=(eps,s,gamma,beta,sigma)        */
+    DMCMC_MODEL_LV = 1,   /* Lotka-Volterra            d=2  m=2  theta=(alpha,beta,gamma,delta,s1,s2)  */
+    DMCMC_MODEL_L63 = 2,  /* Lorenz-63                 d=3  m=3  theta=(th1,th2,th3,sigma)             */
+    DMCMC_MODEL_L96 = 3,  /* Lorenz-96                 d=40 m=40 theta=(F,sigma,c_aux)                 */
+    DMCMC_MODEL_LIN2 = 4, /* linear 2-d (analytic KAT) d=2  m=2  theta=(B00,B01,B10,B11,b0,b1,s0,s1)   */
+    DMCMC_MODEL_LVM = 5   /* Lotka-Volterra, multiplicative noise (state-dependent sigma)              */
+};
+
+typedef struct dmcmc_ctx dmcmc_ctx;
+
+typedef struct {
+    int32_t abi_version;   /* DMCMC_ABI_VERSION                                                    */
+    int32_t model;         /* enum dmcmc_model                                                     */
+    int32_t d;             /* state dimension (fixed by the model except L96)                      */
+    int32_t n_chains;      /* chains held by THIS context (one context per GPU)                    */
+    int32_t chain_offset;  /* global index of local chain 0 (Philox streams are per global chain,  */
+                           /* so results do not depend on how chains are sharded over GPUs)        */
+    int32_t device;        /* CUDA device ordinal                                                  */
+    uint64_t seed;         /* Philox key                                                           */
+    double pin_eps;        /* variance of the (almost exact) end-point observation of pinned blocks */
+} dmcmc_config;
+
+/* -- lifetime -------------------------------------------------------------------------------- */
+int dmcmc_create(const dmcmc_config *cfg, dmcmc_ctx **out);
+void dmcmc_destroy(dmcmc_ctx *ctx);
+const char *dmcmc_last_error(const dmcmc_ctx *ctx); /* ctx may be NULL: last create() error */
+
+/* -- problem definition (replaces DiffusionGlobalSubworkspace's constructor inputs,
+ *    src/workspaces.jl:55-71, :164-170) ------------------------------------------------------ */
+/* Imputation grids from OBS.setup_time_grids: n_steps[j] Euler steps in interval j and the
+ * n_steps[j]+1 grid times of each interval concatenated in t. */
+int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs,
+                   const int32_t *n_steps, const double *t);
+/* Linear-Gaussian observations v_j ~ N(L_j x, Sigma_j) at the right end of interval j
+ * (LinearGsnObs, docs/src/tutorials/simple_inference.md:52-60).  L [J][p][d], Sigma [J][p][p],
+ * v [J][p]. */
+int dmcmc_set_obs(dmcmc_ctx *ctx, int32_t p, const double *L, const double *Sigma,
+                  const double *v);
+/* Known starting points (KnownStartingPt), x0 [n_chains][n_recordings][d]. */
+int dmcmc_set_start(dmcmc_ctx *ctx, const double *x0);
+/* Parameters of the CURRENT law; rebuilds the built-in auxiliary laws (DD.set_parameters!). */
+int dmcmc_set_theta(dmcmc_ctx *ctx, const double *theta, int32_t ntheta);
+/* Optional user-supplied auxiliary law, constant on each interval: B [J][d][d], beta [J][d],
+ * sigma_aux [J][d][m].  which: 0 = current law, 1 = proposal law. */
+int dmcmc_set_aux(dmcmc_ctx *ctx, int32_t which, const double *B, const double *beta,
+                  const double *sigma_aux);
+/* Block layout of the update about to run (src/workspaces.jl:242-261).  pinned[b] = 1 when the
+ * block's right end is conditioned on the current path value (blocking). */
+int dmcmc_set_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
+                     const int32_t *pinned);
+/* Chequerboard layout helper for BlockingChequerboardSwitch(block_half_len), src/blocking.jl:7-9.
+ * pattern 0: delimiters at multiples of 2h; pattern 1: shifted by h.  half_len <= 0: no
+ * blocking (src/schedule.jl:97-100).  Arrays must hold n_intervals entries; returns nblk. */
+int dmcmc_chequerboard_layout(int32_t n_recordings, const int32_t *rec_nobs, int32_t half_len,
+                              int32_t pattern, int32_t *i1, int32_t *i2, int32_t *pinned);
+/* pCN memory per interval, update.rho_s[i][j] (src/updates.jl:53-74). */
+int dmcmc_set_rho(dmcmc_ctx *ctx, const double *rho);
+
+/* -- a8: backward filter (backward_filter!, src/run!_alterations.jl:203;
+ *    recompute_guiding_term!, src/workspaces.jl:428) ------------------------------------------ */
+/* Device kernel: H, F, c tables of law `which` (0 current, 1 proposal) for the current layout. */
+int dmcmc_backward_filter(dmcmc_ctx *ctx, int32_t which);
+/* Host-computed tables instead (bit-exact inputs for parity runs).  Per grid point (N_j+1 per
+ * interval): H [P][d][d], F0 [P][d], Psi [P][d][d] (may be NULL when no block is pinned),
+ * c0 [P]; per block: g [nblk][d], Qc [nblk][d][d] (may be NULL likewise). */
+int dmcmc_upload_tables(dmcmc_ctx *ctx, int32_t which, const double *H, const double *F0,
+                        const double *Psi, const double *c0, const double *blk_g,
+                        const double *blk_Qc);
+int dmcmc_download_tables(dmcmc_ctx *ctx, int32_t which, double *H, double *F0, double *Psi,
+                          double *c0, double *blk_g, double *blk_Qc);
+
+/* -- a13: init_paths! + init_ll! (src/workspaces.jl:80-92, :425-431) -------------------------- */
+/* Z [n_chains][S][m] explicit standard normals (S = total steps) or NULL for Philox noise. */
+int dmcmc_init_paths(dmcmc_ctx *ctx, const double *Z);
+int dmcmc_init_ll(dmcmc_ctx *ctx);
+
+/* -- a1-a7: one eMCMC.update!(::PathImputation) (src/run!_alterations.jl:5-26, :36-91) over every
+ *    (chain, block): pCN refresh, guided Euler-Maruyama solve, Girsanov ll, accept, swap.
+ *    Parity mode: Z [n_chains][S][m], E [n_chains][nblk] (Exp(1) draws).  Production mode:
+ *    Z = E = NULL, noise = Philox4x32-10(seed; iter, interval, global chain, step).
+ *    Outputs (may be NULL) are the history rows of src/run!_alterations.jl:65-74, shape
+ *    [n_chains][nblk]. -------------------------------------------------------------------------- */
+int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E,
+                 double *out_ll_prop, double *out_ll, uint8_t *out_accepted);
+
+/* Production loop: n_iters consecutive updates with Philox noise starting at iteration iter0,
+ * alternating between the given layouts when n_layouts = 2 (chequerboard); histories
+ * [n_iters][n_chains][nblk_max] are copied to the host asynchronously while later iterations run.
+ * Any output may be NULL. */
+int dmcmc_run_imputation(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_iters, double *hist_ll_prop,
+                         double *hist_ll, uint8_t *hist_accepted);
+
+/* -- layout switch (change_laws_for_blocking! + recompute_loglikhd!, called but undefined in the
+ *    reference: src/workspaces.jl:469-470): new tables, Wiener re-inversion, ll recompute. ------ */
+int dmcmc_relayout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
+                   const int32_t *pinned);
+
+/* -- a9: parameter step (set_proposal!, src/run!_alterations.jl:177-211; swap_laws_and_paths!,
+ *    :328-334).  theta_prop -> proposal law; critical != 0 re-runs the backward filter; solve
+ *    with the FIXED accepted Wiener paths.  out_ll_prop [n_chains][nblk], out_success [n_chains]. */
+int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical,
+                       double *out_ll_prop, uint8_t *out_success);
+int dmcmc_param_commit(dmcmc_ctx *ctx, int32_t accepted);
+
+/* -- read-outs -------------------------------------------------------------------------------- */
+/* a12: accepted path of one chain/recording glued as _copy_path! does
+ * (src/path_saving_buffer.jl:54-64): x_out [(sum_j N_j)+1][d]. */
+int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_out);
+/* Full containers in the reference's per-interval shape (N_j+1 points per interval, duplicated
+ * joins): X [n_chains][P][d], W [n_chains][P][m] cumulative.  which: 0 accepted, 1 proposal. */
+int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W);
+int dmcmc_get_ll(dmcmc_ctx *ctx, double *ll /* [n_chains][nblk] */);
+int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll);
+/* Device-side accept counters per block since the last call (src/adaptation.jl:100-103). */
+int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted /* [nblk] */, int64_t *proposed);
+
+/* -- measurement helpers (bench.py) ----------------------------------------------------------- */
+/* Average device time in ms of the last `dmcmc_impute`/`dmcmc_run_imputation` kernels, measured
+ * with CUDA events on the context's stream. */
+int dmcmc_last_kernel_ms(dmcmc_ctx *ctx, double *ms, int64_t *launches);
+int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMCMC_H */

@@ -1,0 +1,230 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerance: 1e-10 relative (north_star) on imputed paths, Wiener paths and
+per-block log-likelihoods; accept decisions identical except ties within that tolerance."""
+import numpy as np
+import pytest
+
+from helpers import RTOL, accept_mismatch_is_tie, close, interior_mask, maxrel
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(pkg, name, **kw):
+    P = pkg.problems
+    return {"fhn": P.fhn_spec, "lv": P.lv_spec, "l63": P.l63_spec, "lin2": P.lin2_spec,
+            "lvm": lambda **k: P.lv_spec(multiplicative=True, **k)}[name](**kw)
+
+
+def _pair(pkg, orc, spec, upload=True):
+    from diffusionmcmc_jl_b200.engine import Engine
+    o = orc.Oracle(spec)
+    e = Engine(spec)
+    if upload:
+        e.upload_tables(o.H, o.F0, None, o.c0)
+    return o, e
+
+
+def _compare_state(o, e, which, what=""):
+    Xg, Wg = e.download_state(which)
+    Xo = o.accepted_X() if which == 0 else o.proposal_X()
+    Wo = o.accepted_W() if which == 0 else o.proposal_W()
+    im = interior_mask(o.N)
+    assert close(Xg[:, im], Xo[:, im]), f"{what} X[{which}] maxrel {maxrel(Xg[:, im], Xo[:, im])}"
+    assert close(Wg[:, im], Wo[:, im]), f"{what} W[{which}] maxrel {maxrel(Wg[:, im], Wo[:, im])}"
+
+
+CASES = [
+    ("fhn", dict(n_obs=6, C=37, dt=0.01)),      # ragged chain count, N=10 -> partial tiles
+    ("fhn", dict(n_obs=3, C=5, dt=0.004)),      # N=25: 3 full tiles + 1 step
+    ("lv", dict(n_obs=5, C=33, dt=0.01)),
+    ("l63", dict(n_obs=7, C=9, dt=1e-3)),
+    ("lin2", dict(n_obs=4, C=3, dt=0.01)),
+    ("lvm", dict(n_obs=5, C=8, dt=0.005)),
+]
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_impute_parity_explicit_noise(pkg, orc, name, kw):
+    spec = _mk(pkg, name, **kw)
+    o, e = _pair(pkg, orc, spec)
+    rng = np.random.default_rng(123)
+    Z0 = rng.standard_normal((o.C, o.S, o.m)) * (0.2 if name in ("lv", "lvm") else 1.0)
+    o.init_paths(Z=Z0)
+    e.init_paths(Z=Z0)
+    assert close(e.get_ll(), o.ll), f"init ll maxrel {maxrel(e.get_ll(), o.ll)}"
+    _compare_state(o, e, 0, "init")
+    n_acc = 0
+    for it in range(4):
+        Z = rng.standard_normal((o.C, o.S, o.m))
+        E = rng.exponential(size=(o.C, o.nblk))
+        ll_before = o.ll.copy()
+        llp_o, ll_o, acc_o = o.impute(Z, E)
+        llp_g, ll_g, acc_g = e.impute(it, Z, E)
+        assert close(llp_g, llp_o), f"it {it} ll deg maxrel {maxrel(llp_g, llp_o)}"
+        assert accept_mismatch_is_tie(acc_g, acc_o, E, llp_o, ll_before)
+        assert np.array_equal(acc_g, acc_o)
+        assert close(ll_g, ll_o)
+        _compare_state(o, e, 0, f"it {it}")
+        _compare_state(o, e, 1, f"it {it}")
+        n_acc += acc_o.sum()
+    assert n_acc > 0
+
+
+def test_lv_bound_violation_rejected(pkg, orc):
+    """A path that leaves the positive quadrant reports ll = -Inf and is rejected
+    (src/run!_alterations.jl:18: `(success, ll)`; SURVEY section 5 failure handling)."""
+    spec = _mk(pkg, "lv", n_obs=4, C=6, dt=0.01)
+    o, e = _pair(pkg, orc, spec)
+    rng = np.random.default_rng(5)
+    Z0 = 0.1 * rng.standard_normal((o.C, o.S, o.m))
+    o.init_paths(Z=Z0)
+    e.init_paths(Z=Z0)
+    Z = rng.standard_normal((o.C, o.S, o.m))
+    Z[::2] *= 400.0  # huge noise on even chains: certain to cross zero
+    o.rho[:] = 0.0
+    e.set_rho(o.rho)
+    E = rng.exponential(size=(o.C, o.nblk))
+    llp_o, ll_o, acc_o = o.impute(Z, E)
+    llp_g, ll_g, acc_g = e.impute(0, Z, E)
+    assert np.all(np.isneginf(llp_o[::2])) and np.all(np.isneginf(llp_g[::2]))
+    assert not acc_g[::2].any()
+    assert np.array_equal(acc_g, acc_o) and close(ll_g, ll_o)
+    _compare_state(o, e, 0)
+
+
+@pytest.mark.parametrize("name,kw", [("fhn", dict(n_obs=5, C=40, dt=0.01)),
+                                     ("l63", dict(n_obs=4, C=3, dt=2e-3))])
+def test_impute_parity_philox(pkg, orc, name, kw):
+    """Production noise: Philox4x32-10 + Box-Muller in-register vs the oracle's restatement."""
+    spec = _mk(pkg, name, **kw)
+    o, e = _pair(pkg, orc, spec)
+    from diffusionmcmc_jl_b200.engine import Engine
+    e.close()
+    e = Engine(spec, seed=0xC0FFEE1234)
+    e.upload_tables(o.H, o.F0, None, o.c0)
+    o.init_paths(seed=0xC0FFEE1234)
+    e.init_paths()
+    assert close(e.get_ll(), o.ll)
+    for it in range(3):
+        llp_o, ll_o, acc_o = o.impute(seed=0xC0FFEE1234, it=it)
+        llp_g, ll_g, acc_g = e.impute(it)
+        assert close(llp_g, llp_o), f"maxrel {maxrel(llp_g, llp_o)}"
+        assert np.array_equal(acc_g, acc_o)
+        _compare_state(o, e, 0, f"philox it {it}")
+
+
+def test_device_backward_filter_vs_oracle(pkg, orc):
+    """a8: device recursion vs oracle recursion (same scheme, FMA contraction differs)."""
+    for name, kw in [("fhn", dict(n_obs=8, C=2, dt=0.01)), ("l63", dict(n_obs=5, C=1, dt=1e-3)),
+                     ("lv", dict(n_obs=6, C=1, dt=0.01))]:
+        spec = _mk(pkg, name, **kw)
+        o, e = _pair(pkg, orc, spec, upload=False)
+        t = e.download_tables()
+        sc = max(1.0, np.abs(o.H).max())
+        assert np.abs(t["H"] - o.H).max() <= 1e-11 * sc
+        assert np.abs(t["F0"] - o.F0).max() <= 1e-11 * max(1.0, np.abs(o.F0).max())
+        assert np.abs(t["c0"] - o.c0).max() <= 1e-11 * max(1.0, np.abs(o.c0).max())
+
+
+def test_blocked_sweeps_parity(pkg, orc):
+    """Chequerboard blocking: relayout (W re-inversion + ll recompute) then imputation, both
+    patterns, pinned end points."""
+    spec = _mk(pkg, "fhn", n_obs=9, C=35, dt=0.01)
+    o, e = _pair(pkg, orc, spec)
+    P = pkg.problems
+    rng = np.random.default_rng(9)
+    Z0 = rng.standard_normal((o.C, o.S, o.m))
+    o.init_paths(Z=Z0)
+    e.init_paths(Z=Z0)
+    for it in range(6):
+        lay = P.chequerboard_layout(o.rec_nobs, 2, it % 2)
+        o.relayout(*lay)
+        e.relayout(*lay)
+        e.upload_tables(o.H, o.F0, o.Psi, o.c0, o.blk_g, o.blk_Qc)
+        e.relayout(*lay)  # recompute with the oracle's tables
+        assert close(e.get_ll(), o.ll, 1e-9), f"relayout ll maxrel {maxrel(e.get_ll(), o.ll)}"
+        Xg, Wg = e.download_state(0)
+        im = interior_mask(o.N)
+        assert close(Wg[:, im], o.accepted_W()[:, im], 1e-9)
+        e.set_ll(o.ll)
+        Z = rng.standard_normal((o.C, o.S, o.m))
+        E = rng.exponential(size=(o.C, o.nblk))
+        ll_before = o.ll.copy()
+        llp_o, ll_o, acc_o = o.impute(Z, E)
+        llp_g, ll_g, acc_g = e.impute(it, Z, E)
+        assert close(llp_g, llp_o, 1e-9), f"it {it} maxrel {maxrel(llp_g, llp_o)}"
+        assert accept_mismatch_is_tie(acc_g, acc_o, E, llp_o, ll_before, 1e-9)
+        Xg, _ = e.download_state(0)
+        assert close(Xg[:, im], o.accepted_X()[:, im], 1e-9)
+        # glued path (PathSavingBuffer format) is continuous and equals the oracle's
+        assert close(e.download_path(3), o.glue_path(3), 1e-9)
+
+
+def test_param_step_parity(pkg, orc):
+    """a9: set_proposal! with fixed W under theta deg, then commit / reject."""
+    spec = _mk(pkg, "fhn", n_obs=6, C=4, dt=0.01)
+    o, e = _pair(pkg, orc, spec)
+    rng = np.random.default_rng(11)
+    Z0 = rng.standard_normal((o.C, o.S, o.m))
+    o.init_paths(Z=Z0)
+    e.init_paths(Z=Z0)
+    im = interior_mask(o.N)
+    for k, accept in enumerate([True, False, True]):
+        th = spec["theta"].copy()
+        th[2] += 0.05 * (k + 1)   # gamma: critical (enters the aux law)
+        th[1] -= 0.02 * (k + 1)
+        llp_o, ok_o = o.param_solve(th)
+        llp_g, ok_g = e.param_loglik(th, critical=True)
+        assert close(llp_g, llp_o, 1e-9), f"maxrel {maxrel(llp_g, llp_o)}"
+        assert np.array_equal(ok_g, ok_o)
+        Xg, _ = e.download_state(1)
+        assert close(Xg[:, im], o.proposal_X()[:, im], 1e-9)
+        o.param_commit(accept)
+        e.param_commit(accept)
+        assert close(e.get_ll(), o.ll, 1e-9)
+        Xg, Wg = e.download_state(0)
+        assert close(Xg[:, im], o.accepted_X()[:, im], 1e-9)
+        assert close(Wg[:, im], o.accepted_W()[:, im], 1e-9)
+        # an imputation sweep after the parameter step still agrees
+        Z = rng.standard_normal((o.C, o.S, o.m))
+        E = rng.exponential(size=(o.C, o.nblk))
+        llp_o2, _, acc_o = o.impute(Z, E)
+        llp_g2, _, acc_g = e.impute(k, Z, E)
+        assert close(llp_g2, llp_o2, 1e-9) and np.array_equal(acc_g, acc_o)
+
+
+def test_rho_one_is_identity_full_size(pkg):
+    """Size-independent property at BASELINE size (FHN, 1024 chains x 100 obs): rho = 1 =>
+    the proposal reproduces the accepted path bit for bit and ll deg == ll (SURVEY section 4 iv)."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = pkg.problems.fhn_spec(n_obs=100, C=1024, dt=1e-3)
+    e = Engine(spec, seed=7)
+    e.init_paths()
+    ll0 = e.get_ll()
+    e.set_rho(np.ones(e.J))
+    llp, ll, acc = e.impute(1)
+    assert np.array_equal(llp, ll0) and acc.all()
+    e.set_rho(np.full(e.J, 0.96))
+    _, _, acc = e.impute(2)
+    p0 = e.download_path(17)
+    assert np.isfinite(p0).all() and p0.shape == (100 * 100 + 1, 2)
+    assert 0.02 < acc.mean() < 0.98
+
+
+def test_chain_sharding_is_invariant(pkg):
+    """Partition invariance: chains [0,24) on one context equal chains
+    [0,12) + [12,24) on two contexts bit for bit (Philox streams are per global chain)."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = pkg.problems.fhn_spec(n_obs=6, C=24, dt=0.01)
+    whole = Engine(spec, seed=99)
+    parts = [Engine(spec, seed=99, chain_offset=o, n_chains=12) for o in (0, 12)]
+    for en in [whole] + parts:
+        en.init_paths()
+    for it in range(3):
+        a = whole.impute(it)
+        b = [p.impute(it) for p in parts]
+        for k in range(3):
+            assert np.array_equal(a[k], np.concatenate([b[0][k], b[1][k]]))
+    Xw, Ww = whole.download_state(0)
+    Xp = np.concatenate([p.download_state(0)[0] for p in parts])
+    assert np.array_equal(Xw, Xp)
