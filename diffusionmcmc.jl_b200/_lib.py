@@ -38,7 +38,10 @@ SYMBOLS = {
     "dmcmc_init_paths": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_init_ll": (C.c_int, [C.c_void_p]),
     "dmcmc_impute": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _dp, _dp, _dp, _bp]),
-    "dmcmc_run_imputation": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, _dp, _dp, _bp]),
+    "dmcmc_run_sweeps": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, _dp,
+                                   C.c_int32, _dp, _dp, _bp]),
+    "dmcmc_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "dmcmc_host_free": (None, [C.c_void_p]),
     "dmcmc_relayout": (C.c_int, [C.c_void_p, C.c_int32, _ip, _ip, _ip]),
     "dmcmc_param_loglik": (C.c_int, [C.c_void_p, _dp, C.c_int32, C.c_int32, _dp, _bp]),
     "dmcmc_param_commit": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -47,8 +50,9 @@ SYMBOLS = {
     "dmcmc_get_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_set_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_accept_counts": (C.c_int, [C.c_void_p, _lp, _lp]),
-    "dmcmc_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _lp]),
+    "dmcmc_kernel_times": (C.c_int, [C.c_void_p, _dp, _lp]),
     "dmcmc_device_bytes": (C.c_int64, [C.c_void_p]),
+    "dmcmc_set_threads": (C.c_int, [C.c_void_p, C.c_int32]),
 }
 
 _lib = None

@@ -72,6 +72,7 @@ struct dmcmc_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> ev;  // pairs (start, stop) of timed solve launches
+    std::vector<int> ev_mode;     // SolveMode of each pair
     size_t ev_used = 0;
     bool timing = true;
     // host copies
@@ -316,6 +317,7 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
 int timed_launch(dmcmc_ctx *ctx, int mode, const SolveParams &sp) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->timing) {
+        if (ctx->ev_used >= 65536) ctx->ev_used = 0;  // nobody is reading the timings
         if (ctx->ev_used + 2 > ctx->ev.size()) {
             for (int i = 0; i < 2; ++i) {
                 cudaEvent_t e;
@@ -325,6 +327,8 @@ int timed_launch(dmcmc_ctx *ctx, int mode, const SolveParams &sp) {
         }
         e0 = ctx->ev[ctx->ev_used];
         e1 = ctx->ev[ctx->ev_used + 1];
+        if (ctx->ev_mode.size() < ctx->ev.size() / 2) ctx->ev_mode.resize(ctx->ev.size() / 2);
+        ctx->ev_mode[ctx->ev_used / 2] = mode;
         ctx->ev_used += 2;
         CK(cudaEventRecord(e0, ctx->stream));
     }
@@ -807,65 +811,118 @@ int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E
     return impute_once(ctx, iter, Z, E, false, nullptr, false, out_ll_prop, out_ll, out_accepted);
 }
 
-int dmcmc_run_imputation(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_iters, double *hist_ll_prop,
-                         double *hist_ll, uint8_t *hist_accepted) {
-    REQUIRE(ctx && n_iters >= 0, "dmcmc_run_imputation: bad argument");
-    CK(cudaSetDevice(ctx->cfg.device));
-    SolveParams sp;
-    if (fill_params(ctx, sp, ctx->law_cur)) return -1;
-    const size_t n = (size_t)ctx->C * sp.nblk;
-    // device-side history ring so that the D2H copies overlap later sweeps
-    const int ring = 4;
-    DevBuf<double> h_llp, h_ll;
-    DevBuf<uint8_t> h_acc;
-    CK(h_llp.ensure(n * ring));
-    CK(h_ll.ensure(n * ring));
-    CK(h_acc.ensure(n * ring));
-    cudaStream_t cs;
-    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> done(ring), freed(ring);
-    for (int i = 0; i < ring; ++i) {
-        CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
-    }
-    sp.acc_count = ctx->d_counts.p;
-    sp.prop_count = ctx->d_counts.p + ctx->J;
-    for (int it = 0; it < n_iters; ++it) {
-        const int slot = it % ring;
-        if (it >= ring) CK(cudaStreamWaitEvent(ctx->stream, freed[slot], 0));
-        sp.iter = iter0 + (uint32_t)it;
-        sp.selX_in = ctx->d_selX[ctx->sel_cur].p; sp.selW_in = ctx->d_selW[ctx->sel_cur].p;
-        sp.selX_out = ctx->d_selX[1 - ctx->sel_cur].p; sp.selW_out = ctx->d_selW[1 - ctx->sel_cur].p;
-        sp.out_llprop = hist_ll_prop ? h_llp.p + n * slot : nullptr;
-        sp.out_ll = hist_ll ? h_ll.p + n * slot : nullptr;
-        sp.out_acc = hist_accepted ? h_acc.p + n * slot : nullptr;
-        if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
-        ctx->sel_cur ^= 1;
-        CK(cudaEventRecord(done[slot], ctx->stream));
-        CK(cudaStreamWaitEvent(cs, done[slot], 0));
-        if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + n * it, h_llp.p + n * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-        if (hist_ll) CK(cudaMemcpyAsync(hist_ll + n * it, h_ll.p + n * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-        if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + n * it, h_acc.p + n * slot, n, cudaMemcpyDeviceToHost, cs));
-        CK(cudaEventRecord(freed[slot], cs));
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(cs));
-    for (int i = 0; i < ring; ++i) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
-    cudaStreamDestroy(cs);
-    h_llp.release(); h_ll.release(); h_acc.release();
-    return 0;
-}
-
-int dmcmc_relayout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2, const int32_t *pinned) {
-    REQUIRE(ctx && i1 && i2 && pinned, "dmcmc_relayout: bad argument");
-    CK(cudaSetDevice(ctx->cfg.device));
+// one layout switch on the stream (no host sync): tables (cached per layout), W re-inversion, ll
+static int relayout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
+                          const int32_t *pinned) {
     if (select_layout(ctx, nblk, i1, i2, pinned)) return -1;
     if (resize_ll(ctx)) return -1;
     Layout &lay = ctx->layout[ctx->lay_cur];
     if (!lay.tab[ctx->law_cur].valid && run_backward_filter(ctx, ctx->law_cur)) return -1;
     SolveParams sp;
     if (fill_params(ctx, sp, ctx->law_cur)) return -1;
-    if (timed_launch(ctx, MODE_RELAYOUT, sp)) return -1;
+    return timed_launch(ctx, MODE_RELAYOUT, sp);
+}
+
+int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
+                     int32_t first_pattern, const double *rho_sched, int32_t nblk_stride,
+                     double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted) {
+    REQUIRE(ctx && n_sweeps >= 0, "dmcmc_run_sweeps: bad argument");
+    REQUIRE(ctx->lay_cur >= 0, "dmcmc_run_sweeps: no layout set");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const bool want_hist = hist_ll_prop || hist_ll || hist_accepted;
+    // the two chequerboard layouts (integer ranges; src/blocking.jl:7-9)
+    std::vector<int32_t> li1[2], li2[2], lpin[2];
+    int nb[2] = {0, 0};
+    if (half_len > 0) {
+        for (int pat = 0; pat < 2; ++pat) {
+            li1[pat].resize(ctx->J); li2[pat].resize(ctx->J); lpin[pat].resize(ctx->J);
+            nb[pat] = dmcmc_chequerboard_layout(ctx->R, ctx->rec_nobs.data(), half_len, pat,
+                                                li1[pat].data(), li2[pat].data(), lpin[pat].data());
+        }
+    } else {
+        nb[0] = nb[1] = ctx->layout[ctx->lay_cur].nblk;
+    }
+    const int nbmax = std::max(nb[0], nb[1]);
+    REQUIRE(!want_hist || nblk_stride >= nbmax, "dmcmc_run_sweeps: nblk_stride smaller than the number of blocks");
+    const size_t row = (size_t)ctx->C * (want_hist ? nblk_stride : nbmax);
+    // device-side history ring: D2H of sweep k overlaps the kernels of sweeps k+1..
+    const int ring = 4;
+    DevBuf<double> h_llp, h_ll;
+    DevBuf<uint8_t> h_acc;
+    cudaStream_t cs = nullptr;
+    std::vector<cudaEvent_t> done(ring, nullptr), freed(ring, nullptr);
+    if (want_hist) {
+        CK(h_llp.ensure(row * ring));
+        CK(h_ll.ensure(row * ring));
+        CK(h_acc.ensure(row * ring));
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        for (int i = 0; i < ring; ++i) {
+            CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+        }
+    }
+    for (int it = 0; it < n_sweeps; ++it) {
+        const int pat = (first_pattern + it) & 1;
+        if (rho_sched) {  // this sweep's pCN memory, host -> device on the compute stream
+            CK(cudaMemcpyAsync(ctx->d_rho.p, rho_sched + (size_t)it * ctx->J, ctx->J * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (half_len > 0 && relayout_async(ctx, nb[pat], li1[pat].data(), li2[pat].data(), lpin[pat].data()))
+            return -1;
+        SolveParams sp;
+        if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+        const int slot = it % ring;
+        const size_t n = (size_t)ctx->C * sp.nblk;
+        if (want_hist && it >= ring) CK(cudaStreamWaitEvent(ctx->stream, freed[slot], 0));
+        sp.iter = iter0 + (uint32_t)it;
+        sp.acc_count = ctx->d_counts.p;
+        sp.prop_count = ctx->d_counts.p + ctx->J;
+        sp.out_llprop = hist_ll_prop ? h_llp.p + row * slot : nullptr;
+        sp.out_ll = hist_ll ? h_ll.p + row * slot : nullptr;
+        sp.out_acc = hist_accepted ? h_acc.p + row * slot : nullptr;
+        if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
+        ctx->sel_cur ^= 1;
+        if (want_hist) {
+            CK(cudaEventRecord(done[slot], ctx->stream));
+            CK(cudaStreamWaitEvent(cs, done[slot], 0));
+            // history rows are [C][nblk] packed; the host rows have stride nblk_stride per chain
+            const size_t hrow = (size_t)ctx->C * nblk_stride;
+            if (sp.nblk == nblk_stride) {
+                if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + hrow * it, h_llp.p + row * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+                if (hist_ll) CK(cudaMemcpyAsync(hist_ll + hrow * it, h_ll.p + row * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+                if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + hrow * it, h_acc.p + row * slot, n, cudaMemcpyDeviceToHost, cs));
+            } else {
+                if (hist_ll_prop) CK(cudaMemcpy2DAsync(hist_ll_prop + hrow * it, nblk_stride * sizeof(double), h_llp.p + row * slot, sp.nblk * sizeof(double), sp.nblk * sizeof(double), ctx->C, cudaMemcpyDeviceToHost, cs));
+                if (hist_ll) CK(cudaMemcpy2DAsync(hist_ll + hrow * it, nblk_stride * sizeof(double), h_ll.p + row * slot, sp.nblk * sizeof(double), sp.nblk * sizeof(double), ctx->C, cudaMemcpyDeviceToHost, cs));
+                if (hist_accepted) CK(cudaMemcpy2DAsync(hist_accepted + hrow * it, nblk_stride, h_acc.p + row * slot, sp.nblk, sp.nblk, ctx->C, cudaMemcpyDeviceToHost, cs));
+            }
+            CK(cudaEventRecord(freed[slot], cs));
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (want_hist) {
+        CK(cudaStreamSynchronize(cs));
+        for (int i = 0; i < ring; ++i) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
+        cudaStreamDestroy(cs);
+        h_llp.release(); h_ll.release(); h_acc.release();
+    }
+    return 0;
+}
+
+void *dmcmc_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void dmcmc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int dmcmc_relayout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2, const int32_t *pinned) {
+    REQUIRE(ctx && i1 && i2 && pinned, "dmcmc_relayout: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (relayout_async(ctx, nblk, i1, i2, pinned)) return -1;
     return sync(ctx);
 }
 
@@ -1026,18 +1083,23 @@ int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted, int64_t *proposed) {
     return 0;
 }
 
-int dmcmc_last_kernel_ms(dmcmc_ctx *ctx, double *ms, int64_t *launches) {
-    REQUIRE(ctx, "dmcmc_last_kernel_ms: null context");
+int dmcmc_kernel_times(dmcmc_ctx *ctx, double *ms, int64_t *launches) {
+    REQUIRE(ctx, "dmcmc_kernel_times: null context");
     CK(cudaSetDevice(ctx->cfg.device));
     if (sync(ctx)) return -1;
-    double tot = 0.0;
+    double tot[4] = {0, 0, 0, 0};
+    int64_t cnt[4] = {0, 0, 0, 0};
     for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
         float f = 0.f;
         CK(cudaEventElapsedTime(&f, ctx->ev[i], ctx->ev[i + 1]));
-        tot += f;
+        const int m = ctx->ev_mode[i / 2] & 3;
+        tot[m] += f;
+        cnt[m] += 1;
     }
-    if (ms) *ms = tot;
-    if (launches) *launches = (int64_t)(ctx->ev_used / 2);
+    for (int m = 0; m < 4; ++m) {
+        if (ms) ms[m] = tot[m];
+        if (launches) launches[m] = cnt[m];
+    }
     ctx->ev_used = 0;
     return 0;
 }
@@ -1054,3 +1116,9 @@ int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx) {
 }
 
 }  // extern "C"
+
+extern "C" int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads) {
+    REQUIRE(ctx && threads >= 32 && threads <= 128 && threads % 32 == 0, "dmcmc_set_threads: 32, 64, 96 or 128");
+    ctx->threads = threads;
+    return 0;
+}

@@ -82,6 +82,9 @@ class Engine:
         if getattr(self, "h", None):
             self.lib.dmcmc_destroy(self.h)
             self.h = None
+            for ptr in getattr(self, "_pinned", []):
+                self.lib.dmcmc_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -155,14 +158,36 @@ class Engine:
         if want:
             return llp, ll, acc.astype(bool)
 
+    def pinned(self, shape, dtype):
+        """NumPy array over pinned host memory (dmcmc_host_alloc); freed with the engine."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = self.lib.dmcmc_host_alloc(max(n, 1))
+        if not ptr:
+            raise DmcmcError("dmcmc_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def run_sweeps(self, it0, n_sweeps, half_len=0, first_pattern=0, rho_sched=None,
+                   hist=None):
+        """dmcmc_run_sweeps.  hist = (ll_prop, ll, accepted) arrays [n][C][stride] or None."""
+        stride = 0
+        llp = ll = acc = None
+        if hist is not None:
+            llp, ll, acc = hist
+            stride = llp.shape[2]
+        self._ck(self.lib.dmcmc_run_sweeps(self.h, it0, n_sweeps, half_len, first_pattern,
+                                           _dp(rho_sched), stride, _dp(llp), _dp(ll), _bp(acc)))
+
     def run_imputation(self, it0, n_iters, histories=True):
-        n = (n_iters, self.C, self.nblk)
+        hist = None
         if histories:
-            llp, ll, acc = np.empty(n), np.empty(n), np.empty(n, np.uint8)
-        else:
-            llp = ll = acc = None
-        self._ck(self.lib.dmcmc_run_imputation(self.h, it0, n_iters, _dp(llp), _dp(ll), _bp(acc)))
-        return llp, ll, acc
+            n = (n_iters, self.C, self.nblk)
+            hist = (np.empty(n), np.empty(n), np.empty(n, np.uint8))
+        self.run_sweeps(it0, n_iters, hist=hist)
+        return hist if histories else (None, None, None)
 
     def param_loglik(self, theta_prop, critical=True):
         th = _f64(theta_prop)
@@ -203,10 +228,15 @@ class Engine:
         self._ck(self.lib.dmcmc_accept_counts(self.h, a.ctypes.data_as(_lib._lp), p.ctypes.data_as(_lib._lp)))
         return a, p
 
+    def kernel_times(self):
+        """(ms[4], launches[4]) per kernel mode since the last call: impute, param, relayout, ll."""
+        ms, n = np.zeros(4), np.zeros(4, np.int64)
+        self._ck(self.lib.dmcmc_kernel_times(self.h, _dp(ms), n.ctypes.data_as(_lib._lp)))
+        return ms, n
+
     def kernel_ms(self):
-        ms, n = C.c_double(), C.c_int64()
-        self._ck(self.lib.dmcmc_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
-        return ms.value, n.value
+        ms, n = self.kernel_times()
+        return float(ms[0]), int(n[0])
 
     def device_bytes(self):
         return int(self.lib.dmcmc_device_bytes(self.h))

@@ -20,6 +20,7 @@
  */
 #ifndef DMCMC_H
 #define DMCMC_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -115,12 +116,19 @@ int dmcmc_init_ll(dmcmc_ctx *ctx);
 int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E,
                  double *out_ll_prop, double *out_ll, uint8_t *out_accepted);
 
-/* Production loop: n_iters consecutive updates with Philox noise starting at iteration iter0,
- * alternating between the given layouts when n_layouts = 2 (chequerboard); histories
- * [n_iters][n_chains][nblk_max] are copied to the host asynchronously while later iterations run.
- * Any output may be NULL. */
-int dmcmc_run_imputation(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_iters, double *hist_ll_prop,
-                         double *hist_ll, uint8_t *hist_accepted);
+/* Production loop (what `run!` drives for a smoothing chain): n_sweeps consecutive
+ * PathImputation updates with Philox noise, iterations iter0, iter0+1, ...  half_len > 0
+ * alternates the two chequerboard layouts (pattern first_pattern first), each sweep = layout
+ * switch + imputation; half_len <= 0 keeps the current layout.  rho_sched [n_sweeps][J] (may be
+ * NULL) is copied host->device before each sweep.  History rows (any may be NULL) are
+ * [n_sweeps][n_chains][nblk_stride]; they stream back while later sweeps run, so host buffers
+ * from dmcmc_host_alloc (pinned) overlap best.  Returns after everything has landed. */
+int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
+                     int32_t first_pattern, const double *rho_sched, int32_t nblk_stride,
+                     double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted);
+/* Pinned host memory for the streaming buffers above. */
+void *dmcmc_host_alloc(size_t bytes);
+void dmcmc_host_free(void *p);
 
 /* -- layout switch (change_laws_for_blocking! + recompute_loglikhd!, called but undefined in the
  *    reference: src/workspaces.jl:469-470): new tables, Wiener re-inversion, ll recompute. ------ */
@@ -147,10 +155,13 @@ int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll);
 int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted /* [nblk] */, int64_t *proposed);
 
 /* -- measurement helpers (bench.py) ----------------------------------------------------------- */
-/* Average device time in ms of the last `dmcmc_impute`/`dmcmc_run_imputation` kernels, measured
- * with CUDA events on the context's stream. */
-int dmcmc_last_kernel_ms(dmcmc_ctx *ctx, double *ms, int64_t *launches);
+/* Device time (ms, CUDA events on the context's stream) and launch count of the solve kernels
+ * since the previous call, per kernel mode: [0] imputation, [1] parameter-step solve,
+ * [2] layout switch (W re-inversion + ll), [3] ll only. */
+int dmcmc_kernel_times(dmcmc_ctx *ctx, double ms[4], int64_t launches[4]);
 int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
+/* Threads per CTA of the solve kernels (32..128, multiple of 32; default 64). */
+int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
 
 #ifdef __cplusplus
 }

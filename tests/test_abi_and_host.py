@@ -1,0 +1,116 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/dmcmc.h declares
+(no compute without a GPU), it refuses to run without CUDA (no CPU fallback), and the host
+mirror's bookkeeping (rho handling, adaptation, path ring) follows the reference."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib(pkg):
+    from diffusionmcmc_jl_b200 import _lib, build
+    build.build()
+    return _lib
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "dmcmc.h")).read()
+    declared = set(re.findall(r"\b(dmcmc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    l = lib.load()
+    for name in declared:
+        assert hasattr(l, name), f"{name} declared in include/dmcmc.h but not exported"
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+
+
+def test_layout_helper_matches_host_mirror(lib, pkg):
+    l = lib.load()
+    for nobs in ([100], [5, 8, 3], [1]):
+        for h in (0, 1, 2, 7):
+            for pat in (0, 1):
+                r = np.array(nobs, np.int32)
+                J = int(r.sum())
+                i1, i2, pin = (np.zeros(J, np.int32) for _ in range(3))
+                nb = l.dmcmc_chequerboard_layout(len(r), r.ctypes.data_as(lib._ip), h, pat,
+                                                 i1.ctypes.data_as(lib._ip), i2.ctypes.data_as(lib._ip),
+                                                 pin.ctypes.data_as(lib._ip))
+                a = pkg.problems.chequerboard_layout(nobs, h, pat)
+                assert nb == len(a[0])
+                assert np.array_equal(i1[:nb], a[0]) and np.array_equal(i2[:nb], a[1]) and np.array_equal(pin[:nb], a[2])
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product refuses to create a context."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    l = lib.load()
+    cfg = lib.Config(lib.ABI_VERSION, 0, 2, 4, 0, 0, 1, 1e-4)
+    h = ctypes.c_void_p()
+    assert l.dmcmc_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"no CPU fallback" in l.dmcmc_last_error(None)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may use oracle/."""
+    pk = os.path.join(ROOT, "diffusionmcmc.jl_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"#include\s+[<\"][^>\"]*oracle",
+                            r"liboracle", r"orc_[a-z_]+\s*\("):
+                    assert not re.search(pat, src, re.M), (f, pat)
+
+
+def test_path_imputation_rho_expansion(pkg):
+    # src/updates.jl:33-74
+    u = pkg.PathImputation(0.96)
+    assert u.rho_s == [[0.96]]
+    u.init_update([2, 2, 1])
+    assert u.rho_s == [[0.96, 0.96], [0.96, 0.96], [0.96]]
+    rho = u.rho_per_interval([0, 2, 4], [1, 3, 4], 5)
+    assert np.array_equal(rho, np.full(5, 0.96))
+    u2 = pkg.PathImputation([[0.5, 0.6], [0.7]])
+    u2.init_update([2, 3])
+    assert u2.rho_s == [[0.5, 0.6], [0.7, 0.7, 0.7]]
+
+
+def test_adaptation_follows_the_reference(pkg):
+    # src/adaptation.jl:32-40 defaults
+    a = pkg.AdaptationPathImputation()
+    assert (a.target_accpt_rate, a.adapt_every_k_steps, a.scale, a.min, a.max, a.offset) == \
+        (0.234, 100, 1.0, 1e-12, 1.0 - 1e-12, 1e2)
+    assert a.acceptance_rate() == 0.0
+    for i in range(100):
+        a.register(i % 2 == 0)
+    assert a.time_to_update() and a.acceptance_rate() == 0.5
+    rho = a.readjust(0.9, 100)   # acceptance above target => rho decreases by delta in logit space
+    d = 1.0 / math.sqrt(max(1.0, 100 / 100 - 100.0))
+    expect = 1 / (1 + math.exp(-(math.log(0.9) - math.log(0.1) - d)))
+    assert abs(rho - expect) < 1e-15 and rho < 0.9
+    assert a.proposed == 0 and a.accepted == 0
+    for i in range(100):
+        a.register(False)
+    assert a.readjust(0.5, 200) > 0.5
+    m = pkg.AdaptationMultiPathImputation(pkg.AdaptationPathImputation(adapt_every_k_steps=10))
+    m.resize(3)
+    assert len(m.v) == 3 and m.v[2].adapt_every_k_steps == 10 and m.v[2] is not m.v[0]
+
+
+def test_path_saving_buffer_ring(pkg):
+    # src/path_saving_buffer.jl:7-64
+    cc = pkg.CyclicCounter(3)
+    assert [cc(nxt=True) for _ in range(7)] == [1, 2, 3, 1, 2, 3, 1]
+    assert np.array_equal(pkg.glue_containers([[1, 2, 3], [3, 4, 5], [5, 6]]), [1, 2, 4 - 1, 4, 5, 6][:0] + [1, 2, 3, 4, 5, 6])
+    buf = pkg.PathSavingBuffer([np.arange(5.0)], 2, 2)
+    buf.save([np.ones((5, 2))])
+    buf.save([2 * np.ones((5, 2))])
+    buf.save([3 * np.ones((5, 2))])
+    assert buf.XX[0][0]["x"][0, 0] == 3 and buf.XX[1][0]["x"][0, 0] == 2
