@@ -47,12 +47,14 @@ SYMBOLS = {
     "dmcmc_param_commit": (C.c_int, [C.c_void_p, C.c_int32]),
     "dmcmc_download_path": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "dmcmc_download_state": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
+    "dmcmc_n_blocks": (C.c_int32, [C.c_void_p]),
     "dmcmc_get_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_set_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_accept_counts": (C.c_int, [C.c_void_p, _lp, _lp]),
     "dmcmc_kernel_times": (C.c_int, [C.c_void_p, _dp, _lp]),
     "dmcmc_device_bytes": (C.c_int64, [C.c_void_p]),
     "dmcmc_set_threads": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dmcmc_set_fast_step": (C.c_int, [C.c_void_p, C.c_int32]),
 }
 
 _lib = None

@@ -94,7 +94,9 @@ struct dmcmc_ctx {
     DevBuf<unsigned long long> d_counts;  // [2][J]: accepted, proposed
     std::vector<double> h_param_llprop;
     bool param_pending = false;
+    bool w_valid = false;  // stored accepted W is consistent with the accepted X under the current law/layout
     int threads = 64;
+    bool fast_step = true;  // allow model-specific fused steps (dmcmc_set_option)
 };
 
 namespace {
@@ -310,6 +312,10 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     sp.selX_out = ctx->d_selX[1 - ctx->sel_cur].p; sp.selW_out = ctx->d_selW[1 - ctx->sel_cur].p;
     sp.x0 = ctx->d_x0.p; sp.ll = ctx->d_ll.p;
     sp.seed = ctx->cfg.seed;
+    sp.out_stride = lay.nblk;
+    sp.reinvert = 0;
+    sp.store_w = 1;
+    sp.fast_ok = (!law.custom_aux && ctx->fast_step) ? 1 : 0;
     for (int i = 0; i < DMCMC_MAX_THETA; ++i) sp.th.v[i] = law.theta[i];
     return 0;
 }
@@ -636,8 +642,10 @@ int dmcmc_chequerboard_layout(int32_t R, const int32_t *rec_nobs, int32_t half_l
 int dmcmc_set_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2, const int32_t *pinned) {
     REQUIRE(ctx && i1 && i2 && pinned, "dmcmc_set_layout: bad argument");
     CK(cudaSetDevice(ctx->cfg.device));
+    const int before = ctx->lay_cur;
     if (select_layout(ctx, nblk, i1, i2, pinned)) return -1;
     if (resize_ll(ctx)) return -1;
+    if (before != ctx->lay_cur) ctx->w_valid = false;
     return sync(ctx);
 }
 
@@ -752,6 +760,8 @@ static int impute_once(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const dou
     }
     sp.iter = iter;
     sp.force_accept = force_accept;
+    sp.reinvert = (!force_accept && !ctx->w_valid) ? 1 : 0;
+    sp.store_w = !sp.reinvert;
     sp.out_llprop = ctx->d_out_llprop.p;
     sp.out_ll = ctx->d_out_ll.p;
     sp.out_acc = ctx->d_out_acc.p;
@@ -764,6 +774,7 @@ static int impute_once(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const dou
     }
     if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
     ctx->sel_cur ^= 1;
+    if (force_accept) ctx->w_valid = true;
     if (out_ll_prop) CK(cudaMemcpyAsync(out_ll_prop, ctx->d_out_llprop.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_ll) CK(cudaMemcpyAsync(out_ll, ctx->d_out_ll.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_acc) CK(cudaMemcpyAsync(out_acc, ctx->d_out_acc.p, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -811,16 +822,31 @@ int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E
     return impute_once(ctx, iter, Z, E, false, nullptr, false, out_ll_prop, out_ll, out_accepted);
 }
 
-// one layout switch on the stream (no host sync): tables (cached per layout), W re-inversion, ll
-static int relayout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
-                          const int32_t *pinned) {
+// select a layout on the stream (no host sync): tables are cached per (layout, law)
+static int switch_layout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
+                               const int32_t *pinned) {
+    const int before = ctx->lay_cur;
     if (select_layout(ctx, nblk, i1, i2, pinned)) return -1;
     if (resize_ll(ctx)) return -1;
     Layout &lay = ctx->layout[ctx->lay_cur];
     if (!lay.tab[ctx->law_cur].valid && run_backward_filter(ctx, ctx->law_cur)) return -1;
+    if (before != ctx->lay_cur) ctx->w_valid = false;  // W and ll belong to the previous layout's law
+    return 0;
+}
+
+// materialise W (re-inversion) and ll under the current law/layout
+static int materialize_async(dmcmc_ctx *ctx) {
     SolveParams sp;
     if (fill_params(ctx, sp, ctx->law_cur)) return -1;
-    return timed_launch(ctx, MODE_RELAYOUT, sp);
+    if (timed_launch(ctx, MODE_RELAYOUT, sp)) return -1;
+    ctx->w_valid = true;
+    return 0;
+}
+
+static int relayout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
+                          const int32_t *pinned) {
+    if (switch_layout_async(ctx, nblk, i1, i2, pinned)) return -1;
+    return materialize_async(ctx);
 }
 
 int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
@@ -867,14 +893,16 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             CK(cudaMemcpyAsync(ctx->d_rho.p, rho_sched + (size_t)it * ctx->J, ctx->J * sizeof(double),
                                cudaMemcpyHostToDevice, ctx->stream));
         }
-        if (half_len > 0 && relayout_async(ctx, nb[pat], li1[pat].data(), li2[pat].data(), lpin[pat].data()))
+        if (half_len > 0 && switch_layout_async(ctx, nb[pat], li1[pat].data(), li2[pat].data(), lpin[pat].data()))
             return -1;
         SolveParams sp;
         if (fill_params(ctx, sp, ctx->law_cur)) return -1;
         const int slot = it % ring;
-        const size_t n = (size_t)ctx->C * sp.nblk;
         if (want_hist && it >= ring) CK(cudaStreamWaitEvent(ctx->stream, freed[slot], 0));
         sp.iter = iter0 + (uint32_t)it;
+        sp.reinvert = !ctx->w_valid;  // fused layout switch: noise and ll recovered from the accepted X
+        sp.store_w = ctx->w_valid;
+        sp.out_stride = want_hist ? nblk_stride : sp.nblk;
         sp.acc_count = ctx->d_counts.p;
         sp.prop_count = ctx->d_counts.p + ctx->J;
         sp.out_llprop = hist_ll_prop ? h_llp.p + row * slot : nullptr;
@@ -885,17 +913,11 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
         if (want_hist) {
             CK(cudaEventRecord(done[slot], ctx->stream));
             CK(cudaStreamWaitEvent(cs, done[slot], 0));
-            // history rows are [C][nblk] packed; the host rows have stride nblk_stride per chain
+            // the kernel wrote rows with the host's stride, so each history is one contiguous copy
             const size_t hrow = (size_t)ctx->C * nblk_stride;
-            if (sp.nblk == nblk_stride) {
-                if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + hrow * it, h_llp.p + row * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-                if (hist_ll) CK(cudaMemcpyAsync(hist_ll + hrow * it, h_ll.p + row * slot, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-                if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + hrow * it, h_acc.p + row * slot, n, cudaMemcpyDeviceToHost, cs));
-            } else {
-                if (hist_ll_prop) CK(cudaMemcpy2DAsync(hist_ll_prop + hrow * it, nblk_stride * sizeof(double), h_llp.p + row * slot, sp.nblk * sizeof(double), sp.nblk * sizeof(double), ctx->C, cudaMemcpyDeviceToHost, cs));
-                if (hist_ll) CK(cudaMemcpy2DAsync(hist_ll + hrow * it, nblk_stride * sizeof(double), h_ll.p + row * slot, sp.nblk * sizeof(double), sp.nblk * sizeof(double), ctx->C, cudaMemcpyDeviceToHost, cs));
-                if (hist_accepted) CK(cudaMemcpy2DAsync(hist_accepted + hrow * it, nblk_stride, h_acc.p + row * slot, sp.nblk, sp.nblk, ctx->C, cudaMemcpyDeviceToHost, cs));
-            }
+            if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + hrow * it, h_llp.p + row * slot, hrow * sizeof(double), cudaMemcpyDeviceToHost, cs));
+            if (hist_ll) CK(cudaMemcpyAsync(hist_ll + hrow * it, h_ll.p + row * slot, hrow * sizeof(double), cudaMemcpyDeviceToHost, cs));
+            if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + hrow * it, h_acc.p + row * slot, hrow, cudaMemcpyDeviceToHost, cs));
             CK(cudaEventRecord(freed[slot], cs));
         }
     }
@@ -958,6 +980,8 @@ int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta,
         CK(cp(tp.ptPsi, tc.ptPsi)); CK(cp(tp.ptc0, tc.ptc0));
         tp.valid = true;
     }
+    // the solve needs the accepted W under the CURRENT law: recover it first when it is stale
+    if (!ctx->w_valid && materialize_async(ctx)) return -1;
     SolveParams sp;
     if (fill_params(ctx, sp, prop)) return -1;
     if (ensure_unit_buffers(ctx)) return -1;
@@ -1011,6 +1035,7 @@ int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W) {
     REQUIRE(ctx->lay_cur >= 0 && ctx->have_start, "dmcmc_download_state: context not initialised");
     CK(cudaSetDevice(ctx->cfg.device));
     Layout &lay = ctx->layout[ctx->lay_cur];
+    if (!ctx->w_valid && which == 0 && lay.tab[ctx->law_cur].valid && materialize_async(ctx)) return -1;
     DevBuf<double> oX, oW;
     const size_t nX = (size_t)ctx->C * ctx->P * ctx->d, nW = (size_t)ctx->C * ctx->P * ctx->m;
     CK(oX.ensure(nX));
@@ -1083,6 +1108,10 @@ int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted, int64_t *proposed) {
     return 0;
 }
 
+int32_t dmcmc_n_blocks(const dmcmc_ctx *ctx) {
+    return (ctx && ctx->lay_cur >= 0) ? ctx->layout[ctx->lay_cur].nblk : -1;
+}
+
 int dmcmc_kernel_times(dmcmc_ctx *ctx, double *ms, int64_t *launches) {
     REQUIRE(ctx, "dmcmc_kernel_times: null context");
     CK(cudaSetDevice(ctx->cfg.device));
@@ -1116,6 +1145,12 @@ int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx) {
 }
 
 }  // extern "C"
+
+extern "C" int dmcmc_set_fast_step(dmcmc_ctx *ctx, int32_t on) {
+    REQUIRE(ctx, "dmcmc_set_fast_step: null context");
+    ctx->fast_step = on != 0;
+    return 0;
+}
 
 extern "C" int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads) {
     REQUIRE(ctx && threads >= 32 && threads <= 128 && threads % 32 == 0, "dmcmc_set_threads: 32, 64, 96 or 128");

@@ -49,6 +49,10 @@ struct SolveParams {
     uint64_t seed;
     uint32_t iter;
     int32_t force_accept;
+    int32_t reinvert;   // 1: accepted noise is recovered from the accepted X (stored W is stale)
+    int32_t store_w;    // 1: write the proposal noise W deg (0 when the next update re-inverts anyway)
+    int32_t fast_ok;    // 1: the law uses the model's built-in aux law (fused model-specific step allowed)
+    int32_t out_stride; // row stride (per chain) of out_llprop / out_ll / out_acc
     const uint8_t *unit_mask;  // [C][nblk] or nullptr
     // outputs
     double *out_llprop, *out_ll;  // [C][nblk]

@@ -25,16 +25,10 @@
 
 namespace dmcmc {
 
-// ---- one guided step: Girsanov integrand G*dt and the drift part (b + a r) dt -----------------
-template <class MD, bool PSI>
-__device__ __forceinline__ void guided_terms(const Theta &th, const double *__restrict__ rec,
-                                             const double *xb, const double *aB,
-                                             const double *abeta, const double *aatil,
-                                             const double *x, double dt, double *drift_dt,
-                                             double &dll) {
-    constexpr int D = MD::D;
+// ---- guiding-term offset of this chain at one grid point: F = F0 + Psi x_b (a3) ---------------
+template <int D, bool PSI>
+__device__ __forceinline__ void guiding_F(const double *rec, const double *xb, double *F) {
     using R = Rec<D, PSI>;
-    double F[D], r[D], b[D], ar[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         double f = rec[R::OFF_F + i];
@@ -46,6 +40,18 @@ __device__ __forceinline__ void guided_terms(const Theta &th, const double *__re
         }
         F[i] = f;
     }
+}
+
+// ---- one guided step: Girsanov integrand G*dt and the drift part (b + a r) dt -----------------
+template <class MD, bool PSI>
+__device__ __forceinline__ void guided_terms(const Theta &th, const double *__restrict__ rec,
+                                             const double *F, const double *aB,
+                                             const double *abeta, const double *aatil,
+                                             const double *x, double dt, double *drift_dt,
+                                             double &dll) {
+    constexpr int D = MD::D;
+    using R = Rec<D, PSI>;
+    double r[D], b[D], ar[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         double s = 0.0;
@@ -78,6 +84,36 @@ __device__ __forceinline__ void guided_terms(const Theta &th, const double *__re
 #pragma unroll
     for (int i = 0; i < D; ++i) drift_dt[i] = (b[i] + ar[i]) * dt;
 }
+
+// ---- FitzHugh-Nagumo fused step (built-in FitzHughNagumoAux only) ------------------------------
+// With the aux law's second row equal to the target's (B = [., .; gamma, -1], beta~_2 = beta) and
+// B_12 = -1/eps, the Girsanov integrand collapses to
+//     (b - b~)'r = [ (1/eps - B_11) y - y^3/eps - (beta~_1 - s/eps) ] r_1 ,
+// a r = (0, sigma^2 r_2), and the noise recovery only needs the second coordinate.  Same
+// mathematics as guided_terms, ~3x fewer FP64 instructions; differences are rounding-level.
+struct FhnK {
+    double ie, s, gam, bet, sig, sig2, isig;  // per law
+    double c1, c2;                            // per interval
+    __device__ __forceinline__ void set_law(const Theta &th) {
+        ie = 1.0 / th.v[0]; s = th.v[1]; gam = th.v[2]; bet = th.v[3]; sig = th.v[4];
+        sig2 = sig * sig; isig = 1.0 / sig;
+    }
+    __device__ __forceinline__ void set_interval(const double *aB, const double *abeta) {
+        c1 = ie - aB[0];
+        c2 = abeta[0] - s * ie;
+    }
+    // Girsanov increment and guiding term r_2 at state (y, x)
+    template <bool PSI>
+    __device__ __forceinline__ void terms(const double *rec, const double *F, double y, double x,
+                                          double dt, double &dll, double &r2) const {
+        using R = Rec<2, PSI>;
+        const double r1 = fma(-rec[R::OFF_H + 1], x, fma(-rec[R::OFF_H], y, F[0]));
+        r2 = fma(-rec[R::OFF_H + 2], x, fma(-rec[R::OFF_H + 1], y, F[1]));
+        const double y3 = (y * y) * y;
+        const double d1 = fma(-ie, y3, fma(c1, y, -c2));
+        dll = (d1 * r1) * dt;
+    }
+};
 
 template <int REC>
 __device__ __forceinline__ void load_rec(const double *__restrict__ p, double *r) {
@@ -112,72 +148,99 @@ __device__ __forceinline__ void load_start(const SolveParams &p, int chain, int 
     }
 }
 
-template <class MD, bool PSI, int MODE, bool PHILOX>
-__global__ void __launch_bounds__(128) solve_kernel(const SolveParams p) {
+// ---- TMA bulk copy + mbarrier plumbing (sm_90+/sm_100a PTX) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (SASS: UBLKCP.S.G), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+template <int REC>
+__device__ __forceinline__ void load_rec_smem(const double *p, double *r) {
+#pragma unroll
+    for (int i = 0; i < REC / 2; ++i) {
+        const double2 v = reinterpret_cast<const double2 *>(p)[i];
+        r[2 * i] = v.x;
+        r[2 * i + 1] = v.y;
+    }
+}
+
+constexpr int CHUNK_TILES = 16;  // table records staged per bulk copy: 16 tiles = 128 Euler steps
+
+// One CTA = one layout block x blockDim.x consecutive chains; one thread = one (chain, block)
+// unit.  The block's backward-filter table is streamed through shared memory in chunks of
+// CHUNK_TILES tiles by TMA bulk copies (double-buffered, mbarrier-signalled), so the per-step
+// H/F/Psi record is an LDS broadcast instead of a dependent global load.
+//   MODE   : see SolveMode
+//   PHILOX : in-register counter-based noise (production) vs explicit Z/E from HBM (parity)
+//   REINV  : the accepted noise increment and the accepted ll are recovered on the fly from the
+//            accepted path X (fused layout switch; no W traffic) instead of read from W
+//   FAST   : model-specific fused step (FitzHugh-Nagumo with its built-in aux law)
+template <class MD, bool PSI, int MODE, bool PHILOX, bool REINV, bool FAST>
+__global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     constexpr int D = MD::D, M = MD::M;
     using R = Rec<D, PSI>;
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= (long long)p.nblk * p.C) return;
-    const int blk = (int)(u / p.C), chain = (int)(u - (long long)blk * p.C);
-    const size_t uo = (size_t)chain * p.nblk + blk;  // [C][nblk] host layout of ll / histories
-    const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
+    constexpr int STAGE = CHUNK_TILES * TILE * R::SIZE;  // doubles per stage
+    __shared__ alignas(128) double stab[2][STAGE];
+    __shared__ alignas(8) uint64_t full[2];
 
-    if (MODE == MODE_IMPUTE && p.unit_mask && !p.unit_mask[uo]) {
-        for (int j = i1; j <= i2; ++j) {
-            const size_t o = (size_t)j * p.C + chain;
-            p.selX_out[o] = p.selX_in[o];
-            p.selW_out[o] = p.selW_in[o];
-        }
-        return;
+    const int groups = (p.C + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int blk = (int)(blockIdx.x / groups);
+    const int chain_raw = (int)(blockIdx.x % groups) * (int)blockDim.x + (int)threadIdx.x;
+    const bool in_range = chain_raw < p.C;
+    const int chain = in_range ? chain_raw : p.C - 1;  // out-of-range lanes shadow the last chain, stores off
+    const size_t uo = (size_t)chain * p.nblk + blk;    // [C][nblk] host layout of ll
+    const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
+    const bool masked = (MODE == MODE_IMPUTE) && p.unit_mask && !p.unit_mask[uo];
+    const bool active = in_range && !masked;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    auto issue = [&](int j, int c0, int q) {  // thread 0: stage chunk (j, c0) of the table
+        const int nt = (p.iv_N[j] + TILE - 1) >> 3;
+        const int ntl = min(CHUNK_TILES, nt - c0);
+        const uint32_t bytes = (uint32_t)(ntl * TILE * R::SIZE * sizeof(double));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[q & 1], bytes);
+        bulk_g2s(stab[q & 1], p.table + ((size_t)p.iv_tile_off[j] + c0) * TILE * R::SIZE, bytes, &full[q & 1]);
+    };
+    if (threadIdx.x == 0) issue(i1, 0, 0);
 
     const bool pinned = PSI && p.blk_pinned[blk];
-    double x[D], xb[D];
+    double x[D], xb[D], xa[D];  // proposal state, pinned end point, accepted state (REINV / RELAYOUT)
     load_start<D>(p, chain, i1, x);
 #pragma unroll
-    for (int c = 0; c < D; ++c) xb[c] = 0.0;
+    for (int c = 0; c < D; ++c) { xb[c] = 0.0; xa[c] = x[c]; }
     if (pinned) load_end<D>(p, chain, i2, xb);
 
-    // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
-    double llp;
-    {
-        double rec[R::SIZE];
-        load_rec<R::SIZE>(p.table + (size_t)p.iv_tile_off[i1] * TILE * R::SIZE, rec);
-        double c = p.blk_c0[blk];
-        if (pinned) {
-            double gx = 0.0, q = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                gx += p.blk_g[(size_t)blk * D + i] * xb[i];
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) s += p.blk_Qc[(size_t)blk * D * D + i * D + k] * xb[k];
-                q += xb[i] * s;
-            }
-            c += gx + 0.5 * q;
-        }
-        double xHx = 0.0, Fx = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            double f = rec[R::OFF_F + i];
-            if constexpr (PSI) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) s += rec[R::OFF_PSI + i * D + k] * xb[k];
-                f += s;
-            }
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) s += rec[R::OFF_H + hidx(D, i, k)] * x[k];
-            xHx += x[i] * s;
-            Fx += f * x[i];
-        }
-        llp = -c - 0.5 * xHx + Fx;
-    }
+    FhnK fk;
+    if constexpr (FAST) fk.set_law(p.th);
 
+    double llp = 0.0, lla = 0.0;  // proposal ll, accepted-path ll (recomputed when REINV)
     bool ok = true;
     const size_t cstride = (size_t)p.TT * p.C * TILE;  // component stride in X / W / Z
     const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
+    int q = 0;
+
+    constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
+    constexpr bool NEED_XA = !SOLVE || REINV;   // walk the accepted path
+    constexpr bool NEED_WA = SOLVE && !REINV;   // read the stored accepted noise
 
     for (int j = i1; j <= i2; ++j) {
         const int N = p.iv_N[j];
@@ -193,182 +256,268 @@ __global__ void __launch_bounds__(128) solve_kernel(const SolveParams p) {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
         }
-        double lsum = 0.0;
+        if constexpr (FAST) fk.set_interval(aB, abeta);
+        const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
+        const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
+        const double *Wa = p.W[sw];
+        double *Wp = p.W[1 - sw];
+        const double *Xa = p.X[sx];
+        double *Xp = p.X[1 - sx];
+        double lsum = 0.0, lsum_a = 0.0;
 
-        if constexpr (MODE == MODE_IMPUTE || MODE == MODE_PARAM) {
-            const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
-            const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
-            const double *Wa = p.W[sw];
-            double *Wp = p.W[1 - sw];
-            double *Xp = p.X[1 - sx];
-            double dwa[M][TILE], dwn[M][TILE];
-            {
-                const size_t base = (toff * p.C + chain) * TILE;
+        // software prefetch of the x-independent streams, one tile ahead
+        double dwn[NEED_WA ? M : 1][TILE], xan[NEED_XA ? D : 1][TILE];
+        {
+            const size_t base = (toff * p.C + chain) * TILE;
+            if constexpr (NEED_WA) {
 #pragma unroll
-                for (int w = 0; w < M; ++w) ld_tile(Wa + w * cstride + base, dwa[w]);
+                for (int w = 0; w < M; ++w) ld_tile(Wa + w * cstride + base, dwn[w]);
             }
-            for (int tl = 0; tl < nt; ++tl) {
+            if constexpr (NEED_XA) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) ld_tile(Xa + c * cstride + base, xan[c]);
+            }
+        }
+
+        for (int c0 = 0; c0 < nt; c0 += CHUNK_TILES, ++q) {
+            __syncthreads();  // every thread is done with chunk q-1: its stage may be refilled
+            if (threadIdx.x == 0) {
+                if (c0 + CHUNK_TILES < nt) issue(j, c0 + CHUNK_TILES, q + 1);
+                else if (j + 1 <= i2) issue(j + 1, 0, q + 1);
+            }
+            mbar_wait(&full[q & 1], (uint32_t)((q >> 1) & 1));
+            const double *srec = stab[q & 1];
+
+            if (q == 0) {
+                // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
+                double rec[R::SIZE], F[D];
+                load_rec_smem<R::SIZE>(srec, rec);
+                guiding_F<D, PSI>(rec, xb, F);
+                double c = p.blk_c0[blk];
+                if (pinned) {
+                    double gx = 0.0, qq = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        gx += p.blk_g[(size_t)blk * D + i] * xb[i];
+                        double s = 0.0;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) s += p.blk_Qc[(size_t)blk * D * D + i * D + k] * xb[k];
+                        qq += xb[i] * s;
+                    }
+                    c += gx + 0.5 * qq;
+                }
+                double xHx = 0.0, Fx = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s += rec[R::OFF_H + hidx(D, i, k)] * x[k];
+                    xHx += x[i] * s;
+                    Fx += F[i] * x[i];
+                }
+                llp = -c - 0.5 * xHx + Fx;
+                lla = llp;
+            }
+
+            const int tl_end = min(nt, c0 + CHUNK_TILES);
+            for (int tl = c0; tl < tl_end; ++tl) {
                 const size_t tile = toff + tl;
                 const size_t base = (tile * p.C + chain) * TILE;
-                if (tl + 1 < nt) {  // accepted noise of the next tile: independent of x, fetch early
+                double dwa[NEED_WA ? M : 1][TILE], xat[NEED_XA ? D : 1][TILE];
+                if constexpr (NEED_WA) {
 #pragma unroll
                     for (int w = 0; w < M; ++w)
-                        ld_tile(Wa + w * cstride + base + (size_t)p.C * TILE, dwn[w]);
+#pragma unroll
+                        for (int s = 0; s < TILE; ++s) dwa[w][s] = dwn[w][s];
+                    if (tl + 1 < nt) {
+#pragma unroll
+                        for (int w = 0; w < M; ++w)
+                            ld_tile(Wa + w * cstride + base + (size_t)p.C * TILE, dwn[w]);
+                    }
                 }
-                double z[M][TILE];
+                if constexpr (NEED_XA) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+#pragma unroll
+                        for (int s = 0; s < TILE; ++s) xat[c][s] = xan[c][s];
+                    if (tl + 1 < nt) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c)
+                            ld_tile(Xa + c * cstride + base + (size_t)p.C * TILE, xan[c]);
+                    }
+                }
+                double z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
                 if constexpr (MODE == MODE_IMPUTE) {
                     if constexpr (PHILOX) {
 #pragma unroll
                         for (int w = 0; w < M; ++w)
 #pragma unroll
-                            for (int q = 0; q < TILE / 2; ++q)
-                                philox_normal_pair(p.seed, p.iter, (uint32_t)j, gchain, (uint32_t)w,
-                                                   (uint32_t)(tl * (TILE / 2) + q), z[w][2 * q],
-                                                   z[w][2 * q + 1]);
+                            for (int h = 0; h < TILE / 4; ++h)
+                                philox_normal4(p.seed, p.iter, (uint32_t)j, gchain, (uint32_t)w,
+                                               (uint32_t)(tl * (TILE / 4) + h), &z[w][4 * h]);
                     } else {
 #pragma unroll
                         for (int w = 0; w < M; ++w) ld_tile_stream(p.Z + w * cstride + base, z[w]);
                     }
                 }
-                double xo[D][TILE], dwo[M][TILE];
-                const double *trec = p.table + tile * TILE * R::SIZE;
+                double xo[SOLVE ? D : 1][TILE], dwo[M][TILE];
+                const double *trec = srec + (size_t)(tl - c0) * TILE * R::SIZE;
 #pragma unroll
                 for (int s = 0; s < TILE; ++s) {
-                    double rec[R::SIZE];
-                    load_rec<R::SIZE>(trec + s * R::SIZE, rec);
-                    double dw[M];
-#pragma unroll
-                    for (int w = 0; w < M; ++w) {
-                        if constexpr (MODE == MODE_IMPUTE)
-                            dw[w] = lam * (rec[1] * z[w][s]) + rho * dwa[w][s];
-                        else
-                            dw[w] = dwa[w][s];
-                        dwo[w][s] = dw[w];
-                    }
-                    if (tl * TILE + s < N) {
-                        double dr[D], sdw[D], dll;
-                        guided_terms<MD, PSI>(p.th, rec, xb, aB, abeta, aatil, x, rec[0], dr, dll);
-                        lsum += dll;
-                        MD::sigma_mul(p.th, x, dw, sdw);
-#pragma unroll
-                        for (int c = 0; c < D; ++c) x[c] = x[c] + dr[c] + sdw[c];
-                        ok = ok && MD::bound_ok(x);
-                    }
-#pragma unroll
-                    for (int c = 0; c < D; ++c) xo[c][s] = x[c];
-                }
-#pragma unroll
-                for (int c = 0; c < D; ++c) st_tile(Xp + c * cstride + base, xo[c]);
-                if (pinned && j == i2 && tl == nt - 1) {  // pin the block's right end to x_b
-#pragma unroll
-                    for (int c = 0; c < D; ++c) Xp[c * cstride + base + ((N - 1) & 7)] = xb[c];
-                }
-                if constexpr (MODE == MODE_IMPUTE) {
-#pragma unroll
-                    for (int w = 0; w < M; ++w) st_tile(Wp + w * cstride + base, dwo[w]);
-                }
-#pragma unroll
-                for (int w = 0; w < M; ++w)
-#pragma unroll
-                    for (int s = 0; s < TILE; ++s) dwa[w][s] = dwn[w][s];
-            }
-        } else {
-            // MODE_RELAYOUT / MODE_LOGLIK: walk the accepted path, recover dW, accumulate ll
-            const double *Xa = p.X[sx];
-            double *Wacc = p.W[sw];
-            for (int tl = 0; tl < nt; ++tl) {
-                const size_t tile = toff + tl;
-                const size_t base = (tile * p.C + chain) * TILE;
-                double xa[D][TILE], dwo[M][TILE];
-#pragma unroll
-                for (int c = 0; c < D; ++c) ld_tile(Xa + c * cstride + base, xa[c]);
-                const double *trec = p.table + tile * TILE * R::SIZE;
-#pragma unroll
-                for (int s = 0; s < TILE; ++s) {
+                    double rec[R::SIZE], F[D];
+                    load_rec_smem<R::SIZE>(trec + s * R::SIZE, rec);
+                    guiding_F<D, PSI>(rec, xb, F);
+                    const double dt = rec[0];
+                    const bool live = tl * TILE + s < N;
                     double dw[M];
 #pragma unroll
                     for (int w = 0; w < M; ++w) dw[w] = 0.0;
-                    if (tl * TILE + s < N) {
-                        double rec[R::SIZE];
-                        load_rec<R::SIZE>(trec + s * R::SIZE, rec);
-                        double dr[D], res[D], dll;
-                        guided_terms<MD, PSI>(p.th, rec, xb, aB, abeta, aatil, x, rec[0], dr, dll);
-                        lsum += dll;
+                    if constexpr (NEED_XA) {  // recover the accepted noise increment from the accepted path
+                        if (live) {
+                            if constexpr (FAST) {
+                                double dll, r2;
+                                fk.terms<PSI>(rec, F, xa[0], xa[1], dt, dll, r2);
+                                lsum_a += dll;
+                                const double u = fma(fk.sig2, r2, fma(fk.gam, xa[0], fk.bet - xa[1]));
+                                dw[0] = fma(-u, dt, xat[1][s] - xa[1]) * fk.isig;
+                            } else {
+                                double dr[D], res[D], dll;
+                                guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, xa, dt, dr, dll);
+                                lsum_a += dll;
 #pragma unroll
-                        for (int c = 0; c < D; ++c) res[c] = xa[c][s] - x[c] - dr[c];
-                        MD::sigma_solve(p.th, x, res, dw);
+                                for (int c = 0; c < D; ++c) res[c] = xat[c][s] - xa[c] - dr[c];
+                                MD::sigma_solve(p.th, xa, res, dw);
+                            }
 #pragma unroll
-                        for (int c = 0; c < D; ++c) x[c] = xa[c][s];
+                            for (int c = 0; c < D; ++c) xa[c] = xat[c][s];
+                        }
+                    } else if constexpr (NEED_WA) {
+#pragma unroll
+                        for (int w = 0; w < M; ++w) dw[w] = dwa[w][s];
+                    }
+                    if constexpr (MODE == MODE_IMPUTE) {  // pCN: W deg = sqrt(1-rho^2) W_fresh + rho W
+#pragma unroll
+                        for (int w = 0; w < M; ++w) dw[w] = lam * (rec[1] * z[w][s]) + rho * dw[w];
                     }
 #pragma unroll
                     for (int w = 0; w < M; ++w) dwo[w][s] = dw[w];
-                }
-                if constexpr (MODE == MODE_RELAYOUT) {
+                    if constexpr (SOLVE) {
+                        if (live) {
+                            if constexpr (FAST) {
+                                double dll, r2;
+                                fk.terms<PSI>(rec, F, x[0], x[1], dt, dll, r2);
+                                lsum += dll;
+                                const double y3 = (x[0] * x[0]) * x[0];
+                                const double wy = (x[0] - y3) + (fk.s - x[1]);
+                                const double u = fma(fk.sig2, r2, fma(fk.gam, x[0], fk.bet - x[1]));
+                                const double ynew = fma(wy, dt * fk.ie, x[0]);
+                                x[1] = fma(u, dt, fma(fk.sig, dw[0], x[1]));
+                                x[0] = ynew;
+                            } else {
+                                double dr[D], sdw[D], dll;
+                                guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, dt, dr, dll);
+                                lsum += dll;
+                                MD::sigma_mul(p.th, x, dw, sdw);
 #pragma unroll
-                    for (int w = 0; w < M; ++w) st_tile(Wacc + w * cstride + base, dwo[w]);
+                                for (int c = 0; c < D; ++c) x[c] = x[c] + dr[c] + sdw[c];
+                                ok = ok && MD::bound_ok(x);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < D; ++c) xo[c][s] = x[c];
+                    }
+                }
+                if (active) {
+                    if constexpr (SOLVE) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) st_tile(Xp + c * cstride + base, xo[c]);
+                        if (pinned && j == i2 && tl == nt - 1) {  // pin the block's right end to x_b
+#pragma unroll
+                            for (int c = 0; c < D; ++c) Xp[c * cstride + base + ((N - 1) & 7)] = xb[c];
+                        }
+                    }
+                    if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
+                        double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
+#pragma unroll
+                        for (int w = 0; w < M; ++w) st_tile(Wdst + w * cstride + base, dwo[w]);
+                    }
                 }
             }
         }
         llp += lsum;
+        lla += lsum_a;
     }
     if (!ok) llp = -INFINITY;
 
     if constexpr (MODE == MODE_IMPUTE) {
-        double llcur = p.ll[uo];
+        if (!in_range) return;
+        if (masked) {
+            for (int j = i1; j <= i2; ++j) {
+                const size_t o = (size_t)j * p.C + chain;
+                p.selX_out[o] = p.selX_in[o];
+                p.selW_out[o] = p.selW_in[o];
+            }
+            return;
+        }
+        double llcur = REINV ? lla : p.ll[uo];
         const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)i1, gchain) : p.E[uo];
         // accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!)
         const bool acc = p.force_accept ? ok : (e > -(llp - llcur));
         for (int j = i1; j <= i2; ++j) {  // swap_paths!: flip the accepted-container selectors
             const size_t o = (size_t)j * p.C + chain;
             p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
-            p.selW_out[o] = p.selW_in[o] ^ (uint8_t)acc;
+            p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && p.store_w);
         }
         if (acc) {
             llcur = llp;
-            p.ll[uo] = llp;
             if (p.acc_count) atomicAdd(p.acc_count + blk, 1ULL);
         }
+        p.ll[uo] = llcur;
         if (p.prop_count && chain == 0) atomicAdd(p.prop_count + blk, (unsigned long long)p.C);
-        if (p.out_llprop) p.out_llprop[uo] = llp;
-        if (p.out_ll) p.out_ll[uo] = llcur;
-        if (p.out_acc) p.out_acc[uo] = (uint8_t)acc;
+        if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = llp;
+        if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = llcur;
+        if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = (uint8_t)acc;
     } else if constexpr (MODE == MODE_PARAM) {
+        if (!in_range) return;
         if (p.out_llprop) p.out_llprop[uo] = llp;
         if (p.out_acc) p.out_acc[uo] = (uint8_t)ok;
     } else {
-        p.ll[uo] = llp;
+        if (in_range) p.ll[uo] = lla;
     }
 }
 
 // ---- launch dispatch ---------------------------------------------------------------------------
-template <class MD, bool PSI>
+template <class MD, bool PSI, bool FAST>
 static cudaError_t launch_model(int mode, const SolveParams &p, int threads, cudaStream_t s) {
-    const long long nunits = (long long)p.nblk * p.C;
-    if (nunits == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((nunits + threads - 1) / threads);
-    const bool philox = (p.Z == nullptr);
+    if ((long long)p.nblk * p.C == 0) return cudaSuccess;
+    const unsigned groups = (unsigned)((p.C + threads - 1) / threads);
+    const unsigned grid = groups * (unsigned)p.nblk;
+    const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
+#define DMCMC_LAUNCH(MODE_, PH_, RE_) solve_kernel<MD, PSI, MODE_, PH_, RE_, FAST><<<grid, threads, 0, s>>>(p)
     switch (mode) {
     case MODE_IMPUTE:
-        if (philox) solve_kernel<MD, PSI, MODE_IMPUTE, true><<<grid, threads, 0, s>>>(p);
-        else solve_kernel<MD, PSI, MODE_IMPUTE, false><<<grid, threads, 0, s>>>(p);
+        if (philox) { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, true, true); else DMCMC_LAUNCH(MODE_IMPUTE, true, false); }
+        else        { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, false, true); else DMCMC_LAUNCH(MODE_IMPUTE, false, false); }
         break;
-    case MODE_PARAM: solve_kernel<MD, PSI, MODE_PARAM, false><<<grid, threads, 0, s>>>(p); break;
-    case MODE_RELAYOUT: solve_kernel<MD, PSI, MODE_RELAYOUT, false><<<grid, threads, 0, s>>>(p); break;
-    case MODE_LOGLIK: solve_kernel<MD, PSI, MODE_LOGLIK, false><<<grid, threads, 0, s>>>(p); break;
+    case MODE_PARAM: DMCMC_LAUNCH(MODE_PARAM, false, false); break;
+    case MODE_RELAYOUT: DMCMC_LAUNCH(MODE_RELAYOUT, false, false); break;
+    case MODE_LOGLIK: DMCMC_LAUNCH(MODE_LOGLIK, false, false); break;
     default: return cudaErrorInvalidValue;
     }
+#undef DMCMC_LAUNCH
     return cudaGetLastError();
 }
 
-template <class MD>
+template <class MD, bool FAST = false>
 static cudaError_t launch_psi(int mode, const SolveParams &p, int threads, cudaStream_t s) {
-    return p.has_psi ? launch_model<MD, true>(mode, p, threads, s)
-                     : launch_model<MD, false>(mode, p, threads, s);
+    return p.has_psi ? launch_model<MD, true, FAST>(mode, p, threads, s)
+                     : launch_model<MD, false, FAST>(mode, p, threads, s);
 }
 
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s) {
     switch (model) {
-    case 0: return launch_psi<ModelFHN>(mode, p, threads, s);
+    case 0: return p.fast_ok ? launch_psi<ModelFHN, true>(mode, p, threads, s)
+                             : launch_psi<ModelFHN, false>(mode, p, threads, s);
     case 1: return launch_psi<ModelLV>(mode, p, threads, s);
     case 2: return launch_psi<ModelL63>(mode, p, threads, s);
     case 4: return launch_psi<ModelLIN2>(mode, p, threads, s);

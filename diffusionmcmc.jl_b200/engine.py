@@ -180,6 +180,7 @@ class Engine:
             stride = llp.shape[2]
         self._ck(self.lib.dmcmc_run_sweeps(self.h, it0, n_sweeps, half_len, first_pattern,
                                            _dp(rho_sched), stride, _dp(llp), _dp(ll), _bp(acc)))
+        self._sync_nblk()
 
     def run_imputation(self, it0, n_iters, histories=True):
         hist = None
@@ -213,17 +214,24 @@ class Engine:
         self._ck(self.lib.dmcmc_download_path(self.h, chain, rec, _dp(out)))
         return out
 
+    def _sync_nblk(self):
+        self.nblk = int(self.lib.dmcmc_n_blocks(self.h))
+        return self.nblk
+
     def get_ll(self):
+        self._sync_nblk()
         ll = np.empty((self.C, self.nblk))
         self._ck(self.lib.dmcmc_get_ll(self.h, _dp(ll)))
         return ll
 
     def set_ll(self, ll):
+        self._sync_nblk()
         ll = _f64(ll)
         assert ll.shape == (self.C, self.nblk)
         self._ck(self.lib.dmcmc_set_ll(self.h, _dp(ll)))
 
     def accept_counts(self):
+        self._sync_nblk()
         a, p = np.zeros(self.nblk, np.int64), np.zeros(self.nblk, np.int64)
         self._ck(self.lib.dmcmc_accept_counts(self.h, a.ctypes.data_as(_lib._lp), p.ctypes.data_as(_lib._lp)))
         return a, p

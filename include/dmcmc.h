@@ -149,6 +149,8 @@ int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_ou
 /* Full containers in the reference's per-interval shape (N_j+1 points per interval, duplicated
  * joins): X [n_chains][P][d], W [n_chains][P][m] cumulative.  which: 0 accepted, 1 proposal. */
 int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W);
+/* Number of blocks of the current layout (-1: none). */
+int32_t dmcmc_n_blocks(const dmcmc_ctx *ctx);
 int dmcmc_get_ll(dmcmc_ctx *ctx, double *ll /* [n_chains][nblk] */);
 int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll);
 /* Device-side accept counters per block since the last call (src/adaptation.jl:100-103). */
@@ -162,6 +164,9 @@ int dmcmc_kernel_times(dmcmc_ctx *ctx, double ms[4], int64_t launches[4]);
 int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
 /* Threads per CTA of the solve kernels (32..128, multiple of 32; default 64). */
 int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
+/* Model-specific fused step kernels (FitzHugh-Nagumo with its built-in aux law); on by default.
+ * Off = the generic step for every model (same mathematics, different rounding). */
+int dmcmc_set_fast_step(dmcmc_ctx *ctx, int32_t on);
 
 #ifdef __cplusplus
 }

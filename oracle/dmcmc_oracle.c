@@ -622,8 +622,8 @@ double orc_loglikhd_block(const orc_problem *p, const orc_state *s, int chain, i
  * Counter-based noise (production mode).  Philox4x32-10 (Salmon et al. 2011), pinned by the
  * Random123 known-answer vectors in tests/test_oracle.py.
  *   key = (seed_lo ^ stream, seed_hi)      stream: 0 = Wiener normals, 0x9E3779B9 = accept draw
- *   ctr = ((wcomp << 24) | pair, interval, chain, iter)
- * Each call gives two N(0,1) (Box-Muller on two 53-bit uniforms): steps 2*pair and 2*pair+1.
+ *   ctr = ((wcomp << 24) | quad, interval, chain, iter)
+ * Each call gives four N(0,1) (two single-precision Box-Muller pairs): steps 4*quad .. 4*quad+3.
  * ---------------------------------------------------------------------------------------- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
@@ -642,16 +642,65 @@ static inline double u01_53(uint32_t hi, uint32_t lo) {
     return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-void orc_philox_normal_pair(uint64_t seed, uint32_t iter, uint32_t interval, uint32_t chain,
-                            uint32_t wcomp, uint32_t pair, double *z0, double *z1) {
-    uint32_t ctr[4] = {(wcomp << 24) | pair, interval, chain, iter};
+/* Single-precision Box-Muller written ONLY with IEEE fmaf/mul/add/sqrtf so that the CUDA kernel
+ * (which uses __fmaf_rn/__fmul_rn/__fadd_rn/__fsqrt_rn in the same order) is bit-identical.
+ * The normals carry float resolution (|err| ~ 1e-7), then widen exactly to double; the Euler
+ * recursion itself is FP64.  Polynomials: log1p on [-1/3,1/3] (degree 7 in f^3 Q(f)),
+ * sin(pi r)/r and cos(pi r) on |r| <= 1/4 (degree 3 in r^2), least-squares/Chebyshev fits. */
+static inline void bm_pair_f32(uint32_t oa, uint32_t ob, float *z0, float *z1) {
+    const float u1 = (float)(((oa >> 9) << 1) | 1u) * 0x1p-24f; /* (0,1), exact */
+    const float t = (float)(ob >> 8) * 0x1p-23f;                /* 2*u2 in [0,2), exact */
+    union { float f; uint32_t u; } cv;
+    cv.f = u1;
+    int e = (int)((cv.u >> 23) & 0xffu) - 127;
+    cv.u = (cv.u & 0x7fffffu) | 0x3f800000u;
+    float m = cv.f;
+    if (m > 1.33333337f) { m = m * 0.5f; e += 1; }
+    const float f = m - 1.0f;
+    float q = -0.124298662f;
+    q = fmaf(q, f, 0.134337738f);
+    q = fmaf(q, f, -0.122872368f);
+    q = fmaf(q, f, 0.141169786f);
+    q = fmaf(q, f, -0.16673398f);
+    q = fmaf(q, f, 0.200038359f);
+    q = fmaf(q, f, -0.249999434f);
+    q = fmaf(q, f, 0.333333194f);
+    const float s = f * f, s3 = s * f;
+    const float r = fmaf(q, s3, fmaf(-0.5f, s, f));
+    const float lnu = fmaf((float)e, 0.693147182f, r);
+    const float rad = sqrtf(-2.0f * lnu);
+    const float qf = rintf(t * 2.0f);
+    const int qi = (int)qf;
+    const float r2 = fmaf(-0.5f, qf, t);
+    const float ss = r2 * r2;
+    float sp = fmaf(ss, -0.589076877f, 2.54976702f);
+    sp = fmaf(sp, ss, -5.16770792f);
+    sp = fmaf(sp, ss, 3.14159274f);
+    const float sn = sp * r2;
+    float cp = fmaf(ss, -1.30612838f, 4.05757761f);
+    cp = fmaf(cp, ss, -4.93478823f);
+    cp = fmaf(cp, ss, 1.0f);
+    float sv, cv2;
+    switch (qi & 3) {
+    case 0: sv = sn; cv2 = cp; break;
+    case 1: sv = cp; cv2 = -sn; break;
+    case 2: sv = -sn; cv2 = -cp; break;
+    default: sv = -cp; cv2 = sn; break;
+    }
+    *z0 = rad * cv2;
+    *z1 = rad * sv;
+}
+
+/* One Philox call -> four N(0,1): Euler steps 4*quad .. 4*quad+3 of Wiener component wcomp. */
+void orc_philox_normal4(uint64_t seed, uint32_t iter, uint32_t interval, uint32_t chain,
+                        uint32_t wcomp, uint32_t quad, double *z) {
+    uint32_t ctr[4] = {(wcomp << 24) | quad, interval, chain, iter};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+    float a, b, c, d;
     orc_philox4x32_10(ctr, key, o);
-    double u1 = u01_53(o[0], o[1]), u2 = u01_53(o[2], o[3]);
-    double rad = sqrt(-2.0 * log(u1));
-    double ang = 2.0 * M_PI * u2; /* device uses sincospi(2 u2); agrees to ~1 ulp */
-    *z0 = rad * cos(ang);
-    *z1 = rad * sin(ang);
+    bm_pair_f32(o[0], o[1], &a, &b);
+    bm_pair_f32(o[2], o[3], &c, &d);
+    z[0] = a; z[1] = b; z[2] = c; z[3] = d;
 }
 
 double orc_philox_exponential(uint64_t seed, uint32_t iter, uint32_t first_interval, uint32_t chain) {
@@ -693,11 +742,10 @@ static void impute_unit(const orc_problem *p, orc_state *s, int c, int b, const 
         if (use_philox) {
             zbuf = (double *)realloc(zbuf, sizeof(double) * (size_t)(N + 1) * m);
             for (int w = 0; w < m; ++w)
-                for (int q = 0; 2 * q < N; ++q) {
-                    double z0, z1;
-                    orc_philox_normal_pair(seed, iter, (uint32_t)j, (uint32_t)c, (uint32_t)w, (uint32_t)q, &z0, &z1);
-                    zbuf[(size_t)(2 * q) * m + w] = z0;
-                    if (2 * q + 1 < N) zbuf[(size_t)(2 * q + 1) * m + w] = z1;
+                for (int q = 0; 4 * q < N; ++q) {
+                    double z4[4];
+                    orc_philox_normal4(seed, iter, (uint32_t)j, (uint32_t)c, (uint32_t)w, (uint32_t)q, z4);
+                    for (int i = 0; i < 4 && 4 * q + i < N; ++i) zbuf[(size_t)(4 * q + i) * m + w] = z4[i];
                 }
             z = zbuf;
         } else {

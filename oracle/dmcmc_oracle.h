@@ -132,8 +132,8 @@ int orc_chequerboard_layout(int R, const int32_t *rec_nobs, int half_len, int pa
 
 /* ---- counter-based noise (production mode) ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-void orc_philox_normal_pair(uint64_t seed, uint32_t iter, uint32_t interval, uint32_t chain,
-                            uint32_t wcomp, uint32_t pair, double *z0, double *z1);
+void orc_philox_normal4(uint64_t seed, uint32_t iter, uint32_t interval, uint32_t chain,
+                        uint32_t wcomp, uint32_t quad, double *z);
 double orc_philox_exponential(uint64_t seed, uint32_t iter, uint32_t first_interval,
                               uint32_t chain);
 

@@ -23,7 +23,7 @@ def build(force=False):
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(_SRC), os.path.getmtime(hdr))):
         return _LIB_PATH
-    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-Wall",
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-mfma", "-fopenmp", "-shared", "-fPIC", "-Wall",
            "-o", _LIB_PATH, _SRC, "-lm"]
     subprocess.check_call(cmd)
     return _LIB_PATH
@@ -140,12 +140,11 @@ def philox4x32_10(ctr, key):
     return out
 
 
-def philox_normal_pair(seed, it, interval, chain, wcomp, pair):
-    z0, z1 = C.c_double(), C.c_double()
-    lib().orc_philox_normal_pair(C.c_uint64(seed), C.c_uint32(it), C.c_uint32(interval),
-                                 C.c_uint32(chain), C.c_uint32(wcomp), C.c_uint32(pair),
-                                 C.byref(z0), C.byref(z1))
-    return z0.value, z1.value
+def philox_normal4(seed, it, interval, chain, wcomp, quad):
+    z = np.zeros(4)
+    lib().orc_philox_normal4(C.c_uint64(seed), C.c_uint32(it), C.c_uint32(interval),
+                             C.c_uint32(chain), C.c_uint32(wcomp), C.c_uint32(quad), _d(z))
+    return z
 
 
 def philox_exponential(seed, it, first_interval, chain):

@@ -18,9 +18,13 @@ def test_philox_known_answers(orc):
 
 
 def test_philox_normals_are_standard(orc):
-    z = np.array([orc.philox_normal_pair(42, 3, j, c, 0, q) for j in range(4) for c in range(50)
+    z = np.array([orc.philox_normal4(42, 3, j, c, 0, q) for j in range(4) for c in range(50)
                   for q in range(25)]).ravel()
-    assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    # the single-precision Box-Muller is a faithful normal: compare quantiles with the exact ones
+    from scipy.stats import norm, kstest
+    assert kstest(z, "norm").pvalue > 1e-3
+    assert abs(np.mean(z ** 4) - 3.0) < 0.25
     e = np.array([orc.philox_exponential(42, it, 0, c) for it in range(40) for c in range(50)])
     assert abs(e.mean() - 1.0) < 0.06 and e.min() > 0
 
