@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 N_OBS, N_CHAINS, DT, RHO, HALF_LEN = 100, 1024, 1e-3, 0.96, 1
 BYTES_PER_STEP = 32  # FHN: read W (8m) + write W deg (8m) + write X deg (8d), m=1 d=2
 METRIC, UNIT = "bridge path-steps/sec", "path-steps/s"
+CPU_SAMPLE_CHAINS, CPU_SAMPLE_SWEEPS = 512, 24  # ~1.2e8 path-steps: 10-30 s of CPU work over the host cores
 
 
 def measured_peak():
@@ -113,10 +114,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_chains = 64
+    # bounded sample: probe the rate on 64 chains, then size the per-step sample so that the whole
+    # --steps K run takes about a minute of wall time (between 16 and 512 of the 1024 chains)
+    pkg, probe = make_spec(64)
+    rate0, _ = cpu_oracle_rate(probe, max(1, min(args.warmup, 2)), cores, pkg)
+    per_chain = N_OBS * 100
+    sample_chains = int(min(512, max(16, (60.0 * rate0 / (args.steps * per_chain)) // 16 * 16)))
     pkg, spec = make_spec(sample_chains)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_rate(spec, 1, cores, pkg)
     rate, secs = cpu_oracle_rate(spec, args.steps, cores, pkg)
     ms = secs / args.steps * 1e3
     sample = (f"{sample_chains} of {N_CHAINS} chains x {N_OBS} obs x 100 steps, {args.steps} sweeps "
@@ -146,8 +150,8 @@ def workload_config():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -185,18 +189,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput (value) ----------------
-    runner.run_device(0, args.warmup)
-    eng.kernel_ms()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    runner.run_device(0, args.warmup)
+    # keep the GPU under the bench's own load while nvidia-smi starts sampling
+    runner.run_device(args.warmup, max(args.warmup, min(args.steps, 2000)))
+    eng.kernel_ms()
+    barrier()
     t0 = time.perf_counter()
-    runner.run_device(args.warmup, args.steps)
+    runner.run_device(100_000, args.steps)
     barrier()
     elapsed = time.perf_counter() - t0
     kern = runner.kernel_breakdown()
     # ---------------- end to end through the host API (e2e) ----------------
+    runner.reserve_host(args.steps)  # pinned host buffers are allocated outside the timed region
     runner.run_host(10_000, args.warmup)
     barrier()
     t1 = time.perf_counter()
@@ -236,12 +243,13 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            _, small = make_spec(64)
-            rate, secs = cpu_oracle_rate(small, 4, cores, pkg)
+            _, small = make_spec(CPU_SAMPLE_CHAINS)
+            rate, secs = cpu_oracle_rate(small, CPU_SAMPLE_SWEEPS, cores, pkg)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"64 of {N_CHAINS} chains x {N_OBS} obs x 100 steps, 4 sweeps (relayout + impute), "
-                          f"{secs:.1f} s, oracle/dmcmc_oracle.c with OpenMP over (chain, block) units"}
+                "sample": f"{CPU_SAMPLE_CHAINS} of {N_CHAINS} chains x {N_OBS} obs x 100 steps, "
+                          f"{CPU_SAMPLE_SWEEPS} sweeps (relayout + impute), {secs:.1f} s wall, "
+                          f"oracle/dmcmc_oracle.c with OpenMP over (chain, block) units"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -316,13 +316,20 @@ class ImputationRunner:
         self.e.run_sweeps(it0, n, self.half_len, self.sweeps & 1)
         self.sweeps += n
 
-    def run_host(self, it0, n):
+    def reserve_host(self, n):
+        """Pinned host buffers for n sweeps of rho schedule and history rows (allocated once)."""
         e = self.e
-        if self._host is None or self._host[0].shape[0] != n:
+        if self._host is None or self._host[0].shape[0] < n:
             self._host = (e.pinned((n, e.J), np.float64), e.pinned((n, e.C, self.stride), np.float64),
                           e.pinned((n, e.C, self.stride), np.float64),
                           e.pinned((n, e.C, self.stride), np.uint8))
-        rho, llp, ll, acc = self._host
+            for a in self._host:
+                a[...] = 0  # touch the pages
+
+    def run_host(self, it0, n):
+        e = self.e
+        self.reserve_host(n)
+        rho, llp, ll, acc = (a[:n] for a in self._host)
         rho[...] = self.rho
         e.run_sweeps(it0, n, self.half_len, self.sweeps & 1, rho, (llp, ll, acc))
         self.sweeps += n
