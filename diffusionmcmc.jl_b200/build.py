@@ -9,7 +9,7 @@ SOURCES = ["dmcmc_capi.cu", "dmcmc_solve.cu", "dmcmc_bf.cu"]
 HEADERS = ["dmcmc_device.cuh", "dmcmc_internal.h", "dmcmc_models.cuh",
            os.path.join("..", "..", "include", "dmcmc.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared"] + os.environ.get("DMCMC_NVCC_EXTRA", "").split()
 
 
 def _stale():
