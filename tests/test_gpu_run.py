@@ -1,0 +1,76 @@
+"""`run_` (the reference's `run!`) end to end on the GPU: smoothing, adaptation, blocking,
+parameter inference.  Statistical sanity mirrors the docs' informal acceptance tests
+(docs/src/tutorials/simple_inference.md:105-117, :160-161, :189-192)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_smoothing_like_the_tutorial(pkg):
+    data = pkg.problems.fhn_spec(n_obs=100, C=1, dt=1e-3, rho=0.96)
+    mcmc = pkg.MCMC([pkg.PathImputation(0.96, "FitzHughNagumoAux")], backend=pkg.DiffusionMCMCBackend())
+    gws, lws = pkg.run_(mcmc, 1000, data, None, path_buffer_size=10, seed=3)
+    acc = lws[0].acceptance_history           # [iter][block]
+    assert acc.shape == (1000, 1)
+    assert 0.05 < acc.mean() < 0.95
+    ll = lws[0].ll_history
+    assert np.all(np.isfinite(ll)) and ll[-1, 0] > ll[0, 0] - 50
+    xs = gws.XX_buffer.XX                     # ring of 10 glued paths, saved every 100 iterations
+    assert len(xs) == 10 and xs[0][0]["x"].shape == (100 * 100 + 1, 2)
+    assert np.allclose(xs[0][0]["t"][[0, -1]], [0.0, 10.0])
+    # the smoothed first coordinate follows the observations (sd 0.1)
+    v = data["obs_v"][:, 0]
+    at_obs = xs[9][0]["x"][100::100, 0]
+    assert np.sqrt(np.mean((at_obs - v) ** 2)) < 0.3
+    # consecutive saved paths differ (the chain moves)
+    assert not np.array_equal(xs[8][0]["x"], xs[9][0]["x"])
+
+
+def test_adaptation_moves_rho_towards_the_target(pkg):
+    """docs: rho = 0.1 never accepts (0.0); adaptation drives rho up to ~0.95 and the rate to ~0.23."""
+    data = pkg.problems.fhn_spec(n_obs=50, C=1, dt=1e-3)
+    fixed = pkg.MCMC([pkg.PathImputation(0.1, "FitzHughNagumoAux")])
+    _, lws = pkg.run_(fixed, 300, data, None, seed=1)
+    assert lws[0].acceptance_history.mean() < 0.02
+    adpt = pkg.AdaptationPathImputation(adapt_every_k_steps=50, scale=1.0, offset=0.0)
+    u = pkg.PathImputation(0.1, "FitzHughNagumoAux", adpt=adpt)
+    _, lws = pkg.run_(pkg.MCMC([u]), 3000, data, None, seed=1)
+    assert u.rho_s[0][0] > 0.8
+    assert 0.08 < lws[0].acceptance_history[-500:].mean() < 0.6
+
+
+def test_blocked_smoothing_matches_unblocked_in_distribution(pkg):
+    """Chequerboard blocking (ours; the reference has only the decorator) targets the same
+    smoothing distribution: posterior means of the path agree with the unblocked sampler."""
+    data = pkg.problems.fhn_spec(n_obs=20, C=256, dt=2e-3, rho=0.9, pin_eps=1e-4)
+    un = pkg.MCMC([pkg.PathImputation(0.9, "FitzHughNagumoAux")])
+    bl = pkg.MCMC([pkg.BlockingChequerboardSwitch(2), pkg.PathImputation(0.9, "FitzHughNagumoAux"),
+                   pkg.BlockingChequerboardSwitch(2), pkg.PathImputation(0.9, "FitzHughNagumoAux")])
+    g1, l1 = pkg.run_(un, 400, data, None, n_chains=256, seed=11)
+    g2, l2 = pkg.run_(bl, 400, data, None, n_chains=256, seed=12)
+    assert l2[0].acceptance_history.shape == (400, 256, 5) and l2[1].acceptance_history.shape == (400, 256, 6)
+    assert l2[0].acceptance_history.mean() > 0.1
+    X1, _ = g1.engine.download_state(0)
+    X2, _ = g2.engine.download_state(0)
+    m1, m2 = X1.mean(axis=0), X2.mean(axis=0)
+    s1 = X1.std(axis=0)
+    # means over 256 independent chains: agree within a few standard errors (+ pin_eps softness)
+    err = np.abs(m1 - m2) / (s1 / np.sqrt(256) * 2 ** 0.5 + 0.02)
+    assert np.quantile(err, 0.99) < 6.0, np.quantile(err, [0.5, 0.9, 0.99, 1.0])
+
+
+def test_parameter_inference_recovers_gamma(pkg):
+    """PathImputation + RandomWalkUpdate on one drift parameter (config 2 pattern): the chain
+    moves from a wrong start towards the data-generating value."""
+    data = pkg.problems.fhn_spec(n_obs=100, C=1, dt=2e-3, rho=0.95)
+    th0 = data["theta"].copy()
+    th0[2] = 1.0  # gamma, truth 1.5
+    mcmc = pkg.MCMC([pkg.PathImputation(0.95, "FitzHughNagumoAux"),
+                     pkg.RandomWalkUpdate(0.1, [2])])
+    gws, lws = pkg.run_(mcmc, 1500, data, th0, seed=5)
+    th = np.array(gws.state_history)
+    assert th.shape == (1500, 5)
+    assert lws[1].acceptance_history.mean() > 0.02
+    assert abs(th[-500:, 2].mean() - 1.5) < 0.35, th[-500:, 2].mean()
+    assert np.all(th[:, [0, 1, 3, 4]] == th0[[0, 1, 3, 4]])
