@@ -13,11 +13,12 @@ _lp = C.POINTER(C.c_int64)
 
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("model", C.c_int32), ("d", C.c_int32),
-                ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("device", C.c_int32),
+                ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("interval_offset", C.c_int32),
+                ("device", C.c_int32),
                 ("seed", C.c_uint64), ("pin_eps", C.c_double)]
 
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); every symbol include/dmcmc.h declares
 SYMBOLS = {
@@ -47,6 +48,9 @@ SYMBOLS = {
     "dmcmc_param_commit": (C.c_int, [C.c_void_p, C.c_int32]),
     "dmcmc_download_path": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "dmcmc_download_state": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
+    "dmcmc_set_block_mask": (C.c_int, [C.c_void_p, _ip]),
+    "dmcmc_download_segment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "dmcmc_upload_segment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "dmcmc_n_blocks": (C.c_int32, [C.c_void_p]),
     "dmcmc_get_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_set_ll": (C.c_int, [C.c_void_p, _dp]),

@@ -51,7 +51,8 @@ struct Layout {
     std::vector<int32_t> i1, i2, pinned, iv_blk;
     int32_t nblk = 0;
     bool has_psi = false;
-    DevBuf<int32_t> d_i1, d_i2, d_pinned, d_iv_blk;
+    DevBuf<int32_t> d_i1, d_i2, d_pinned, d_iv_blk, d_active;
+    bool has_mask = false;
     Tables tab[2];  // per law slot
     uint64_t last_used = 0;
     bool used = false;
@@ -85,7 +86,7 @@ struct dmcmc_ctx {
     int lay_cur = -1;
     uint64_t lay_clock = 0;
     // device
-    DevBuf<int32_t> d_N, d_tile_off, d_first, d_rec, d_pt_off;
+    DevBuf<int32_t> d_N, d_tile_off, d_first, d_rec, d_pt_off, d_st_off;
     DevBuf<double> d_t, d_rho, d_Hobs, d_Fobs, d_cobs, d_x0, d_ll, d_Z, d_E;
     DevBuf<double> d_X[2], d_W[2];
     DevBuf<uint8_t> d_selX[2], d_selW[2], d_mask, d_out_acc;
@@ -295,10 +296,12 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     REQUIRE(ctx->have_grid && ctx->have_start, "grid / starting points missing");
     Layout &lay = ctx->layout[ctx->lay_cur];
     Tables &tb = lay.tab[slot];
-    REQUIRE(tb.valid, "backward-filter tables missing: call dmcmc_backward_filter / dmcmc_upload_tables");
+    if (!tb.valid && run_backward_filter(ctx, slot)) return -1;  // tables follow the layout lazily
     Law &law = ctx->law[slot];
     sp = SolveParams{};
     sp.C = ctx->C; sp.nblk = lay.nblk; sp.J = ctx->J; sp.chain_offset = ctx->cfg.chain_offset;
+    sp.interval_offset = ctx->cfg.interval_offset;
+    sp.blk_active = lay.has_mask ? lay.d_active.p : nullptr;
     sp.TT = ctx->TT;
     sp.blk_i1 = lay.d_i1.p; sp.blk_i2 = lay.d_i2.p; sp.blk_pinned = lay.d_pinned.p;
     sp.iv_N = ctx->d_N.p; sp.iv_tile_off = ctx->d_tile_off.p; sp.iv_first = ctx->d_first.p;
@@ -400,7 +403,8 @@ int select_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t
         REQUIRE(i1[b] == expect && i2[b] >= i1[b] && i2[b] < ctx->J, "dmcmc_set_layout: blocks must partition the intervals in order");
         REQUIRE(ctx->iv_rec[i1[b]] == ctx->iv_rec[i2[b]], "dmcmc_set_layout: a block straddles two recordings");
         const bool last_of_rec = (i2[b] == ctx->J - 1) || ctx->iv_first[i2[b] + 1];
-        REQUIRE(!(pinned[b] && last_of_rec) , "dmcmc_set_layout: the last block of a recording cannot be pinned");
+        // a pinned LAST block is allowed: it is the halo of a recording sharded over GPUs (its end
+        // point is conditioned on the value the right neighbour holds)
         REQUIRE(pinned[b] || last_of_rec, "dmcmc_set_layout: an interior block must be pinned");
         expect = i2[b] + 1;
     }
@@ -430,6 +434,7 @@ int select_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t
         upload(ctx, l.d_iv_blk, l.iv_blk))
         return -1;
     l.tab[0].valid = l.tab[1].valid = false;
+    l.has_mask = false;
     l.last_used = ++ctx->lay_clock;
     ctx->lay_cur = s;
     return 0;
@@ -488,14 +493,14 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     rel_law(ctx->law[0]);
     rel_law(ctx->law[1]);
     for (auto &l : ctx->layout) {
-        l.d_i1.release(); l.d_i2.release(); l.d_pinned.release(); l.d_iv_blk.release();
+        l.d_i1.release(); l.d_i2.release(); l.d_pinned.release(); l.d_iv_blk.release(); l.d_active.release();
         for (auto &t : l.tab) {
             t.table.release(); t.blk_c0.release(); t.blk_g.release(); t.blk_Qc.release();
             t.ptH.release(); t.ptF0.release(); t.ptPsi.release(); t.ptc0.release();
         }
     }
     ctx->d_N.release(); ctx->d_tile_off.release(); ctx->d_first.release(); ctx->d_rec.release();
-    ctx->d_pt_off.release(); ctx->d_t.release(); ctx->d_rho.release(); ctx->d_Hobs.release();
+    ctx->d_pt_off.release(); ctx->d_st_off.release(); ctx->d_t.release(); ctx->d_rho.release(); ctx->d_Hobs.release();
     ctx->d_Fobs.release(); ctx->d_cobs.release(); ctx->d_x0.release(); ctx->d_ll.release();
     ctx->d_Z.release(); ctx->d_E.release();
     for (int b = 0; b < 2; ++b) {
@@ -548,7 +553,8 @@ int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs
             REQUIRE(t[ctx->pt_off[j] + k + 1] > t[ctx->pt_off[j] + k], "dmcmc_set_grid: grid times must increase");
     if (upload(ctx, ctx->d_N, ctx->N) || upload(ctx, ctx->d_tile_off, ctx->tile_off) ||
         upload(ctx, ctx->d_first, ctx->iv_first) || upload(ctx, ctx->d_rec, ctx->iv_rec) ||
-        upload(ctx, ctx->d_pt_off, ctx->pt_off) || upload(ctx, ctx->d_t, ctx->t))
+        upload(ctx, ctx->d_pt_off, ctx->pt_off) || upload(ctx, ctx->d_st_off, ctx->st_off) ||
+        upload(ctx, ctx->d_t, ctx->t))
         return -1;
     ctx->rho.assign(J, 0.0);
     if (upload(ctx, ctx->d_rho, ctx->rho)) return -1;
@@ -588,6 +594,7 @@ int dmcmc_set_start(dmcmc_ctx *ctx, const double *x0) {
             for (int i = 0; i < d; ++i) tr[((size_t)r * d + i) * C + c] = x0[((size_t)c * R + r) * d + i];
     if (upload(ctx, ctx->d_x0, tr)) return -1;
     ctx->have_start = true;
+    ctx->w_valid = false;
     return sync(ctx);
 }
 
@@ -647,6 +654,51 @@ int dmcmc_set_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int3
     if (resize_ll(ctx)) return -1;
     if (before != ctx->lay_cur) ctx->w_valid = false;
     return sync(ctx);
+}
+
+int dmcmc_set_block_mask(dmcmc_ctx *ctx, const int32_t *active) {
+    REQUIRE(ctx && ctx->lay_cur >= 0, "dmcmc_set_block_mask: no layout set");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Layout &l = ctx->layout[ctx->lay_cur];
+    if (!active) {
+        l.has_mask = false;
+        return 0;
+    }
+    std::vector<int32_t> a(active, active + l.nblk);
+    if (upload(ctx, l.d_active, a)) return -1;
+    l.has_mask = true;
+    return sync(ctx);
+}
+
+static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool up) {
+    REQUIRE(ctx && X && j0 >= 0 && j1 > j0 && j1 <= ctx->J, "segment: bad interval range");
+    REQUIRE(ctx->have_grid, "segment: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int steps = ctx->st_off[j1] - ctx->st_off[j0];
+    const size_t n = (size_t)ctx->C * steps * ctx->d;
+    DevBuf<double> pk;
+    CK(pk.ensure(n));
+    if (up) CK(cudaMemcpyAsync(pk.p, X, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SegmentParams g{};
+    g.C = ctx->C; g.D = ctx->d; g.j0 = j0; g.j1 = j1; g.steps = steps; g.TT = ctx->TT;
+    g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_st_off = ctx->d_st_off.p;
+    g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
+    g.selX = ctx->d_selX[ctx->sel_cur].p;
+    g.packed = pk.p; g.upload = up;
+    CK(launch_segment(g, ctx->stream));
+    if (!up) CK(cudaMemcpyAsync(X, pk.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    pk.release();
+    if (up) ctx->w_valid = false;
+    return 0;
+}
+
+int dmcmc_download_segment(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X) {
+    return segment_copy(ctx, j0, j1, X, false);
+}
+
+int dmcmc_upload_segment(dmcmc_ctx *ctx, int32_t j0, int32_t j1, const double *X) {
+    return segment_copy(ctx, j0, j1, const_cast<double *>(X), true);
 }
 
 int dmcmc_set_rho(dmcmc_ctx *ctx, const double *rho) {

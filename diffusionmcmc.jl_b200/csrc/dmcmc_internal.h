@@ -17,10 +17,11 @@ enum SolveMode {
 // Everything a solve kernel needs.  Pointers are device pointers.
 struct SolveParams {
     int32_t C, nblk, J;
-    int32_t chain_offset;
+    int32_t chain_offset, interval_offset;
     int64_t TT;  // total tiles over all intervals
     // layout
     const int32_t *blk_i1, *blk_i2, *blk_pinned;
+    const int32_t *blk_active;  // nullptr: every block is updated
     // intervals
     const int32_t *iv_N, *iv_tile_off, *iv_first, *iv_rec;
     const double *rho;      // [J]
@@ -79,6 +80,18 @@ struct GatherParams {
     int64_t P;
 };
 cudaError_t launch_gather(const GatherParams &g, cudaStream_t s);
+
+// halo exchange of a block-sharded recording: accepted X of intervals [j0, j1), packed [C][steps][D]
+struct SegmentParams {
+    int32_t C, D, j0, j1, steps;
+    int64_t TT;
+    const int32_t *iv_N, *iv_tile_off, *iv_st_off;
+    double *X[2];
+    const uint8_t *selX;
+    double *packed;   // device [C][steps][D]
+    int32_t upload;   // 0: X -> packed, 1: packed -> X
+};
+cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s);
 
 // noise transposition [C][S][M] -> [M][TT][C][8] is done on the host in the C-ABI layer.
 

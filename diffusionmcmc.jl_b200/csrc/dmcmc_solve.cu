@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     const int chain = in_range ? chain_raw : p.C - 1;  // out-of-range lanes shadow the last chain, stores off
     const size_t uo = (size_t)chain * p.nblk + blk;    // [C][nblk] host layout of ll
     const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
-    const bool masked = (MODE == MODE_IMPUTE) && p.unit_mask && !p.unit_mask[uo];
+    const bool masked = (MODE == MODE_IMPUTE) && ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
     const bool active = in_range && !masked;
 
     if (threadIdx.x == 0) {
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                         for (int w = 0; w < M; ++w)
 #pragma unroll
                             for (int h = 0; h < TILE / 4; ++h)
-                                philox_normal4(p.seed, p.iter, (uint32_t)j, gchain, (uint32_t)w,
+                                philox_normal4(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w,
                                                (uint32_t)(tl * (TILE / 4) + h), &z[w][4 * h]);
                     } else {
 #pragma unroll
@@ -457,10 +457,16 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                 p.selX_out[o] = p.selX_in[o];
                 p.selW_out[o] = p.selW_in[o];
             }
+            if (p.blk_active && !p.blk_active[blk]) {  // block owned by a neighbouring shard
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = nan;
+                if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = nan;
+                if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = 0;
+            }
             return;
         }
         double llcur = REINV ? lla : p.ll[uo];
-        const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)i1, gchain) : p.E[uo];
+        const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain) : p.E[uo];
         // accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!)
         const bool acc = p.force_accept ? ok : (e > -(llp - llcur));
         for (int j = i1; j <= i2; ++j) {  // swap_paths!: flip the accepted-container selectors
@@ -561,6 +567,41 @@ __global__ void gather_kernel(const GatherParams g) {
         for (int w = 0; w < g.M; ++w)
             g.outW[(pt0 + k + 1) * g.M + w] = g.outW[(pt0 + k) * g.M + w] + g.W[sw][w * cs + e];
     }
+}
+
+__global__ void segment_kernel(const SegmentParams g) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nj = g.j1 - g.j0;
+    if (u >= (long long)nj * g.C) return;
+    const int j = g.j0 + (int)(u / g.C), chain = (int)(u % g.C);
+    const size_t cs = (size_t)g.TT * g.C * TILE;
+    double *X = g.X[g.selX[(size_t)j * g.C + chain]];
+    const int off = g.iv_st_off[j] - g.iv_st_off[g.j0];
+    for (int k = 0; k < g.iv_N[j]; ++k) {
+        const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
+        const size_t e = (tile * g.C + chain) * TILE + (k & 7);
+        for (int c = 0; c < g.D; ++c) {
+            double *pk = g.packed + ((size_t)chain * g.steps + off + k) * g.D + c;
+            if (g.upload) X[c * cs + e] = *pk;
+            else *pk = X[c * cs + e];
+        }
+    }
+    if (g.upload) {  // pad slots repeat the last value (they are no-ops for the solve kernels)
+        const int N = g.iv_N[j];
+        for (int k = N; k < ((N + TILE - 1) / TILE) * TILE; ++k) {
+            const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
+            const size_t e = (tile * g.C + chain) * TILE + (k & 7);
+            for (int c = 0; c < g.D; ++c)
+                X[c * cs + e] = g.packed[((size_t)chain * g.steps + off + N - 1) * g.D + c];
+        }
+    }
+}
+
+cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s) {
+    const long long n = (long long)(g.j1 - g.j0) * g.C;
+    if (n <= 0) return cudaSuccess;
+    segment_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gather(const GatherParams &g, cudaStream_t s) {

@@ -39,7 +39,7 @@ class DmcmcError(RuntimeError):
 
 
 class Engine:
-    def __init__(self, spec, device=0, seed=0, chain_offset=0, n_chains=None):
+    def __init__(self, spec, device=0, seed=0, chain_offset=0, n_chains=None, interval_offset=0):
         self.lib = _lib.load()
         self.spec = spec
         self.model, self.d, self.m = int(spec["model"]), int(spec["d"]), int(spec["m"])
@@ -48,7 +48,7 @@ class Engine:
             x0 = x0[chain_offset:chain_offset + n_chains] if x0.shape[0] >= chain_offset + n_chains \
                 else np.broadcast_to(x0[:1], (n_chains,) + x0.shape[1:]).copy()
         self.C = x0.shape[0]
-        cfg = _lib.Config(_lib.ABI_VERSION, self.model, self.d, self.C, chain_offset, device,
+        cfg = _lib.Config(_lib.ABI_VERSION, self.model, self.d, self.C, chain_offset, interval_offset, device,
                           seed, float(spec.get("pin_eps", 1e-4)))
         h = C.c_void_p()
         if self.lib.dmcmc_create(C.byref(cfg), C.byref(h)) != 0:
@@ -118,6 +118,30 @@ class Engine:
         self.nblk = len(self.blk_i1)
         self._ck(self.lib.dmcmc_relayout(self.h, self.nblk, _ip(self.blk_i1), _ip(self.blk_i2),
                                          _ip(self.blk_pinned)))
+
+    def set_block_mask(self, active):
+        if active is None:
+            self._ck(self.lib.dmcmc_set_block_mask(self.h, None))
+        else:
+            a = _i32(active)
+            assert len(a) == self.nblk
+            self._ck(self.lib.dmcmc_set_block_mask(self.h, _ip(a)))
+
+    def set_start(self, x0):
+        x0 = _f64(x0)
+        assert x0.shape == (self.C, self.R, self.d)
+        self._ck(self.lib.dmcmc_set_start(self.h, _dp(x0)))
+
+    def download_segment(self, j0, j1):
+        n = int(self.N[j0:j1].sum())
+        X = np.empty((self.C, n, self.d))
+        self._ck(self.lib.dmcmc_download_segment(self.h, j0, j1, _dp(X)))
+        return X
+
+    def upload_segment(self, j0, j1, X):
+        X = _f64(X)
+        assert X.shape == (self.C, int(self.N[j0:j1].sum()), self.d)
+        self._ck(self.lib.dmcmc_upload_segment(self.h, j0, j1, _dp(X)))
 
     def backward_filter(self, which=0):
         self._ck(self.lib.dmcmc_backward_filter(self.h, which))

@@ -1,0 +1,257 @@
+"""Multi-GPU decomposition of the imputation path.
+
+Two ways the path shards, both one process/context per GPU:
+
+* chains: independent, no collective at all -- every rank builds its `Engine` with
+  `chain_offset = rank * chains_per_rank` (Philox streams are keyed by the GLOBAL chain index, so
+  the union of the shards is bit-identical to one big context).  See `shard_chains`.
+
+* blocks of one long recording (BASELINE config 4): rank r owns the contiguous interval range
+  [a_r, a_{r+1}) whose ends are chequerboard delimiters of pattern A.  Blocks of pattern A never
+  cross a rank edge.  Blocks of pattern B straddle it, so every rank but the last also holds a
+  halo copy of the next h intervals and updates the straddling block itself; after each sweep the
+  freshly imputed half is exchanged with the neighbour:
+      after sweep A : rank r+1 -> r   its first h intervals        (h*N*d doubles per chain)
+      after sweep B : rank r   -> r+1 the halo + the edge point x(t_{a_{r+1}})
+  These are the "block-boundary endpoint exchange" messages of the north star: a few KB, latency
+  bound, sent with NCCL send/recv (gloo in the CPU tests).  Philox counters use the GLOBAL interval
+  index (`interval_offset`), and each block's backward-filter table depends only on the block's own
+  observations, so a sharded run reproduces the single-GPU run bit for bit.
+"""
+import numpy as np
+
+
+def shard_chains(n_chains, world):
+    """[(offset, count)] per rank: contiguous, sizes differing by at most one."""
+    base, rem = divmod(n_chains, world)
+    out, off = [], 0
+    for r in range(world):
+        c = base + (1 if r < rem else 0)
+        out.append((off, c))
+        off += c
+    return out
+
+
+def shard_intervals(n_intervals, world, half_len):
+    """Rank edges a_0=0 < a_1 < ... < a_world = n, every interior edge a multiple of 2*half_len."""
+    unit = 2 * half_len
+    nunits = n_intervals // unit
+    if nunits < world:
+        raise ValueError("too few chequerboard blocks for this many ranks")
+    edges = [0]
+    for r in range(1, world):
+        edges.append((nunits * r // world) * unit)
+    edges.append(n_intervals)
+    return edges
+
+
+def local_spec(spec, a, b_ext, x_start):
+    """Sub-problem on intervals [a, b_ext) of a single-recording spec, starting from x_start [C][d]."""
+    N = np.asarray(spec["N"])
+    pt_off = np.concatenate([[0], np.cumsum(N + 1)])
+    out = dict(spec)
+    out["N"] = N[a:b_ext].copy()
+    out["t"] = np.asarray(spec["t"])[pt_off[a]:pt_off[b_ext]].copy()
+    rf = np.zeros(b_ext - a, np.int32)
+    rf[0] = 1
+    out["rec_first"] = rf
+    for k in ("obs_L", "obs_Sigma", "obs_v", "rho"):
+        out[k] = np.asarray(spec[k])[a:b_ext].copy()
+    out["x0"] = np.asarray(x_start, float)[:, None, :].copy()
+    return out
+
+
+def local_layouts(a, b, b_ext, n, half_len, rank):
+    """Local (0-based from a) block ranges, pinned flags and activity masks of the two patterns."""
+    h = half_len
+    lays = []
+    for pattern in (0, 1):
+        i1, i2, pin, act = [], [], [], []
+        start = a
+        if pattern == 1:  # first (half) block [a, a+h): the true first block on rank 0, else owned by the left rank
+            i1.append(a), i2.append(min(a + h, n) - 1), act.append(1 if rank == 0 else 0)
+            start = min(a + h, n)
+        limit = b if pattern == 0 else b_ext
+        while start < limit:
+            end = min(start + 2 * h, n)
+            if pattern == 0:
+                end = min(end, b)
+            i1.append(start), i2.append(end - 1), act.append(1)
+            start = end
+        if pattern == 0 and b_ext > b:  # halo filler, updated by the right neighbour in pattern A
+            i1.append(b), i2.append(b_ext - 1), act.append(0)
+        i1, i2 = np.array(i1, np.int32), np.array(i2, np.int32)
+        pin = (i2 < n - 1).astype(np.int32)
+        lays.append((i1 - a, i2 - a, pin, np.array(act, np.int32)))
+    return lays
+
+
+class BlockShardedSampler:
+    """One rank of a block-sharded chequerboard sampler over a single long recording.
+
+    `make_engine(local_spec, interval_offset)` returns an object with the Engine interface
+    (set_layout, set_block_mask, backward_filter, impute, download_segment, upload_segment,
+    set_start, set_rho); `full_path` is the initial accepted path [C][S+1][d] of the WHOLE record
+    (every rank computes it identically, see `initial_full_path`)."""
+
+    def __init__(self, spec, rank, world, half_len, make_engine, full_path):
+        self.rank, self.world, self.h = rank, world, half_len
+        N = np.asarray(spec["N"])
+        self.n = len(N)
+        edges = shard_intervals(self.n, world, half_len)
+        self.a, self.b = edges[rank], edges[rank + 1]
+        self.b_ext = min(self.b + half_len, self.n) if rank < world - 1 else self.b
+        st_off = np.concatenate([[0], np.cumsum(N)])
+        self.Nloc = N[self.a:self.b_ext]
+        # full_path has one point per step plus the start: point index = 1 + global step index
+        x_start = full_path[:, st_off[self.a], :]
+        self.engine = make_engine(local_spec(spec, self.a, self.b_ext, x_start), self.a)
+        seg = full_path[:, st_off[self.a] + 1:st_off[self.b_ext] + 1, :]
+        self.engine.upload_segment(0, self.b_ext - self.a, seg)
+        self.lays = local_layouts(self.a, self.b, self.b_ext, self.n, half_len, rank)
+        self.sweeps = 0
+
+    # -- one PathImputation update under pattern `pat` (layout switch fused into the kernel) ---
+    def sweep(self, pat, it):
+        i1, i2, pin, act = self.lays[pat]
+        e = self.engine
+        e.set_layout(i1, i2, pin)
+        e.set_block_mask(act)
+        out = e.impute(it)
+        self.sweeps += 1
+        return out, act
+
+    # -- halo messages ------------------------------------------------------------------------
+    def pack_for_left(self):
+        """after sweep A: my first h intervals, for the left neighbour's halo."""
+        return self.engine.download_segment(0, min(self.h, self.b - self.a))
+
+    def unpack_from_right(self, X):
+        self.engine.upload_segment(self.b - self.a, self.b_ext - self.a, X)
+
+    def pack_for_right(self):
+        """after sweep B: the halo I just updated plus the edge point x(t_b) (my interval b-1's end)."""
+        halo = self.engine.download_segment(self.b - self.a, self.b_ext - self.a)
+        edge = self.engine.download_segment(self.b - self.a - 1, self.b - self.a)[:, -1:, :]
+        return np.concatenate([edge, halo], axis=1)
+
+    def unpack_from_left(self, msg):
+        e = self.engine
+        e.set_start(msg[:, :1, :].copy())           # [C][1][d]: my new starting point
+        e.upload_segment(0, min(self.h, self.b - self.a), msg[:, 1:, :])
+
+    def owned_path(self):
+        """accepted X of the intervals this rank owns, [C][steps][d]."""
+        return self.engine.download_segment(0, self.b - self.a)
+
+    def msg_shape_right(self, C, d):
+        steps = int(self.Nloc[self.b - self.a:self.b_ext - self.a].sum())
+        return (C, 1 + steps, d)
+
+    def msg_shape_left(self, C, d):
+        return (C, int(self.Nloc[:min(self.h, self.b - self.a)].sum()), d)
+
+
+def iterate(sampler, comm, it):
+    """One MCMC iteration = sweep A, exchange, sweep B, exchange (all ranks call this together).
+    `comm` has send(array, dst) [non-blocking], recv(shape, src) and flush()."""
+    s = sampler
+    C, d = s.engine.C, s.engine.d
+    out_a = s.sweep(0, 2 * it)
+    post_a(s, comm)
+    take_a(s, comm, C, d)
+    out_b = s.sweep(1, 2 * it + 1)
+    post_b(s, comm)
+    take_b(s, comm, C, d)
+    return out_a, out_b
+
+
+def post_a(s, comm):
+    if s.world > 1 and s.rank > 0:
+        comm.send(s.pack_for_left(), s.rank - 1)      # rank r -> r-1 : my first h intervals
+
+
+def take_a(s, comm, C, d):
+    if s.world > 1 and s.rank < s.world - 1:
+        steps = int(s.Nloc[s.b - s.a:s.b_ext - s.a].sum())
+        s.unpack_from_right(comm.recv((C, steps, d), s.rank + 1))
+    comm.flush()
+
+
+def post_b(s, comm):
+    if s.world > 1 and s.rank < s.world - 1:
+        comm.send(s.pack_for_right(), s.rank + 1)     # rank r -> r+1 : halo + edge point
+
+
+def take_b(s, comm, C, d):
+    if s.world > 1 and s.rank > 0:
+        steps = int(s.Nloc[:min(s.h, s.b - s.a)].sum())
+        s.unpack_from_left(comm.recv((C, 1 + steps, d), s.rank - 1))
+    comm.flush()
+
+
+class TorchComm:
+    """send/recv of float64 NumPy arrays over torch.distributed (NCCL: staged through a CUDA
+    tensor; gloo: CPU tensor)."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
+
+        self.pending = []
+
+    def send(self, arr, dst):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        self.pending.append((self.dist.isend(t, dst), t))
+
+    def flush(self):
+        for h, _ in self.pending:
+            h.wait()
+        self.pending = []
+
+    def recv(self, shape, src):
+        t = self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
+        self.dist.recv(t, src)
+        return t.cpu().numpy()
+
+    def allreduce_sum(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+class LocalComm:
+    """In-process mailbox for emulating several ranks on one device (tests): ranks are stepped in
+    an order that makes every recv find its message."""
+
+    def __init__(self):
+        self.box = {}
+
+    def view(self, rank):
+        outer = self
+
+        class _V:
+            def send(self, arr, dst):
+                outer.box[(rank, dst)] = np.array(arr, copy=True)
+
+            def recv(self, shape, src):
+                return outer.box.pop((src, rank))
+
+            def flush(self):
+                pass
+        return _V()
+
+
+def initial_full_path(spec, make_engine):
+    """Every rank initialises the WHOLE record identically (same seed => same Philox streams) and
+    keeps its slice: [C][S+1][d] with point 0 = the starting point."""
+    e = make_engine(spec, 0)
+    e.init_paths()
+    J = len(np.asarray(spec["N"]))
+    seg = e.download_segment(0, J)
+    x0 = np.asarray(spec["x0"], float)[:, 0:1, :]
+    e.close()
+    return np.concatenate([x0, seg], axis=1)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMCMC_ABI_VERSION 1
+#define DMCMC_ABI_VERSION 2
 
 /* Built-in diffusion laws (DiffusionDefinition.jl `@load_diffusion`, src/DiffusionMCMC.jl:4). */
 enum dmcmc_model {
@@ -48,6 +48,8 @@ typedef struct {
     int32_t n_chains;      /* chains held by THIS context (one context per GPU)                    */
     int32_t chain_offset;  /* global index of local chain 0 (Philox streams are per global chain,  */
                            /* so results do not depend on how chains are sharded over GPUs)        */
+    int32_t interval_offset; /* global index of local interval 0 when one long recording is sharded    */
+                           /* over GPUs by contiguous interval ranges (same purpose)     */
     int32_t device;        /* CUDA device ordinal                                                  */
     uint64_t seed;         /* Philox key                                                           */
     double pin_eps;        /* variance of the (almost exact) end-point observation of pinned blocks */
@@ -81,6 +83,10 @@ int dmcmc_set_aux(dmcmc_ctx *ctx, int32_t which, const double *B, const double *
  * block's right end is conditioned on the current path value (blocking). */
 int dmcmc_set_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2,
                      const int32_t *pinned);
+/* Optional per-block activity mask of the CURRENT layout (NULL = all active).  Inactive blocks are
+ * skipped by dmcmc_impute / dmcmc_run_sweeps (their histories read NaN).  Used when a recording is
+ * sharded over GPUs: halo intervals are present in the context but updated by the neighbour. */
+int dmcmc_set_block_mask(dmcmc_ctx *ctx, const int32_t *active);
 /* Chequerboard layout helper for BlockingChequerboardSwitch(block_half_len), src/blocking.jl:7-9.
  * pattern 0: delimiters at multiples of 2h; pattern 1: shifted by h.  half_len <= 0: no
  * blocking (src/schedule.jl:97-100).  Arrays must hold n_intervals entries; returns nblk. */
@@ -151,6 +157,11 @@ int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_ou
 int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W);
 /* Number of blocks of the current layout (-1: none). */
 int32_t dmcmc_n_blocks(const dmcmc_ctx *ctx);
+/* Accepted path values of intervals [j0, j1) (points 1..N_j of each, i.e. without the start point),
+ * X [n_chains][steps][d]: the halo exchange of a block-sharded recording.  Uploading
+ * overwrites the accepted containers and invalidates the stored noise (it is re-inverted). */
+int dmcmc_download_segment(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X);
+int dmcmc_upload_segment(dmcmc_ctx *ctx, int32_t j0, int32_t j1, const double *X);
 int dmcmc_get_ll(dmcmc_ctx *ctx, double *ll /* [n_chains][nblk] */);
 int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll);
 /* Device-side accept counters per block since the last call (src/adaptation.jl:100-103). */

@@ -744,7 +744,7 @@ static void impute_unit(const orc_problem *p, orc_state *s, int c, int b, const 
             for (int w = 0; w < m; ++w)
                 for (int q = 0; 4 * q < N; ++q) {
                     double z4[4];
-                    orc_philox_normal4(seed, iter, (uint32_t)j, (uint32_t)c, (uint32_t)w, (uint32_t)q, z4);
+                    orc_philox_normal4(seed, iter, (uint32_t)(j + p->interval_offset), (uint32_t)(c + p->chain_offset), (uint32_t)w, (uint32_t)q, z4);
                     for (int i = 0; i < 4 && 4 * q + i < N; ++i) zbuf[(size_t)(4 * q + i) * m + w] = z4[i];
                 }
             z = zbuf;
@@ -762,7 +762,7 @@ static void impute_unit(const orc_problem *p, orc_state *s, int c, int b, const 
     }
     free(zbuf);
     double *ll = s->ll + (size_t)c * p->nblk + b;
-    double e = use_philox ? orc_philox_exponential(seed, iter, (uint32_t)i1, (uint32_t)c)
+    double e = use_philox ? orc_philox_exponential(seed, iter, (uint32_t)(i1 + p->interval_offset), (uint32_t)(c + p->chain_offset))
                           : E[(size_t)c * p->nblk + b];
     /* accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!) */
     int acc = force_accept ? ok : (e > -(llp - *ll));

@@ -65,6 +65,8 @@ typedef struct {
     const double *blk_Qc;    /* [nblk][d*d] (pinned blocks)                               */
     const double *rho;       /* [J] pCN memory per interval                               */
     int32_t C;               /* chains                                                    */
+    int32_t chain_offset;    /* global index of chain 0 / interval 0: Philox streams are keyed   */
+    int32_t interval_offset; /* by GLOBAL indices so shards reproduce the unsharded run         */
 } orc_problem;
 
 typedef struct {

@@ -40,7 +40,8 @@ class _Problem(C.Structure):
                 ("st_off", _ip), ("t", _dp), ("auxB", _dp), ("auxbeta", _dp), ("auxsig", _dp),
                 ("nblk", C.c_int32), ("blk_i1", _ip), ("blk_i2", _ip), ("blk_pinned", _ip),
                 ("H", _dp), ("F0", _dp), ("Psi", _dp), ("c0", _dp), ("blk_g", _dp),
-                ("blk_Qc", _dp), ("rho", _dp), ("C", C.c_int32)]
+                ("blk_Qc", _dp), ("rho", _dp), ("C", C.c_int32), ("chain_offset", C.c_int32),
+                ("interval_offset", C.c_int32)]
 
 
 class _State(C.Structure):
@@ -172,8 +173,9 @@ class Oracle:
     x0[C][R][d], rho[J], pin_eps.
     """
 
-    def __init__(self, spec, nthreads=1):
+    def __init__(self, spec, nthreads=1, chain_offset=0, interval_offset=0):
         self.nthreads = nthreads
+        self.chain_offset, self.interval_offset = chain_offset, interval_offset
         self.model, self.d, self.m = int(spec["model"]), int(spec["d"]), int(spec["m"])
         self.N = i32(spec["N"])
         self.J = len(self.N)
@@ -248,6 +250,7 @@ class Oracle:
         p.nblk, p.blk_i1, p.blk_i2, p.blk_pinned = self.nblk, _i(self.blk_i1), _i(self.blk_i2), _i(self.blk_pinned)
         p.H, p.F0, p.Psi, p.c0 = _d(self.H), _d(self.F0), _d(self.Psi), _d(self.c0)
         p.blk_g, p.blk_Qc, p.rho, p.C = _d(self.blk_g), _d(self.blk_Qc), _d(self.rho), self.C
+        p.chain_offset, p.interval_offset = self.chain_offset, self.interval_offset
         return p
 
     def _state(self):

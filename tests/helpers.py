@@ -37,3 +37,59 @@ def accept_mismatch_is_tie(acc_g, acc_o, E, llp, ll_before, rtol=RTOL):
         return True
     gap = np.abs(E + (llp - ll_before))
     return bool(np.all(gap[bad] <= rtol * np.maximum(1.0, np.abs(ll_before[bad]))))
+
+
+class OracleEngine:
+    """Adapter giving the CPU oracle the Engine interface that parallel.BlockShardedSampler
+    drives (tests only): lets the multi-process host logic run under gloo without a GPU."""
+
+    def __init__(self, orc, spec, interval_offset=0, seed=0, chain_offset=0):
+        self.o = orc.Oracle(spec, interval_offset=interval_offset, chain_offset=chain_offset)
+        self.seed = seed
+        self.C, self.d, self.N = self.o.C, self.o.d, self.o.N
+        self.layout, self.mask = None, None
+
+    def close(self):
+        pass
+
+    def init_paths(self):
+        self.o.init_paths(seed=self.seed)
+
+    def set_layout(self, i1, i2, pin):
+        self.layout = (np.asarray(i1, np.int32), np.asarray(i2, np.int32), np.asarray(pin, np.int32))
+
+    def set_block_mask(self, act):
+        self.mask = None if act is None else np.asarray(act, np.uint8)
+
+    def impute(self, it):
+        o = self.o
+        o.relayout(*self.layout)   # the CUDA path fuses this into the imputation kernel
+        mask = None if self.mask is None else np.broadcast_to(self.mask, (o.C, o.nblk)).copy()
+        return o.impute(seed=self.seed, it=it, unit_mask=mask)
+
+    def _acc(self, c, j):
+        o = self.o
+        return o.X[o.selX[c, j]][c, o.pt_off[j]:o.pt_off[j + 1]]
+
+    def download_segment(self, j0, j1):
+        o = self.o
+        return np.stack([np.concatenate([self._acc(c, j)[1:] for j in range(j0, j1)]) for c in range(o.C)])
+
+    def upload_segment(self, j0, j1, X):
+        o = self.o
+        for c in range(o.C):
+            off = 0
+            for j in range(j0, j1):
+                cont = self._acc(c, j)
+                if j > 0:
+                    cont[0] = self._acc(c, j - 1)[-1]
+                cont[1:] = X[c, off:off + o.N[j]]
+                off += o.N[j]
+            if j1 < o.J:
+                self._acc(c, j1)[0] = X[c, -1]
+
+    def set_start(self, x0):
+        o = self.o
+        for c in range(o.C):
+            o.X[0][c, 0] = x0[c, 0]
+            o.X[1][c, 0] = x0[c, 0]
