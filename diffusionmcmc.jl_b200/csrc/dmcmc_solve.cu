@@ -134,7 +134,7 @@ __device__ __forceinline__ void load_end(const SolveParams &p, int chain, int j,
     const double *X = p.X[s];
 #pragma unroll
     for (int c = 0; c < D; ++c)
-        x[c] = X[(((size_t)c * p.TT + tile) * p.C + chain) * TILE + (k & 7)];
+        x[c] = X[x_off(tile, chain, c, p.C, D) + (k & 7)];
 }
 
 template <int D>
@@ -261,22 +261,32 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
         const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
         const double *Wa = p.W[sw];
         double *Wp = p.W[1 - sw];
-        const double *Xa = p.X[sx];
-        double *Xp = p.X[1 - sx];
+        // pair-cooperative access to the X containers (see PairX): lanes 2i / 2i+1 share both chains' pointers
+        PairX<D> px;
+        {
+            const int odd = threadIdx.x & 1;
+            const int sx_o = __shfl_xor_sync(0xffffffffu, sx, 1);
+            const int chain_o = __shfl_xor_sync(0xffffffffu, chain, 1);
+            const int act_o = __shfl_xor_sync(0xffffffffu, (int)active, 1);
+            const int sA = odd ? sx_o : sx, sB = odd ? sx : sx_o;
+            px.odd = odd; px.C = p.C;
+            px.cA = odd ? chain_o : chain; px.cB = odd ? chain : chain_o;
+            px.accA = p.X[sA]; px.accB = p.X[sB];
+            px.prpA = p.X[1 - sA]; px.prpB = p.X[1 - sB];
+            px.storeA = odd ? act_o : (int)active; px.storeB = odd ? (int)active : act_o;
+        }
         double lsum = 0.0, lsum_a = 0.0;
 
         // software prefetch of the x-independent streams, one tile ahead
-        double dwn[NEED_WA ? M : 1][TILE], xan[NEED_XA ? D : 1][TILE];
+        double dwn[NEED_WA ? M : 1][TILE];
+        double xnA[NEED_XA ? D : 1][4], xnB[NEED_XA ? D : 1][4];  // raw halves of the next accepted-X tile
         {
             const size_t base = (toff * p.C + chain) * TILE;
             if constexpr (NEED_WA) {
 #pragma unroll
                 for (int w = 0; w < M; ++w) ld_tile(Wa + w * cstride + base, dwn[w]);
             }
-            if constexpr (NEED_XA) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) ld_tile(Xa + c * cstride + base, xan[c]);
-            }
+            if constexpr (NEED_XA) px.load(toff, xnA, xnB);
         }
 
         for (int c0 = 0; c0 < nt; c0 += CHUNK_TILES, ++q) {
@@ -336,15 +346,8 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                     }
                 }
                 if constexpr (NEED_XA) {
-#pragma unroll
-                    for (int c = 0; c < D; ++c)
-#pragma unroll
-                        for (int s = 0; s < TILE; ++s) xat[c][s] = xan[c][s];
-                    if (tl + 1 < nt) {
-#pragma unroll
-                        for (int c = 0; c < D; ++c)
-                            ld_tile(Xa + c * cstride + base + (size_t)p.C * TILE, xan[c]);
-                    }
+                    px.unpack(xnA, xnB, xat);
+                    if (tl + 1 < nt) px.load(tile + 1, xnA, xnB);
                 }
                 double z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
                 if constexpr (MODE == MODE_IMPUTE) {
@@ -427,15 +430,17 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                         for (int c = 0; c < D; ++c) xo[c][s] = x[c];
                     }
                 }
-                if (active) {
-                    if constexpr (SOLVE) {
+                if constexpr (SOLVE) {
+                    if (pinned && j == i2 && tl == nt - 1) {  // pin the block's right end to x_b
+                        const int last = (N - 1) & 7;
 #pragma unroll
-                        for (int c = 0; c < D; ++c) st_tile(Xp + c * cstride + base, xo[c]);
-                        if (pinned && j == i2 && tl == nt - 1) {  // pin the block's right end to x_b
+                        for (int s = 0; s < TILE; ++s)
 #pragma unroll
-                            for (int c = 0; c < D; ++c) Xp[c * cstride + base + ((N - 1) & 7)] = xb[c];
-                        }
+                            for (int c = 0; c < D; ++c) xo[c][s] = (s == last) ? xb[c] : xo[c][s];
                     }
+                    px.store(tile, xo);  // every lane takes part (shuffles); stores are predicated per chain
+                }
+                if (active) {
                     if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
                         double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
 #pragma unroll
@@ -555,7 +560,7 @@ __global__ void gather_kernel(const GatherParams g) {
             const int sp = g.selX[(size_t)jp * g.C + chain] ^ (same_blk ? 1 : 0);
             const int k = g.iv_N[jp] - 1;
             const size_t tile = (size_t)g.iv_tile_off[jp] + (k >> 3);
-            v = g.X[sp][(((size_t)c * g.TT + tile) * g.C + chain) * TILE + (k & 7)];
+            v = g.X[sp][x_off(tile, chain, c, g.C, g.D) + (k & 7)];
         }
         g.outX[(pt0)*g.D + c] = v;
     }
@@ -563,7 +568,7 @@ __global__ void gather_kernel(const GatherParams g) {
     for (int k = 0; k < N; ++k) {
         const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
         const size_t e = (tile * g.C + chain) * TILE + (k & 7);
-        for (int c = 0; c < g.D; ++c) g.outX[(pt0 + k + 1) * g.D + c] = g.X[sx][c * cs + e];
+        for (int c = 0; c < g.D; ++c) g.outX[(pt0 + k + 1) * g.D + c] = g.X[sx][x_off(tile, chain, c, g.C, g.D) + (k & 7)];
         for (int w = 0; w < g.M; ++w)
             g.outW[(pt0 + k + 1) * g.M + w] = g.outW[(pt0 + k) * g.M + w] + g.W[sw][w * cs + e];
     }
@@ -582,8 +587,9 @@ __global__ void segment_kernel(const SegmentParams g) {
         const size_t e = (tile * g.C + chain) * TILE + (k & 7);
         for (int c = 0; c < g.D; ++c) {
             double *pk = g.packed + ((size_t)chain * g.steps + off + k) * g.D + c;
-            if (g.upload) X[c * cs + e] = *pk;
-            else *pk = X[c * cs + e];
+            const size_t xe = x_off(tile, chain, c, g.C, g.D) + (k & 7);
+            if (g.upload) X[xe] = *pk;
+            else *pk = X[xe];
         }
     }
     if (g.upload) {  // pad slots repeat the last value (they are no-ops for the solve kernels)
@@ -592,7 +598,7 @@ __global__ void segment_kernel(const SegmentParams g) {
             const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
             const size_t e = (tile * g.C + chain) * TILE + (k & 7);
             for (int c = 0; c < g.D; ++c)
-                X[c * cs + e] = g.packed[((size_t)chain * g.steps + off + N - 1) * g.D + c];
+                X[x_off(tile, chain, c, g.C, g.D) + (k & 7)] = g.packed[((size_t)chain * g.steps + off + N - 1) * g.D + c];
         }
     }
 }
