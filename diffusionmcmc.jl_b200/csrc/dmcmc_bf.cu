@@ -280,8 +280,294 @@ __global__ void bf_kernel(const BFParams b) {
     for (int i = 0; i < D * D; ++i) b.blk_Qc[(size_t)blk * D * D + i] = s.Qc[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large state dimension (Lorenz-96, D = 40): one CTA per layout block, matrices in shared memory,
+// every matrix operation of the small-D recursion spread over the CTA's threads.  Each output
+// element is still produced by ONE thread that sums in the same order as the scalar code (and the
+// oracle), the LU pivot is chosen by the same first-maximum rule, so the result differs from the
+// oracle only by FMA contraction.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct Coop {
+    int tid, nt;
+    __device__ void mm(const double *A, const double *B, double *C) const {   // C = A B
+        for (int e = tid; e < D * D; e += nt) {
+            const int i = e / D, j = e % D;
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[i * D + k] * B[k * D + j];
+            C[e] = s;
+        }
+        __syncthreads();
+    }
+    __device__ void mmT(const double *A, const double *B, double *C) const {  // C = A B'
+        for (int e = tid; e < D * D; e += nt) {
+            const int i = e / D, j = e % D;
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[i * D + k] * B[j * D + k];
+            C[e] = s;
+        }
+        __syncthreads();
+    }
+    __device__ void mTm(const double *A, const double *B, double *C) const {  // C = A' B
+        for (int e = tid; e < D * D; e += nt) {
+            const int i = e / D, j = e % D;
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[k * D + i] * B[k * D + j];
+            C[e] = s;
+        }
+        __syncthreads();
+    }
+    __device__ void mv(const double *A, const double *x, double *y) const {
+        for (int i = tid; i < D; i += nt) {
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[i * D + k] * x[k];
+            y[i] = s;
+        }
+        __syncthreads();
+    }
+    __device__ void mTv(const double *A, const double *x, double *y) const {
+        for (int i = tid; i < D; i += nt) {
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += A[k * D + i] * x[k];
+            y[i] = s;
+        }
+        __syncthreads();
+    }
+    __device__ double dot(const double *a, const double *b) const {  // every thread sums in order
+        double s = 0.0;
+        for (int i = 0; i < D; ++i) s += a[i] * b[i];
+        return s;
+    }
+    __device__ void sym(double *A) const {
+        for (int e = tid; e < D * D; e += nt) {
+            const int i = e / D, j = e % D;
+            if (j > i) {
+                const double s = 0.5 * (A[i * D + j] + A[j * D + i]);
+                A[i * D + j] = s;
+                A[j * D + i] = s;
+            }
+        }
+        __syncthreads();
+    }
+    __device__ void copy(double *dst, const double *src, int n) const {
+        for (int e = tid; e < n; e += nt) dst[e] = src[e];
+        __syncthreads();
+    }
+    // LU with partial pivoting in place; returns log|det| (same value on every thread)
+    __device__ double lu(double *A, int *piv) const {
+        double lad = 0.0;
+        for (int k = 0; k < D; ++k) {
+            if (tid == 0) {
+                int p = k;
+                double best = fabs(A[k * D + k]);
+                for (int i = k + 1; i < D; ++i)
+                    if (fabs(A[i * D + k]) > best) { best = fabs(A[i * D + k]); p = i; }
+                piv[k] = p;
+            }
+            __syncthreads();
+            const int p = piv[k];
+            if (p != k) {
+                for (int j = tid; j < D; j += nt) {
+                    const double t = A[k * D + j]; A[k * D + j] = A[p * D + j]; A[p * D + j] = t;
+                }
+                __syncthreads();
+            }
+            const double pivv = A[k * D + k];
+            lad += log(fabs(pivv));
+            const double inv = 1.0 / pivv;
+            __syncthreads();
+            for (int i = k + 1 + tid; i < D; i += nt) A[i * D + k] = A[i * D + k] * inv;
+            __syncthreads();
+            const int m = D - k - 1;
+            for (int e = tid; e < m * m; e += nt) {
+                const int i = k + 1 + e / m, j = k + 1 + e % m;
+                A[i * D + j] -= A[i * D + k] * A[k * D + j];
+            }
+            __syncthreads();
+        }
+        return lad;
+    }
+    // solve A X = Bm for NR columns (Bm row-major D x NR, overwritten): one thread per column
+    __device__ void solve(const double *LU, const int *piv, double *Bm, int NR) const {
+        for (int j = tid; j < NR; j += nt) {
+            for (int k = 0; k < D; ++k) {
+                const int p = piv[k];
+                if (p != k) { const double t = Bm[k * NR + j]; Bm[k * NR + j] = Bm[p * NR + j]; Bm[p * NR + j] = t; }
+                const double bk = Bm[k * NR + j];
+                for (int i = k + 1; i < D; ++i) Bm[i * NR + j] -= LU[i * D + k] * bk;
+            }
+            for (int k = D - 1; k >= 0; --k) {
+                double sacc = Bm[k * NR + j];
+                for (int i = k + 1; i < D; ++i) sacc -= LU[k * D + i] * Bm[i * NR + j];
+                Bm[k * NR + j] = sacc * (1.0 / LU[k * D + k]);
+            }
+        }
+        __syncthreads();
+    }
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) bf_big_kernel(const BFParams b) {
+    extern __shared__ double smem[];
+    constexpr int DD = D * D;
+    double *H = smem, *Psi = H + DD, *Qc = Psi + DD, *Phi = Qc + DD, *Q = Phi + DD, *A = Q + DD;
+    double *Hs = A + DD, *T1 = Hs + DD, *Psis = T1 + DD, *T2 = Psis + DD;
+    double *F0 = T2 + DD, *g = F0 + D, *mvec = g + D, *Fs = mvec + D, *tv = Fs + D, *tv2 = tv + D;
+    double *a1 = tv2 + D, *a2 = a1 + D, *bn = a2 + D;
+    __shared__ int piv[D];
+    __shared__ double c0s;
+    const Coop<D> co{(int)threadIdx.x, (int)blockDim.x};
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int blk = blockIdx.x;
+    for (int e = tid; e < DD; e += nt) { H[e] = 0.0; Psi[e] = 0.0; Qc[e] = 0.0; }
+    for (int e = tid; e < D; e += nt) { F0[e] = 0.0; g[e] = 0.0; }
+    if (tid == 0) c0s = 0.0;
+    __syncthreads();
+    const bool pinned = b.blk_pinned[blk] != 0;
+    const int i1 = b.blk_i1[blk], i2 = b.blk_i2[blk];
+
+    auto store = [&](size_t pt, long long step, double dt) {
+        if (b.ptH) for (int e = tid; e < DD; e += nt) b.ptH[pt * DD + e] = H[e];
+        if (b.ptF0) for (int e = tid; e < D; e += nt) b.ptF0[pt * D + e] = F0[e];
+        if (b.ptPsi) for (int e = tid; e < DD; e += nt) b.ptPsi[pt * DD + e] = Psi[e];
+        if (b.ptc0 && tid == 0) b.ptc0[pt] = c0s;
+        if (step >= 0) {
+            double *r = b.table + (size_t)step * b.rec;
+            if (tid == 0) { r[0] = dt; r[1] = sqrt(dt); }
+            for (int e = tid; e < DD; e += nt) r[2 + e] = H[e];
+            for (int e = tid; e < D; e += nt) r[2 + DD + e] = F0[e];
+            if (b.has_psi)
+                for (int e = tid; e < DD; e += nt) r[2 + DD + D + e] = Psi[(e % D) * D + (e / D)];  // transposed
+        }
+        __syncthreads();
+    };
+
+    for (int j = i2; j >= i1; --j) {
+        if (j == i2 && pinned) {
+            const double ie = 1.0 / b.pin_eps;
+            for (int i = tid; i < D; i += nt) { H[i * D + i] = ie; Psi[i * D + i] = ie; Qc[i * D + i] = ie; }
+            if (tid == 0) c0s = 0.5 * D * log(2.0 * M_PI * b.pin_eps);
+        } else {
+            for (int e = tid; e < DD; e += nt) H[e] += b.Hobs[(size_t)j * DD + e];
+            for (int e = tid; e < D; e += nt) F0[e] += b.Fobs[(size_t)j * D + e];
+            if (tid == 0) c0s += b.cobs[j];
+        }
+        __syncthreads();
+        const int N = b.iv_N[j];
+        const size_t base = (size_t)b.iv_pt_off[j];
+        const long long sbase = (long long)b.iv_tile_off[j] * TILE;
+        store(base + N, -1, 0.0);
+        const double *Bj = b.auxB + (size_t)j * DD, *betaj = b.auxbeta + (size_t)j * D, *atj = b.auxatil + (size_t)j * DD;
+        double dt_cached = -1.0;
+        for (int k = N - 1; k >= 0; --k) {
+            const double dt = b.t[base + k + 1] - b.t[base + k];
+            if (!(fabs(dt - dt_cached) <= 1e-12 * fabs(dt_cached))) {
+                // transition (Phi, Q, mvec): Taylor series with scaling-and-doubling (mirrors transition<D>)
+                double nrm = 0.0;
+                for (int i = 0; i < D; ++i) {
+                    double sacc = 0.0;
+                    for (int jj = 0; jj < D; ++jj) sacc += fabs(Bj[i * D + jj]);
+                    if (sacc > nrm) nrm = sacc;
+                }
+                int sq = 0;
+                double h = dt;
+                while (nrm * h > 0.25 && sq < 40) { h *= 0.5; ++sq; }
+                double *Pn = A, *An = Hs;  // scratch: A and Hs are free between steps
+                for (int e = tid; e < DD; e += nt) {
+                    const double idm = (e / D == e % D) ? 1.0 : 0.0;
+                    Phi[e] = idm; Pn[e] = idm; An[e] = atj[e];
+                }
+                for (int e = tid; e < D; e += nt) bn[e] = betaj[e];
+                __syncthreads();
+                double coef = h;
+                for (int e = tid; e < DD; e += nt) Q[e] = coef * An[e];
+                for (int e = tid; e < D; e += nt) mvec[e] = coef * bn[e];
+                __syncthreads();
+                for (int n = 1; n <= TAYLOR_TERMS; ++n) {
+                    co.mm(Bj, Pn, T1);
+                    for (int e = tid; e < DD; e += nt) { Pn[e] = T1[e] * (h / n); Phi[e] += Pn[e]; }
+                    __syncthreads();
+                    co.mm(Bj, An, T1);
+                    co.mmT(An, Bj, T2);
+                    for (int e = tid; e < DD; e += nt) An[e] = T1[e] + T2[e];
+                    co.mv(Bj, bn, tv);
+                    for (int e = tid; e < D; e += nt) bn[e] = tv[e];
+                    coef = coef * h / (n + 1);
+                    __syncthreads();
+                    for (int e = tid; e < DD; e += nt) Q[e] += coef * An[e];
+                    for (int e = tid; e < D; e += nt) mvec[e] += coef * bn[e];
+                    __syncthreads();
+                }
+                for (int s2 = 0; s2 < sq; ++s2) {
+                    co.mm(Phi, Q, T1);
+                    co.mmT(T1, Phi, T2);
+                    for (int e = tid; e < DD; e += nt) Q[e] += T2[e];
+                    co.mv(Phi, mvec, tv);
+                    for (int e = tid; e < D; e += nt) mvec[e] += tv[e];
+                    __syncthreads();
+                    co.mm(Phi, Phi, T1);
+                    co.copy(Phi, T1, DD);
+                }
+                co.sym(Q);
+                dt_cached = dt;
+            }
+            // ---- one exact backward step (mirrors bf_step<D>) ----
+            co.mm(H, Q, A);
+            for (int i = tid; i < D; i += nt) A[i * D + i] += 1.0;
+            __syncthreads();
+            const double lad = co.lu(A, piv);
+            co.copy(Hs, H, DD);
+            co.solve(A, piv, Hs, D);
+            co.sym(Hs);
+            co.copy(Fs, F0, D);
+            co.solve(A, piv, Fs, 1);
+            co.mv(Hs, mvec, tv);
+            co.mv(Q, Fs, tv2);
+            if (tid == 0)
+                c0s = c0s + 0.5 * lad + 0.5 * co.dot(mvec, tv) - co.dot(mvec, Fs) - 0.5 * co.dot(F0, tv2);
+            __syncthreads();
+            if (pinned) {
+                co.copy(Psis, Psi, DD);
+                co.solve(A, piv, Psis, D);
+                co.mTv(Psis, mvec, a1);
+                co.mTv(Psi, tv2, a2);
+                for (int i = tid; i < D; i += nt) g[i] = g[i] - a1[i] - a2[i];
+                co.mm(Q, Psis, T1);
+                co.mTm(Psi, T1, A);
+                for (int e = tid; e < DD; e += nt) Qc[e] -= A[e];
+                __syncthreads();
+                co.sym(Qc);
+                co.mTm(Phi, Psis, Psi);
+            }
+            for (int i = tid; i < D; i += nt) tv2[i] = Fs[i] - tv[i];
+            __syncthreads();
+            co.mTv(Phi, tv2, F0);
+            co.mm(Hs, Phi, T1);
+            co.mTm(Phi, T1, H);
+            co.sym(H);
+            store(base + k, sbase + k, dt);
+        }
+        for (int k = N; k < ((N + TILE - 1) / TILE) * TILE; ++k) {  // pad slots: benign record
+            double *r = b.table + (size_t)(sbase + k) * b.rec;
+            for (int e = tid; e < b.rec; e += nt) r[e] = 0.0;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) b.blk_c0[blk] = c0s;
+    for (int e = tid; e < D; e += nt) b.blk_g[(size_t)blk * D + e] = g[e];
+    for (int e = tid; e < DD; e += nt) b.blk_Qc[(size_t)blk * DD + e] = Qc[e];
+}
+
 cudaError_t launch_backward_filter(const BFParams &b, cudaStream_t s) {
     if (b.nblk == 0) return cudaSuccess;
+    if (b.D == 40) {
+        constexpr int D = 40;
+        const size_t smem = (size_t)(10 * D * D + 9 * D) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(bf_big_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        bf_big_kernel<D><<<b.nblk, 256, smem, s>>>(b);
+        return cudaGetLastError();
+    }
     const int threads = 32;
     const unsigned grid = (unsigned)((b.nblk + threads - 1) / threads);
     switch (b.D) {

@@ -259,9 +259,13 @@ int ensure_tables_alloc(dmcmc_ctx *ctx, Layout &lay, int slot) {
     CK(tb.blk_c0.ensure(lay.nblk));
     CK(tb.blk_g.ensure((size_t)lay.nblk * d));
     CK(tb.blk_Qc.ensure((size_t)lay.nblk * d * d));
-    CK(tb.ptH.ensure((size_t)ctx->P * d * d));
+    // per-grid-point copies exist for dmcmc_download_tables / parity runs; skipped when they would
+    // not be small (Lorenz-96 at full size: 5 GB each)
+    if ((size_t)ctx->P * d * d * sizeof(double) <= ((size_t)512 << 20)) {
+        CK(tb.ptH.ensure((size_t)ctx->P * d * d));
+        CK(tb.ptPsi.ensure((size_t)ctx->P * d * d));
+    }
     CK(tb.ptF0.ensure((size_t)ctx->P * d));
-    CK(tb.ptPsi.ensure((size_t)ctx->P * d * d));
     CK(tb.ptc0.ensure((size_t)ctx->P));
     return 0;
 }
@@ -299,7 +303,7 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     if (!tb.valid && run_backward_filter(ctx, slot)) return -1;  // tables follow the layout lazily
     Law &law = ctx->law[slot];
     sp = SolveParams{};
-    sp.C = ctx->C; sp.nblk = lay.nblk; sp.J = ctx->J; sp.chain_offset = ctx->cfg.chain_offset;
+    sp.C = ctx->C; sp.nblk = lay.nblk; sp.J = ctx->J; sp.D = ctx->d; sp.chain_offset = ctx->cfg.chain_offset;
     sp.interval_offset = ctx->cfg.interval_offset;
     sp.blk_active = lay.has_mask ? lay.d_active.p : nullptr;
     sp.TT = ctx->TT;
@@ -356,7 +360,7 @@ int stage_noise(dmcmc_ctx *ctx, const double *Z) {
             for (int k = 0; k < ctx->N[j]; ++k) {
                 const size_t tile = (size_t)ctx->tile_off[j] + (k >> 3);
                 for (int w = 0; w < m; ++w)
-                    buf[(((size_t)w * ctx->TT + tile) * C + c) * TILE + (k & 7)] =
+                    buf[x_off(tile, c, w, C, m) + (k & 7)] =
                         Z[((size_t)c * ctx->S + ctx->st_off[j] + k) * m + w];
             }
     CK(ctx->d_Z.ensure(n));
@@ -739,11 +743,19 @@ int dmcmc_upload_tables(dmcmc_ctx *ctx, int32_t which, const double *H, const do
             r[0] = dt;
             r[1] = std::sqrt(dt);
             int o = 2;
-            for (int i = 0; i < d; ++i)
-                for (int q = i; q < d; ++q) r[o++] = H[pt * d * d + i * d + q];
-            for (int i = 0; i < d; ++i) r[o++] = F0[pt * d + i];
-            if (lay.has_psi)
-                for (int i = 0; i < d * d; ++i) r[o++] = Psi[pt * d * d + i];
+            if (d > 3) {  // large-D record: full H, F0, Psi transposed
+                for (int i = 0; i < d * d; ++i) r[o++] = H[pt * d * d + i];
+                for (int i = 0; i < d; ++i) r[o++] = F0[pt * d + i];
+                if (lay.has_psi)
+                    for (int k = 0; k < d; ++k)
+                        for (int i = 0; i < d; ++i) r[o++] = Psi[pt * d * d + (size_t)i * d + k];
+            } else {
+                for (int i = 0; i < d; ++i)
+                    for (int q = i; q < d; ++q) r[o++] = H[pt * d * d + i * d + q];
+                for (int i = 0; i < d; ++i) r[o++] = F0[pt * d + i];
+                if (lay.has_psi)
+                    for (int i = 0; i < d * d; ++i) r[o++] = Psi[pt * d * d + i];
+            }
         }
     std::vector<double> c0b(lay.nblk), g((size_t)lay.nblk * d, 0.0), Qc((size_t)lay.nblk * d * d, 0.0);
     for (int b = 0; b < lay.nblk; ++b) c0b[b] = c0[ctx->pt_off[lay.i1[b]]];
@@ -753,10 +765,12 @@ int dmcmc_upload_tables(dmcmc_ctx *ctx, int32_t which, const double *H, const do
     CK(cudaMemcpy(tb.blk_c0.p, c0b.data(), c0b.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(tb.blk_g.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(tb.blk_Qc.p, Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(tb.ptH.p, H, (size_t)ctx->P * d * d * sizeof(double), cudaMemcpyHostToDevice));
+    if (tb.ptH.p) CK(cudaMemcpy(tb.ptH.p, H, (size_t)ctx->P * d * d * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(tb.ptF0.p, F0, (size_t)ctx->P * d * sizeof(double), cudaMemcpyHostToDevice));
-    if (Psi) CK(cudaMemcpy(tb.ptPsi.p, Psi, (size_t)ctx->P * d * d * sizeof(double), cudaMemcpyHostToDevice));
-    else CK(cudaMemset(tb.ptPsi.p, 0, (size_t)ctx->P * d * d * sizeof(double)));
+    if (tb.ptPsi.p) {
+        if (Psi) CK(cudaMemcpy(tb.ptPsi.p, Psi, (size_t)ctx->P * d * d * sizeof(double), cudaMemcpyHostToDevice));
+        else CK(cudaMemset(tb.ptPsi.p, 0, (size_t)ctx->P * d * d * sizeof(double)));
+    }
     CK(cudaMemcpy(tb.ptc0.p, c0, (size_t)ctx->P * sizeof(double), cudaMemcpyHostToDevice));
     tb.valid = true;
     return 0;
@@ -772,6 +786,7 @@ int dmcmc_download_tables(dmcmc_ctx *ctx, int32_t which, double *H, double *F0, 
     REQUIRE(tb.valid, "dmcmc_download_tables: tables not computed");
     if (sync(ctx)) return -1;
     const size_t d = ctx->d, P = ctx->P;
+    REQUIRE(tb.ptH.p || (!H && !Psi), "dmcmc_download_tables: per-point H/Psi are not kept for this problem size");
     if (H) CK(cudaMemcpy(H, tb.ptH.p, P * d * d * sizeof(double), cudaMemcpyDeviceToHost));
     if (F0) CK(cudaMemcpy(F0, tb.ptF0.p, P * d * sizeof(double), cudaMemcpyDeviceToHost));
     if (Psi) CK(cudaMemcpy(Psi, tb.ptPsi.p, P * d * d * sizeof(double), cudaMemcpyDeviceToHost));

@@ -16,7 +16,7 @@ enum SolveMode {
 
 // Everything a solve kernel needs.  Pointers are device pointers.
 struct SolveParams {
-    int32_t C, nblk, J;
+    int32_t C, nblk, J, D;
     int32_t chain_offset, interval_offset;
     int64_t TT;  // total tiles over all intervals
     // layout
@@ -35,8 +35,8 @@ struct SolveParams {
     const double *blk_Qc;   // [nblk][D*D]
     int32_t has_psi;
     // state
-    double *X[2];           // [D][TT][C][8]
-    double *W[2];           // [M][TT][C][8]
+    double *X[2];           // [TT][C][D][8]  one record per (tile, chain)
+    double *W[2];           // [TT][C][M][8]
     // accepted-container selectors [J][C]: read from *_in, written (flipped on accept) to *_out;
     // the two arrays are swapped by the host after the sweep, so no unit ever reads a selector
     // that a neighbouring block's unit is flipping.
@@ -45,7 +45,7 @@ struct SolveParams {
     const double *x0;       // [R][D][C]
     double *ll;             // [C][nblk]
     // noise
-    const double *Z;        // [M][TT][C][8] explicit normals or nullptr (Philox)
+    const double *Z;        // [TT][C][M][8] explicit normals or nullptr (Philox)
     const double *E;        // [C][nblk] explicit Exp(1) or nullptr
     uint64_t seed;
     uint32_t iter;
@@ -64,6 +64,7 @@ struct SolveParams {
 
 // launchers (dmcmc_solve.cu); return the CUDA error of the launch
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s);
+cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_big.cu
 
 // state gather for read-outs (dmcmc_solve.cu)
 struct GatherParams {

@@ -234,7 +234,6 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
 
     double llp = 0.0, lla = 0.0;  // proposal ll, accepted-path ll (recomputed when REINV)
     bool ok = true;
-    const size_t cstride = (size_t)p.TT * p.C * TILE;  // component stride in X / W / Z
     const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
     int q = 0;
 
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
             const size_t base = (toff * p.C + chain) * TILE;
             if constexpr (NEED_WA) {
 #pragma unroll
-                for (int w = 0; w < M; ++w) ld_tile(Wa + w * cstride + base, dwn[w]);
+                for (int w = 0; w < M; ++w) ld_tile(Wa + x_off(toff, chain, w, p.C, M), dwn[w]);
             }
             if constexpr (NEED_XA) px.load(toff, xnA, xnB);
         }
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                     if (tl + 1 < nt) {
 #pragma unroll
                         for (int w = 0; w < M; ++w)
-                            ld_tile(Wa + w * cstride + base + (size_t)p.C * TILE, dwn[w]);
+                            ld_tile(Wa + x_off(tile + 1, chain, w, p.C, M), dwn[w]);
                     }
                 }
                 if constexpr (NEED_XA) {
@@ -360,7 +359,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                                                (uint32_t)(tl * (TILE / 4) + h), &z[w][4 * h]);
                     } else {
 #pragma unroll
-                        for (int w = 0; w < M; ++w) ld_tile_stream(p.Z + w * cstride + base, z[w]);
+                        for (int w = 0; w < M; ++w) ld_tile_stream(p.Z + x_off(tile, chain, w, p.C, M), z[w]);
                     }
                 }
                 double xo[SOLVE ? D : 1][TILE], dwo[M][TILE];
@@ -444,7 +443,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                     if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
                         double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
 #pragma unroll
-                        for (int w = 0; w < M; ++w) st_tile(Wdst + w * cstride + base, dwo[w]);
+                        for (int w = 0; w < M; ++w) st_tile(Wdst + x_off(tile, chain, w, p.C, M), dwo[w]);
                     }
                 }
             }
@@ -531,6 +530,7 @@ cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads,
                              : launch_psi<ModelFHN, false>(mode, p, threads, s);
     case 1: return launch_psi<ModelLV>(mode, p, threads, s);
     case 2: return launch_psi<ModelL63>(mode, p, threads, s);
+    case 3: return launch_solve_big(p.D, mode, p, s);
     case 4: return launch_psi<ModelLIN2>(mode, p, threads, s);
     case 5: return launch_psi<ModelLVM>(mode, p, threads, s);
     }
@@ -570,7 +570,7 @@ __global__ void gather_kernel(const GatherParams g) {
         const size_t e = (tile * g.C + chain) * TILE + (k & 7);
         for (int c = 0; c < g.D; ++c) g.outX[(pt0 + k + 1) * g.D + c] = g.X[sx][x_off(tile, chain, c, g.C, g.D) + (k & 7)];
         for (int w = 0; w < g.M; ++w)
-            g.outW[(pt0 + k + 1) * g.M + w] = g.outW[(pt0 + k) * g.M + w] + g.W[sw][w * cs + e];
+            g.outW[(pt0 + k + 1) * g.M + w] = g.outW[(pt0 + k) * g.M + w] + g.W[sw][x_off(tile, chain, w, g.C, g.M) + (k & 7)];
     }
 }
 

@@ -1,0 +1,332 @@
+// dmcmc_solve_big.cu -- the imputation hot path for large state dimension (Lorenz-96, d = 40).
+//
+// One WARP owns one (chain, block) unit; lanes own state components (lane l: components l and
+// l+32).  The per-step work is three dense mat-vecs (Psi x_b, H x, and H x_acc when the accepted
+// noise is recovered on the fly), each a loop over columns k in which every lane accumulates its
+// rows -- H and Psi' are read column-contiguous (coalesced, and shared through L1/L2 by the warps
+// of the CTA, which all work on the same block), the state vector is broadcast from shared
+// memory.  Log-likelihood terms are accumulated per lane and reduced with warp shuffles once per
+// block; the accept decision is taken by lane 0 and broadcast.  The path record of one
+// (tile, chain) is 40 x 64 contiguous bytes, read and written by the warp as a whole.
+//
+// Same rows of SURVEY.md section 8a as dmcmc_solve.cu (a1-a7, a9, layout switch, init_ll).
+#include <cmath>
+
+#include "dmcmc_device.cuh"
+#include "dmcmc_internal.h"
+
+namespace dmcmc {
+
+constexpr int BIG_WARPS = 8;  // warps (= units) per CTA
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Lorenz-96 drift and its built-in auxiliary drift, row i, from the state in shared memory
+template <int D>
+__device__ __forceinline__ double l96_drift(const double *x, int i, double F) {
+    const int ip = (i + 1 == D) ? 0 : i + 1, im1 = (i == 0) ? D - 1 : i - 1, im2 = (i < 2) ? i + D - 2 : i - 2;
+    return (x[ip] - x[im2]) * x[im1] - x[i] + F;
+}
+template <int D>
+__device__ __forceinline__ double l96_aux_drift(const double *x, int i, double F, double c) {
+    const int ip = (i + 1 == D) ? 0 : i + 1, im2 = (i < 2) ? i + D - 2 : i - 2;
+    // B = -I + c (S_{+1} - S_{-2}), beta = F   (same summation order as the dense product)
+    return ((-x[i]) + c * x[ip] + (-c) * x[im2]) + F;
+}
+
+template <int D, bool PSI, int MODE, bool PHILOX, bool REINV>
+__global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolveParams p) {
+    constexpr int NS = (D + 31) / 32;
+    constexpr int REC = rec_size_big(D, PSI);
+    constexpr int OFF_H = 2, OFF_F = 2 + D * D, OFF_PSI = 2 + D * D + D;
+    constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
+    constexpr bool NEED_XA = !SOLVE || REINV;
+    constexpr bool NEED_WA = SOLVE && !REINV;
+    __shared__ double sm[BIG_WARPS][3][D];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long u = (long long)blockIdx.x * BIG_WARPS + warp;
+    if (u >= (long long)p.nblk * p.C) return;  // whole warp leaves; there is no CTA-wide barrier below
+    const int blk = (int)(u / p.C), chain = (int)(u % p.C);
+    const size_t uo = (size_t)chain * p.nblk + blk;
+    const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
+    const bool masked = (MODE == MODE_IMPUTE) &&
+                        ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
+    double *xs = sm[warp][0], *xas = sm[warp][1], *xbs = sm[warp][2];
+    int idx[NS];
+    bool has[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { idx[s] = lane + 32 * s; has[s] = idx[s] < D; }
+
+    const double Fth = p.th.v[0], sig = p.th.v[1], caux = p.th.v[2];
+    const double sig2 = sig * sig, isig = 1.0 / sig;
+    const bool fast_aux = p.fast_ok != 0;
+    const bool pinned = PSI && p.blk_pinned[blk];
+    const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
+
+    // ---- start point and pinned end point -----------------------------------------------------
+    auto end_value = [&](int j, int c) {
+        const int s = p.selX_in[(size_t)j * p.C + chain];
+        const int k = p.iv_N[j] - 1;
+        return p.X[s][x_off((size_t)p.iv_tile_off[j] + (k >> 3), chain, c, p.C, D) + (k & 7)];
+    };
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if (has[s]) {
+            const int c = idx[s];
+            const double v = p.iv_first[i1] ? p.x0[((size_t)p.iv_rec[i1] * D + c) * p.C + chain] : end_value(i1 - 1, c);
+            xs[c] = v;
+            xas[c] = v;
+            xbs[c] = pinned ? end_value(i2, c) : 0.0;
+        }
+    __syncwarp();
+
+    // per-lane rows of y = M' v with M stored [k][i] (column-contiguous for the lanes)
+    auto matvec = [&](const double *Mt, const double *v, double (&acc)[NS]) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < D; ++k) {
+            const double vk = v[k];
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (has[s]) acc[s] += __ldg(Mt + (size_t)k * D + idx[s]) * vk;
+        }
+    };
+
+    // ---- log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point ----------------
+    double llp, lla;
+    {
+        const double *rec = p.table + (size_t)p.iv_tile_off[i1] * TILE * REC;
+        double Hx[NS], Px[NS], Qx[NS];
+        matvec(rec + OFF_H, xs, Hx);
+        double part = 0.0;
+        if (PSI) matvec(rec + OFF_PSI, xbs, Px);
+        if (pinned) matvec(p.blk_Qc + (size_t)blk * D * D, xbs, Qx);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (has[s]) {
+                const int c = idx[s];
+                double f = __ldg(rec + OFF_F + c);
+                if (PSI) f += Px[s];
+                part += f * xs[c] - 0.5 * xs[c] * Hx[s];
+                if (pinned) part -= p.blk_g[(size_t)blk * D + c] * xbs[c] + 0.5 * xbs[c] * Qx[s];
+            }
+        llp = warp_sum(part) - p.blk_c0[blk];
+        lla = llp;
+    }
+
+    double lsum = 0.0, lsum_a = 0.0;  // per-lane partial sums of the Girsanov integrals
+
+    for (int j = i1; j <= i2; ++j) {
+        const int N = p.iv_N[j];
+        const size_t toff = (size_t)p.iv_tile_off[j];
+        const int nt = (N + TILE - 1) >> 3;
+        const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
+        const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
+        const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
+        const double *Wa = p.W[sw];
+        double *Wp = p.W[1 - sw];
+        const double *Xa = p.X[sx];
+        double *Xp = p.X[1 - sx];
+        const double *aB = p.auxB + (size_t)j * D * D, *abeta = p.auxbeta + (size_t)j * D;
+
+        for (int tl = 0; tl < nt; ++tl) {
+            const size_t tile = toff + tl;
+            double cur[NS][TILE], z[NS][TILE], xo[NS][TILE], dwo[NS][TILE];
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (has[s]) {
+                    if constexpr (NEED_XA) ld_tile(Xa + x_off(tile, chain, idx[s], p.C, D), cur[s]);
+                    if constexpr (NEED_WA) ld_tile(Wa + x_off(tile, chain, idx[s], p.C, D), cur[s]);
+                    if constexpr (MODE == MODE_IMPUTE) {
+                        if constexpr (PHILOX) {
+#pragma unroll
+                            for (int h = 0; h < TILE / 4; ++h)
+                                philox_normal4(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain,
+                                               (uint32_t)idx[s], (uint32_t)(tl * (TILE / 4) + h), &z[s][4 * h]);
+                        } else {
+                            ld_tile_stream(p.Z + x_off(tile, chain, idx[s], p.C, D), z[s]);
+                        }
+                    }
+                }
+#pragma unroll
+            for (int st = 0; st < TILE; ++st) {
+                const bool live = tl * TILE + st < N;  // warp-uniform
+                const double *rec = p.table + (tile * TILE + st) * REC;
+                double dw[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) dw[s] = 0.0;
+                if (live) {
+                    const double dt = __ldg(rec), sq = __ldg(rec + 1);
+                    // the three mat-vecs share one sweep over the columns
+                    double Hx[NS], Hxa[NS], Px[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) { Hx[s] = 0.0; Hxa[s] = 0.0; Px[s] = 0.0; }
+#pragma unroll 4
+                    for (int k = 0; k < D; ++k) {
+                        const double xk = xs[k], xak = xas[k], xbk = xbs[k];
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (has[s]) {
+                                const double h = __ldg(rec + OFF_H + (size_t)k * D + idx[s]);
+                                if (SOLVE) Hx[s] += h * xk;
+                                if (NEED_XA) Hxa[s] += h * xak;
+                                if (PSI) Px[s] += __ldg(rec + OFF_PSI + (size_t)k * D + idx[s]) * xbk;
+                            }
+                    }
+                    double xnew[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) xnew[s] = 0.0;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        if (has[s]) {
+                            const int c = idx[s];
+                            double F = __ldg(rec + OFF_F + c);
+                            if (PSI) F += Px[s];
+                            if constexpr (NEED_XA) {  // recover the accepted noise increment
+                                const double r = F - Hxa[s];
+                                const double b = l96_drift<D>(xas, c, Fth);
+                                double bt;
+                                if (fast_aux) bt = l96_aux_drift<D>(xas, c, Fth, caux);
+                                else {
+                                    double a = 0.0;
+                                    for (int k = 0; k < D; ++k) a += aB[(size_t)c * D + k] * xas[k];
+                                    bt = a + abeta[c];
+                                }
+                                lsum_a += ((b - bt) * r) * dt;
+                                const double res = cur[s][st] - xas[c] - (b + sig2 * r) * dt;
+                                dw[s] = res * isig;
+                            } else if constexpr (NEED_WA) {
+                                dw[s] = cur[s][st];
+                            }
+                            if constexpr (MODE == MODE_IMPUTE) dw[s] = lam * (sq * z[s][st]) + rho * dw[s];
+                            if constexpr (SOLVE) {
+                                const double r = F - Hx[s];
+                                const double b = l96_drift<D>(xs, c, Fth);
+                                double bt;
+                                if (fast_aux) bt = l96_aux_drift<D>(xs, c, Fth, caux);
+                                else {
+                                    double a = 0.0;
+                                    for (int k = 0; k < D; ++k) a += aB[(size_t)c * D + k] * xs[k];
+                                    bt = a + abeta[c];
+                                }
+                                lsum += ((b - bt) * r) * dt;
+                                xnew[s] = xs[c] + (b + sig2 * r) * dt + sig * dw[s];
+                            }
+                        }
+                    __syncwarp();  // everyone has read the old state
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        if (has[s]) {
+                            if constexpr (SOLVE) xs[idx[s]] = xnew[s];
+                            if constexpr (NEED_XA) xas[idx[s]] = cur[s][st];
+                        }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    dwo[s][st] = dw[s];
+                    if (SOLVE && has[s]) xo[s][st] = xs[idx[s]];
+                }
+            }
+            if (!masked) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (has[s]) {
+                        if constexpr (SOLVE) {
+                            if (pinned && j == i2 && tl == nt - 1) {
+                                const int last = (N - 1) & 7;
+#pragma unroll
+                                for (int st = 0; st < TILE; ++st) xo[s][st] = (st == last) ? xbs[idx[s]] : xo[s][st];
+                            }
+                            st_tile(Xp + x_off(tile, chain, idx[s], p.C, D), xo[s]);
+                        }
+                        if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
+                            double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
+                            st_tile(Wdst + x_off(tile, chain, idx[s], p.C, D), dwo[s]);
+                        }
+                    }
+            }
+        }
+    }
+    llp += warp_sum(lsum);
+    lla += warp_sum(lsum_a);
+
+    if constexpr (MODE == MODE_IMPUTE) {
+        if (masked) {
+            for (int j = i1 + lane; j <= i2; j += 32) {
+                const size_t o = (size_t)j * p.C + chain;
+                p.selX_out[o] = p.selX_in[o];
+                p.selW_out[o] = p.selW_in[o];
+            }
+            if (lane == 0 && p.blk_active && !p.blk_active[blk]) {
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = nan;
+                if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = nan;
+                if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = 0;
+            }
+            return;
+        }
+        double llcur = REINV ? lla : p.ll[uo];
+        const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain) : p.E[uo];
+        const bool ok = isfinite(llp);
+        const bool acc = p.force_accept ? ok : (e > -(llp - llcur));  // identical on every lane
+        for (int j = i1 + lane; j <= i2; j += 32) {
+            const size_t o = (size_t)j * p.C + chain;
+            p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
+            p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && p.store_w);
+        }
+        if (lane == 0) {
+            if (acc) {
+                llcur = llp;
+                if (p.acc_count) atomicAdd(p.acc_count + blk, 1ULL);
+            }
+            p.ll[uo] = llcur;
+            if (p.prop_count && chain == 0) atomicAdd(p.prop_count + blk, (unsigned long long)p.C);
+            if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = llp;
+            if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = llcur;
+            if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = (uint8_t)acc;
+        }
+    } else if constexpr (MODE == MODE_PARAM) {
+        if (lane == 0) {
+            if (p.out_llprop) p.out_llprop[uo] = llp;
+            if (p.out_acc) p.out_acc[uo] = (uint8_t)isfinite(llp);
+        }
+    } else {
+        if (lane == 0) p.ll[uo] = lla;
+    }
+}
+
+template <int D, bool PSI>
+static cudaError_t launch_big_model(int mode, const SolveParams &p, cudaStream_t s) {
+    const long long nunits = (long long)p.nblk * p.C;
+    if (nunits == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((nunits + BIG_WARPS - 1) / BIG_WARPS);
+    const unsigned threads = BIG_WARPS * 32;
+    const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
+#define DMCMC_LAUNCH(MODE_, PH_, RE_) solve_big_kernel<D, PSI, MODE_, PH_, RE_><<<grid, threads, 0, s>>>(p)
+    switch (mode) {
+    case MODE_IMPUTE:
+        if (philox) { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, true, true); else DMCMC_LAUNCH(MODE_IMPUTE, true, false); }
+        else        { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, false, true); else DMCMC_LAUNCH(MODE_IMPUTE, false, false); }
+        break;
+    case MODE_PARAM: DMCMC_LAUNCH(MODE_PARAM, false, false); break;
+    case MODE_RELAYOUT: DMCMC_LAUNCH(MODE_RELAYOUT, false, false); break;
+    case MODE_LOGLIK: DMCMC_LAUNCH(MODE_LOGLIK, false, false); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef DMCMC_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s) {
+    if (d != 40) return cudaErrorInvalidValue;
+    return p.has_psi ? launch_big_model<40, true>(mode, p, s) : launch_big_model<40, false>(mode, p, s);
+}
+
+}  // namespace dmcmc
