@@ -15,10 +15,10 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("model", C.c_int32), ("d", C.c_int32),
                 ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("interval_offset", C.c_int32),
                 ("device", C.c_int32),
-                ("seed", C.c_uint64), ("pin_eps", C.c_double)]
+                ("seed", C.c_uint64), ("pin_eps", C.c_double), ("store_noise", C.c_int32)]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); every symbol include/dmcmc.h declares
 SYMBOLS = {

@@ -373,9 +373,11 @@ int alloc_state(dmcmc_ctx *ctx) {
     const size_t ns = (size_t)ctx->J * ctx->C;
     for (int b = 0; b < 2; ++b) {
         CK(ctx->d_X[b].ensure(nx));
-        CK(ctx->d_W[b].ensure(nw));
         CK(cudaMemsetAsync(ctx->d_X[b].p, 0, nx * sizeof(double), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_W[b].p, 0, nw * sizeof(double), ctx->stream));
+        if (ctx->cfg.store_noise) {
+            CK(ctx->d_W[b].ensure(nw));
+            CK(cudaMemsetAsync(ctx->d_W[b].p, 0, nw * sizeof(double), ctx->stream));
+        }
         CK(ctx->d_selX[b].ensure(ns));
         CK(ctx->d_selW[b].ensure(ns));
         CK(cudaMemsetAsync(ctx->d_selX[b].p, 0, ns, ctx->stream));
@@ -827,7 +829,9 @@ static int impute_once(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const dou
     }
     sp.iter = iter;
     sp.force_accept = force_accept;
-    sp.reinvert = (!force_accept && !ctx->w_valid) ? 1 : 0;
+    // without stored noise every update recovers it from the accepted X (for init_paths, rho = 0
+    // makes the recovered value irrelevant)
+    sp.reinvert = ((!force_accept && !ctx->w_valid) || !ctx->cfg.store_noise) ? 1 : 0;
     sp.store_w = !sp.reinvert;
     sp.out_llprop = ctx->d_out_llprop.p;
     sp.out_ll = ctx->d_out_ll.p;
@@ -841,7 +845,7 @@ static int impute_once(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const dou
     }
     if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
     ctx->sel_cur ^= 1;
-    if (force_accept) ctx->w_valid = true;
+    if (force_accept) ctx->w_valid = ctx->cfg.store_noise != 0;
     if (out_ll_prop) CK(cudaMemcpyAsync(out_ll_prop, ctx->d_out_llprop.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_ll) CK(cudaMemcpyAsync(out_ll, ctx->d_out_ll.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_acc) CK(cudaMemcpyAsync(out_acc, ctx->d_out_acc.p, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -903,6 +907,7 @@ static int switch_layout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, 
 
 // materialise W (re-inversion) and ll under the current law/layout
 static int materialize_async(dmcmc_ctx *ctx) {
+    REQUIRE(ctx->cfg.store_noise, "this context was created with store_noise = 0: the accepted Wiener increments are not kept (parameter steps and dmcmc_relayout need them)");
     SolveParams sp;
     if (fill_params(ctx, sp, ctx->law_cur)) return -1;
     if (timed_launch(ctx, MODE_RELAYOUT, sp)) return -1;
@@ -1102,7 +1107,8 @@ int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W) {
     REQUIRE(ctx->lay_cur >= 0 && ctx->have_start, "dmcmc_download_state: context not initialised");
     CK(cudaSetDevice(ctx->cfg.device));
     Layout &lay = ctx->layout[ctx->lay_cur];
-    if (!ctx->w_valid && which == 0 && lay.tab[ctx->law_cur].valid && materialize_async(ctx)) return -1;
+    if (ctx->cfg.store_noise && !ctx->w_valid && which == 0 && lay.tab[ctx->law_cur].valid && materialize_async(ctx)) return -1;
+    REQUIRE(ctx->cfg.store_noise, "dmcmc_download_state: store_noise = 0 keeps no W; use dmcmc_download_path / dmcmc_download_segment");
     DevBuf<double> oX, oW;
     const size_t nX = (size_t)ctx->C * ctx->P * ctx->d, nW = (size_t)ctx->C * ctx->P * ctx->m;
     CK(oX.ensure(nX));
@@ -1127,21 +1133,17 @@ int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W) {
 int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_out) {
     REQUIRE(ctx && x_out, "dmcmc_download_path: bad argument");
     REQUIRE(chain >= 0 && chain < ctx->C && rec >= 0 && rec < ctx->R, "dmcmc_download_path: index out of range");
-    // glue: every interval's points but the last, then the final end point
-    // (_copy_path!, src/path_saving_buffer.jl:54-64)
-    std::vector<double> X((size_t)ctx->C * ctx->P * ctx->d), W((size_t)ctx->C * ctx->P * ctx->m);
-    if (dmcmc_download_state(ctx, 0, X.data(), W.data())) return -1;
+    REQUIRE(ctx->have_start, "dmcmc_download_path: context not initialised");
+    // glue: the starting point, then every interval's points 1..N -- exactly what _copy_path!
+    // builds from the per-interval containers (src/path_saving_buffer.jl:54-64)
     int j0 = 0;
     for (int r = 0; r < rec; ++r) j0 += ctx->rec_nobs[r];
-    const int j1 = j0 + ctx->rec_nobs[rec] - 1, d = ctx->d;
-    size_t off = 0;
-    for (int j = j0; j <= j1; ++j) {
-        const double *src = &X[((size_t)chain * ctx->P + ctx->pt_off[j]) * d];
-        std::copy(src, src + (size_t)ctx->N[j] * d, x_out + off * d);
-        off += ctx->N[j];
-    }
-    const double *last = &X[((size_t)chain * ctx->P + ctx->pt_off[j1] + ctx->N[j1]) * d];
-    std::copy(last, last + d, x_out + off * d);
+    const int j1 = j0 + ctx->rec_nobs[rec], d = ctx->d;
+    const int steps = ctx->st_off[j1] - ctx->st_off[j0];
+    std::vector<double> seg((size_t)ctx->C * steps * d);
+    if (segment_copy(ctx, j0, j1, seg.data(), false)) return -1;
+    for (int i = 0; i < d; ++i) x_out[i] = ctx->x0[((size_t)chain * ctx->R + rec) * d + i];
+    std::copy(seg.begin() + (size_t)chain * steps * d, seg.begin() + (size_t)(chain + 1) * steps * d, x_out + d);
     return 0;
 }
 

@@ -39,7 +39,8 @@ class DmcmcError(RuntimeError):
 
 
 class Engine:
-    def __init__(self, spec, device=0, seed=0, chain_offset=0, n_chains=None, interval_offset=0):
+    def __init__(self, spec, device=0, seed=0, chain_offset=0, n_chains=None, interval_offset=0,
+                 store_noise=True):
         self.lib = _lib.load()
         self.spec = spec
         self.model, self.d, self.m = int(spec["model"]), int(spec["d"]), int(spec["m"])
@@ -49,7 +50,7 @@ class Engine:
                 else np.broadcast_to(x0[:1], (n_chains,) + x0.shape[1:]).copy()
         self.C = x0.shape[0]
         cfg = _lib.Config(_lib.ABI_VERSION, self.model, self.d, self.C, chain_offset, interval_offset, device,
-                          seed, float(spec.get("pin_eps", 1e-4)))
+                          seed, float(spec.get("pin_eps", 1e-4)), int(bool(store_noise)))
         h = C.c_void_p()
         if self.lib.dmcmc_create(C.byref(cfg), C.byref(h)) != 0:
             raise DmcmcError(self.lib.dmcmc_last_error(None).decode())

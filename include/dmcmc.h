@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMCMC_ABI_VERSION 2
+#define DMCMC_ABI_VERSION 3
 
 /* Built-in diffusion laws (DiffusionDefinition.jl `@load_diffusion`, src/DiffusionMCMC.jl:4). */
 enum dmcmc_model {
@@ -53,6 +53,9 @@ typedef struct {
     int32_t device;        /* CUDA device ordinal                                                  */
     uint64_t seed;         /* Philox key                                                           */
     double pin_eps;        /* variance of the (almost exact) end-point observation of pinned blocks */
+    int32_t store_noise;   /* 1: keep the accepted Wiener increments W in HBM like the reference's    */
+                           /* WW containers; 0: never store W, always recover it from the accepted X  */
+                           /* (halves the state: needed for Lorenz-96 at full size)                   */
 } dmcmc_config;
 
 /* -- lifetime -------------------------------------------------------------------------------- */

@@ -13,11 +13,11 @@ const eMCMC = ExtensibleMCMC
 const OBS = ObservationSchemes
 
 const LIB = get(ENV, "DMCMC_B200_LIB", "libdmcmc_b200.so")
-const ABI_VERSION = Int32(2)
+const ABI_VERSION = Int32(3)
 
 struct Config
     abi_version::Int32; model::Int32; d::Int32; n_chains::Int32
-    chain_offset::Int32; interval_offset::Int32; device::Int32; seed::UInt64; pin_eps::Float64
+    chain_offset::Int32; interval_offset::Int32; device::Int32; seed::UInt64; pin_eps::Float64; store_noise::Int32
 end
 
 mutable struct Ctx
@@ -27,7 +27,7 @@ end
 check(ctx, rc) = rc == 0 || error(unsafe_string(ccall((:dmcmc_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h)))
 
 function Ctx(model, d, n_chains; device=0, seed=0x1, chain_offset=0, pin_eps=1e-4)
-    cfg = Ref(Config(ABI_VERSION, model, d, n_chains, chain_offset, 0, device, seed, pin_eps))
+    cfg = Ref(Config(ABI_VERSION, model, d, n_chains, chain_offset, 0, device, seed, pin_eps, 1))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:dmcmc_create, LIB), Cint, (Ref{Config}, Ref{Ptr{Cvoid}}), cfg, h)
     rc == 0 || error(unsafe_string(ccall((:dmcmc_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))

@@ -51,7 +51,7 @@ def test_no_cpu_fallback(lib):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     l = lib.load()
-    cfg = lib.Config(lib.ABI_VERSION, 0, 2, 4, 0, 0, 0, 1, 1e-4)
+    cfg = lib.Config(lib.ABI_VERSION, 0, 2, 4, 0, 0, 0, 1, 1e-4, 1)
     h = ctypes.c_void_p()
     assert l.dmcmc_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
     assert b"no CPU fallback" in l.dmcmc_last_error(None)
