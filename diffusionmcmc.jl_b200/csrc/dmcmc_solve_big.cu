@@ -17,12 +17,29 @@
 
 namespace dmcmc {
 
-constexpr int BIG_WARPS = 8;  // warps (= units) per CTA
+constexpr int BIG_WARPS = 16;  // warps (= chains) per CTA; all of them work on the same layout block
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32b(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_b(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32b(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_b(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32b(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_b(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32b(dst)), "l"(src), "r"(bytes), "r"(smem_u32b(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_b(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAITB_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra WAITB_DONE;\n bra WAITB_LOOP;\n WAITB_DONE:\n}" ::"r"(smem_u32b(b)), "r"(parity) : "memory");
 }
 
 // Lorenz-96 drift and its built-in auxiliary drift, row i, from the state in shared memory
@@ -34,10 +51,13 @@ __device__ __forceinline__ double l96_drift(const double *x, int i, double F) {
 template <int D>
 __device__ __forceinline__ double l96_aux_drift(const double *x, int i, double F, double c) {
     const int ip = (i + 1 == D) ? 0 : i + 1, im2 = (i < 2) ? i + D - 2 : i - 2;
-    // B = -I + c (S_{+1} - S_{-2}), beta = F   (same summation order as the dense product)
-    return ((-x[i]) + c * x[ip] + (-c) * x[im2]) + F;
+    return ((-x[i]) + c * x[ip] + (-c) * x[im2]) + F;  // B = -I + c (S_{+1} - S_{-2}), beta = F
 }
 
+// One CTA = one layout block x BIG_WARPS chains, one warp = one (chain, block) unit, lanes = state
+// components.  The CTA walks the block's Euler steps in lockstep: the step's table record
+// (H, F0, Psi': 26 KB for d = 40) is brought into shared memory ONCE per CTA by a TMA bulk copy,
+// double-buffered one step ahead, and read by every warp as conflict-free LDS.
 template <int D, bool PSI, int MODE, bool PHILOX, bool REINV>
 __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolveParams p) {
     constexpr int NS = (D + 31) / 32;
@@ -46,17 +66,23 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
     constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
     constexpr bool NEED_XA = !SOLVE || REINV;
     constexpr bool NEED_WA = SOLVE && !REINV;
-    __shared__ double sm[BIG_WARPS][3][D];
+    extern __shared__ __align__(128) double dsm[];
+    double *stage0 = dsm, *stage1 = dsm + REC;
+    double *vecs = dsm + 2 * REC;  // [BIG_WARPS][3][D]
+    __shared__ __align__(8) uint64_t full[2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long u = (long long)blockIdx.x * BIG_WARPS + warp;
-    if (u >= (long long)p.nblk * p.C) return;  // whole warp leaves; there is no CTA-wide barrier below
-    const int blk = (int)(u / p.C), chain = (int)(u % p.C);
+    const int groups = (p.C + BIG_WARPS - 1) / BIG_WARPS;
+    const int blk = (int)(blockIdx.x / groups);
+    const int chain_raw = (int)(blockIdx.x % groups) * BIG_WARPS + warp;
+    const bool in_range = chain_raw < p.C;
+    const int chain = in_range ? chain_raw : p.C - 1;  // surplus warps shadow the last chain (stores off)
     const size_t uo = (size_t)chain * p.nblk + blk;
     const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
     const bool masked = (MODE == MODE_IMPUTE) &&
                         ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
-    double *xs = sm[warp][0], *xas = sm[warp][1], *xbs = sm[warp][2];
+    const bool active = in_range && !masked;
+    double *xs = vecs + (size_t)warp * 3 * D, *xas = xs + D, *xbs = xas + D;
     int idx[NS];
     bool has[NS];
 #pragma unroll
@@ -67,6 +93,19 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
     const bool fast_aux = p.fast_ok != 0;
     const bool pinned = PSI && p.blk_pinned[blk];
     const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
+
+    if (threadIdx.x == 0) {
+        mbar_init_b(&full[0], 1);
+        mbar_init_b(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](size_t step_index, int q) {  // thread 0: stage the record of one Euler step
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx_b(&full[q & 1], (uint32_t)(REC * sizeof(double)));
+        bulk_g2s_b((q & 1) ? stage1 : stage0, p.table + step_index * REC, (uint32_t)(REC * sizeof(double)), &full[q & 1]);
+    };
+    if (threadIdx.x == 0) issue((size_t)p.iv_tile_off[i1] * TILE, 0);
 
     // ---- start point and pinned end point -----------------------------------------------------
     auto end_value = [&](int j, int c) {
@@ -85,42 +124,9 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
         }
     __syncwarp();
 
-    // per-lane rows of y = M' v with M stored [k][i] (column-contiguous for the lanes)
-    auto matvec = [&](const double *Mt, const double *v, double (&acc)[NS]) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) acc[s] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < D; ++k) {
-            const double vk = v[k];
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-                if (has[s]) acc[s] += __ldg(Mt + (size_t)k * D + idx[s]) * vk;
-        }
-    };
-
-    // ---- log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point ----------------
-    double llp, lla;
-    {
-        const double *rec = p.table + (size_t)p.iv_tile_off[i1] * TILE * REC;
-        double Hx[NS], Px[NS], Qx[NS];
-        matvec(rec + OFF_H, xs, Hx);
-        double part = 0.0;
-        if (PSI) matvec(rec + OFF_PSI, xbs, Px);
-        if (pinned) matvec(p.blk_Qc + (size_t)blk * D * D, xbs, Qx);
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-            if (has[s]) {
-                const int c = idx[s];
-                double f = __ldg(rec + OFF_F + c);
-                if (PSI) f += Px[s];
-                part += f * xs[c] - 0.5 * xs[c] * Hx[s];
-                if (pinned) part -= p.blk_g[(size_t)blk * D + c] * xbs[c] + 0.5 * xbs[c] * Qx[s];
-            }
-        llp = warp_sum(part) - p.blk_c0[blk];
-        lla = llp;
-    }
-
+    double llp = 0.0, lla = 0.0;
     double lsum = 0.0, lsum_a = 0.0;  // per-lane partial sums of the Girsanov integrals
+    int q = 0;                        // Euler steps staged so far (pipeline position)
 
     for (int j = i1; j <= i2; ++j) {
         const int N = p.iv_N[j];
@@ -154,29 +160,59 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
                         }
                     }
                 }
+            const int nlive = min(TILE, N - tl * TILE);
 #pragma unroll
             for (int st = 0; st < TILE; ++st) {
-                const bool live = tl * TILE + st < N;  // warp-uniform
-                const double *rec = p.table + (tile * TILE + st) * REC;
                 double dw[NS];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) dw[s] = 0.0;
-                if (live) {
-                    const double dt = __ldg(rec), sq = __ldg(rec + 1);
-                    // the three mat-vecs share one sweep over the columns
+                if (st < nlive) {  // CTA-uniform
+                    // ---- pipeline: everyone is done with the other stage, refill it one step ahead ----
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        if (st + 1 < nlive) issue((tile * TILE) + st + 1, q + 1);
+                        else if (tl + 1 < nt) issue((tile + 1) * TILE, q + 1);
+                        else if (j + 1 <= i2) issue((size_t)p.iv_tile_off[j + 1] * TILE, q + 1);
+                    }
+                    mbar_wait_b(&full[q & 1], (uint32_t)((q >> 1) & 1));
+                    const double *rec = (q & 1) ? stage1 : stage0;
+                    ++q;
+                    if (q == 1) {
+                        // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point
+                        double part = 0.0;
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (has[s]) {
+                                const int c = idx[s];
+                                double hx = 0.0, px = 0.0, qx = 0.0;
+                                for (int k = 0; k < D; ++k) {
+                                    hx += rec[OFF_H + k * D + c] * xs[k];
+                                    if (PSI) px += rec[OFF_PSI + k * D + c] * xbs[k];
+                                    if (pinned) qx += p.blk_Qc[(size_t)blk * D * D + (size_t)k * D + c] * xbs[k];
+                                }
+                                double f = rec[OFF_F + c];
+                                if (PSI) f += px;
+                                part += f * xs[c] - 0.5 * xs[c] * hx;
+                                if (pinned) part -= p.blk_g[(size_t)blk * D + c] * xbs[c] + 0.5 * xbs[c] * qx;
+                            }
+                        llp = warp_sum(part) - p.blk_c0[blk];
+                        lla = llp;
+                    }
+                    const double dt = rec[0], sq = rec[1];
+                    // the three mat-vecs share one sweep over the columns (LDS, conflict-free rows)
                     double Hx[NS], Hxa[NS], Px[NS];
 #pragma unroll
                     for (int s = 0; s < NS; ++s) { Hx[s] = 0.0; Hxa[s] = 0.0; Px[s] = 0.0; }
-#pragma unroll 4
+#pragma unroll 8
                     for (int k = 0; k < D; ++k) {
                         const double xk = xs[k], xak = xas[k], xbk = xbs[k];
 #pragma unroll
                         for (int s = 0; s < NS; ++s)
                             if (has[s]) {
-                                const double h = __ldg(rec + OFF_H + (size_t)k * D + idx[s]);
+                                const double h = rec[OFF_H + k * D + idx[s]];
                                 if (SOLVE) Hx[s] += h * xk;
                                 if (NEED_XA) Hxa[s] += h * xak;
-                                if (PSI) Px[s] += __ldg(rec + OFF_PSI + (size_t)k * D + idx[s]) * xbk;
+                                if (PSI) Px[s] += rec[OFF_PSI + k * D + idx[s]] * xbk;
                             }
                     }
                     double xnew[NS];
@@ -186,7 +222,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
                     for (int s = 0; s < NS; ++s)
                         if (has[s]) {
                             const int c = idx[s];
-                            double F = __ldg(rec + OFF_F + c);
+                            double F = rec[OFF_F + c];
                             if (PSI) F += Px[s];
                             if constexpr (NEED_XA) {  // recover the accepted noise increment
                                 const double r = F - Hxa[s];
@@ -234,7 +270,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
                     if (SOLVE && has[s]) xo[s][st] = xs[idx[s]];
                 }
             }
-            if (!masked) {
+            if (active) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
                     if (has[s]) {
@@ -256,6 +292,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
     }
     llp += warp_sum(lsum);
     lla += warp_sum(lsum_a);
+    if (!in_range) return;
 
     if constexpr (MODE == MODE_IMPUTE) {
         if (masked) {
@@ -304,12 +341,19 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
 
 template <int D, bool PSI>
 static cudaError_t launch_big_model(int mode, const SolveParams &p, cudaStream_t s) {
-    const long long nunits = (long long)p.nblk * p.C;
-    if (nunits == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((nunits + BIG_WARPS - 1) / BIG_WARPS);
+    if ((long long)p.nblk * p.C == 0) return cudaSuccess;
+    const unsigned groups = (unsigned)((p.C + BIG_WARPS - 1) / BIG_WARPS);
+    const unsigned grid = groups * (unsigned)p.nblk;
     const unsigned threads = BIG_WARPS * 32;
+    const size_t smem = (size_t)(2 * rec_size_big(D, PSI) + BIG_WARPS * 3 * D) * sizeof(double);
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
-#define DMCMC_LAUNCH(MODE_, PH_, RE_) solve_big_kernel<D, PSI, MODE_, PH_, RE_><<<grid, threads, 0, s>>>(p)
+#define DMCMC_LAUNCH(MODE_, PH_, RE_)                                                                      \
+    do {                                                                                                   \
+        cudaError_t e_ = cudaFuncSetAttribute(solve_big_kernel<D, PSI, MODE_, PH_, RE_>,                    \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e_ != cudaSuccess) return e_;                                                                  \
+        solve_big_kernel<D, PSI, MODE_, PH_, RE_><<<grid, threads, smem, s>>>(p);                          \
+    } while (0)
     switch (mode) {
     case MODE_IMPUTE:
         if (philox) { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, true, true); else DMCMC_LAUNCH(MODE_IMPUTE, true, false); }
