@@ -77,7 +77,8 @@ struct dmcmc_ctx {
     size_t ev_used = 0;
     bool timing = true;
     // host copies
-    std::vector<int32_t> rec_nobs, N, pt_off, st_off, tile_off, iv_first, iv_rec;
+    std::vector<int32_t> rec_nobs, N, pt_off, st_off, tile_off, iv_first, iv_rec, xs;
+    std::vector<int64_t> xoff;  // [J+1] X container layout: interval j starts at xoff[j], chain stride xs[j]
     std::vector<double> t, L, Sigma, v, Hobs, Fobs, cobs, rho, x0;
     bool have_grid = false, have_obs = false, have_start = false;
     Law law[2];
@@ -86,7 +87,8 @@ struct dmcmc_ctx {
     int lay_cur = -1;
     uint64_t lay_clock = 0;
     // device
-    DevBuf<int32_t> d_N, d_tile_off, d_first, d_rec, d_pt_off, d_st_off;
+    DevBuf<int32_t> d_N, d_tile_off, d_first, d_rec, d_pt_off, d_st_off, d_xs;
+    DevBuf<int64_t> d_xoff;
     DevBuf<double> d_t, d_rho, d_Hobs, d_Fobs, d_cobs, d_x0, d_ll, d_Z, d_E;
     DevBuf<double> d_X[2], d_W[2];
     DevBuf<uint8_t> d_selX[2], d_selW[2], d_mask, d_out_acc;
@@ -310,6 +312,7 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     sp.blk_i1 = lay.d_i1.p; sp.blk_i2 = lay.d_i2.p; sp.blk_pinned = lay.d_pinned.p;
     sp.iv_N = ctx->d_N.p; sp.iv_tile_off = ctx->d_tile_off.p; sp.iv_first = ctx->d_first.p;
     sp.iv_rec = ctx->d_rec.p;
+    sp.iv_xoff = ctx->d_xoff.p; sp.iv_xs = ctx->d_xs.p;
     sp.rho = ctx->d_rho.p;
     sp.auxB = law.d_auxB.p; sp.auxbeta = law.d_auxbeta.p; sp.auxatil = law.d_auxatil.p;
     sp.table = tb.table.p; sp.blk_c0 = tb.blk_c0.p; sp.blk_g = tb.blk_g.p; sp.blk_Qc = tb.blk_Qc.p;
@@ -360,7 +363,7 @@ int stage_noise(dmcmc_ctx *ctx, const double *Z) {
             for (int k = 0; k < ctx->N[j]; ++k) {
                 const size_t tile = (size_t)ctx->tile_off[j] + (k >> 3);
                 for (int w = 0; w < m; ++w)
-                    buf[x_off(tile, c, w, C, m) + (k & 7)] =
+                    buf[w_off(tile, c, w, C, m) + (k & 7)] =
                         Z[((size_t)c * ctx->S + ctx->st_off[j] + k) * m + w];
             }
     CK(ctx->d_Z.ensure(n));
@@ -369,7 +372,7 @@ int stage_noise(dmcmc_ctx *ctx, const double *Z) {
 }
 
 int alloc_state(dmcmc_ctx *ctx) {
-    const size_t nx = (size_t)ctx->d * ctx->TT * ctx->C * TILE, nw = (size_t)ctx->m * ctx->TT * ctx->C * TILE;
+    const size_t nx = (size_t)ctx->xoff[ctx->J], nw = (size_t)ctx->m * ctx->TT * ctx->C * TILE;
     const size_t ns = (size_t)ctx->J * ctx->C;
     for (int b = 0; b < 2; ++b) {
         CK(ctx->d_X[b].ensure(nx));
@@ -538,6 +541,8 @@ int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs
     ctx->tile_off.assign(J + 1, 0);
     ctx->iv_first.assign(J, 0);
     ctx->iv_rec.assign(J, 0);
+    ctx->xoff.assign(J + 1, 0);
+    ctx->xs.assign(J, 0);
     int j = 0;
     for (int r = 0; r < n_recordings; ++r)
         for (int i = 0; i < rec_nobs[r]; ++i, ++j) {
@@ -549,6 +554,8 @@ int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs
         ctx->pt_off[j + 1] = ctx->pt_off[j] + n_steps[j] + 1;
         ctx->st_off[j + 1] = ctx->st_off[j] + n_steps[j];
         ctx->tile_off[j + 1] = ctx->tile_off[j] + (n_steps[j] + TILE - 1) / TILE;
+        ctx->xs[j] = x_stride(n_steps[j], ctx->d);
+        ctx->xoff[j + 1] = ctx->xoff[j] + (int64_t)ctx->C * ctx->xs[j];
     }
     ctx->P = ctx->pt_off[J];
     ctx->S = ctx->st_off[J];
@@ -560,7 +567,7 @@ int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs
     if (upload(ctx, ctx->d_N, ctx->N) || upload(ctx, ctx->d_tile_off, ctx->tile_off) ||
         upload(ctx, ctx->d_first, ctx->iv_first) || upload(ctx, ctx->d_rec, ctx->iv_rec) ||
         upload(ctx, ctx->d_pt_off, ctx->pt_off) || upload(ctx, ctx->d_st_off, ctx->st_off) ||
-        upload(ctx, ctx->d_t, ctx->t))
+        upload(ctx, ctx->d_xoff, ctx->xoff) || upload(ctx, ctx->d_xs, ctx->xs) || upload(ctx, ctx->d_t, ctx->t))
         return -1;
     ctx->rho.assign(J, 0.0);
     if (upload(ctx, ctx->d_rho, ctx->rho)) return -1;
@@ -688,6 +695,7 @@ static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool 
     SegmentParams g{};
     g.C = ctx->C; g.D = ctx->d; g.j0 = j0; g.j1 = j1; g.steps = steps; g.TT = ctx->TT;
     g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_st_off = ctx->d_st_off.p;
+    g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
     g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
     g.selX = ctx->d_selX[ctx->sel_cur].p;
     g.packed = pk.p; g.upload = up;
@@ -1118,6 +1126,7 @@ int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W) {
     g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_first = ctx->d_first.p;
     g.iv_rec = ctx->d_rec.p; g.iv_pt_off = ctx->d_pt_off.p; g.iv_blk = lay.d_iv_blk.p;
     g.blk_i1 = lay.d_i1.p;
+    g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
     for (int b = 0; b < 2; ++b) { g.X[b] = ctx->d_X[b].p; g.W[b] = ctx->d_W[b].p; }
     g.selX = ctx->d_selX[ctx->sel_cur].p; g.selW = ctx->d_selW[ctx->sel_cur].p;
     g.x0 = ctx->d_x0.p; g.which = which; g.outX = oX.p; g.outW = oW.p;

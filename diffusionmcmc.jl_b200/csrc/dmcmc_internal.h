@@ -24,6 +24,8 @@ struct SolveParams {
     const int32_t *blk_active;  // nullptr: every block is updated
     // intervals
     const int32_t *iv_N, *iv_tile_off, *iv_first, *iv_rec;
+    const int64_t *iv_xoff; // [J] first element of interval j in an X container
+    const int32_t *iv_xs;   // [J] per-chain stride of interval j in an X container: even(N_j * D)
     const double *rho;      // [J]
     const double *auxB;     // [J][D*D]
     const double *auxbeta;  // [J][D]
@@ -35,7 +37,7 @@ struct SolveParams {
     const double *blk_Qc;   // [nblk][D*D]
     int32_t has_psi;
     // state
-    double *X[2];           // [TT][C][D][8]  one record per (tile, chain)
+    double *X[2];           // [iv_xoff[j] + chain * iv_xs[j] + k * D + comp]  one record per (interval, chain)
     double *W[2];           // [TT][C][M][8]
     // accepted-container selectors [J][C]: read from *_in, written (flipped on accept) to *_out;
     // the two arrays are swapped by the host after the sweep, so no unit ever reads a selector
@@ -53,6 +55,7 @@ struct SolveParams {
     int32_t reinvert;   // 1: accepted noise is recovered from the accepted X (stored W is stale)
     int32_t store_w;    // 1: write the proposal noise W deg (0 when the next update re-inverts anyway)
     int32_t fast_ok;    // 1: the law uses the model's built-in aux law (fused model-specific step allowed)
+    int32_t depth;      // tiles in flight of the table / input pipelines (2, 4 or 8; set by the launcher)
     int32_t out_stride; // row stride (per chain) of out_llprop / out_ll / out_acc
     const uint8_t *unit_mask;  // [C][nblk] or nullptr
     // outputs
@@ -71,6 +74,8 @@ struct GatherParams {
     int32_t C, J, D, M;
     int64_t TT;
     const int32_t *iv_N, *iv_tile_off, *iv_first, *iv_rec, *iv_pt_off, *iv_blk;
+    const int64_t *iv_xoff;
+    const int32_t *iv_xs;
     const int32_t *blk_i1;
     const double *X[2], *W[2];
     const uint8_t *selX, *selW;
@@ -87,6 +92,8 @@ struct SegmentParams {
     int32_t C, D, j0, j1, steps;
     int64_t TT;
     const int32_t *iv_N, *iv_tile_off, *iv_st_off;
+    const int64_t *iv_xoff;
+    const int32_t *iv_xs;
     double *X[2];
     const uint8_t *selX;
     double *packed;   // device [C][steps][D]

@@ -2,13 +2,19 @@
 //
 // One thread owns one (chain, block) unit -- the parallel axis the reference itself names
 // ("this loop should be entirely parallelizable", /root/reference src/run!_alterations.jl:15-16)
-// times the chain batch axis.  Consecutive lanes are consecutive chains of the same block, so
-//   * path/noise traffic is 64 contiguous bytes per lane per 8 steps (256-bit LDG/STG), 2 KB per
-//     warp request, and
-//   * the backward-filter table record of a step is the same address for the whole warp (one
-//     broadcast transaction).
-// Inside a unit the Euler recursion is serial (x_{k+1} needs x_k); everything that does not
-// depend on x -- accepted-noise loads, Philox/Box-Muller, table records -- is issued a tile ahead.
+// times the chain batch axis.  One CTA = one layout block x blockDim.x consecutive chains, so the
+// backward-filter table of the block is shared by the whole CTA.  Inside a unit the Euler
+// recursion is serial (x_{k+1} needs x_k); everything that does not depend on x is moved off
+// that chain:
+//   * the accepted path is brought into shared memory by 16-byte asynchronous copies (LDGSTS), 16
+//     consecutive lanes per (chain, 16-step tile) = 256 contiguous bytes, one tile ahead, no
+//     registers involved; each lane then reads its own chain's states with conflict-free LDS.128;
+//   * the block's table records are streamed by TMA bulk copies (UBLKCP + mbarrier) one tile
+//     ahead, and for FitzHugh-Nagumo rewritten once per CTA into the per-step coefficients that
+//     are the same for every chain (fhn_derive), so the per-chain step is ~30 FP64 instructions;
+//   * Philox4x32-10 normals are generated in-register, four per call;
+//   * the proposal is stored straight from registers, 32 bytes per two steps, into the chain's
+//     proposal container (whole 128-byte lines are assembled in L2 before they reach HBM).
 //
 // Reference rows:
 //   a2 pCN refresh            forward_guide!(..., rho, ...; Wnr)   src/run!_alterations.jl:18-21
@@ -18,7 +24,9 @@
 //   a6 accept                 eMCMC.accept_reject!                 src/run!_alterations.jl:22-24
 //   a7 register + swap        swap_paths!                          src/run!_alterations.jl:36-47, :81-91
 //   a9 parameter-step solve   set_proposal!                        src/run!_alterations.jl:177-211
+#include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "dmcmc_device.cuh"
 #include "dmcmc_internal.h"
@@ -88,64 +96,59 @@ __device__ __forceinline__ void guided_terms(const Theta &th, const double *__re
 // ---- FitzHugh-Nagumo fused step (built-in FitzHughNagumoAux only) ------------------------------
 // With the aux law's second row equal to the target's (B = [., .; gamma, -1], beta~_2 = beta) and
 // B_12 = -1/eps, the Girsanov integrand collapses to
-//     (b - b~)'r = [ (1/eps - B_11) y - y^3/eps - (beta~_1 - s/eps) ] r_1 ,
-// a r = (0, sigma^2 r_2), and the noise recovery only needs the second coordinate.  Same
-// mathematics as guided_terms, ~3x fewer FP64 instructions; differences are rounding-level.
+//     (b - b~)'r = [ (y - y^3)/eps - B_11 y - (beta~_1 - s/eps) ] r_1 ,
+// and a r = (0, sigma^2 r_2), so the second coordinate is an affine map of the state,
+//     x' = A1 x + B1 y + Cf + sigma dW ,   A1 = 1 - dt (1 + sigma^2 H_22),  B1 = dt (gamma - sigma^2 H_12),
+//     Cf = dt (beta + sigma^2 F_2) ,       F = F0 + Psi x_b .
+// A1, B1 and the dt-scaled rows of H, F0, Psi are the same for every chain: fhn_derive rewrites
+// the staged table records once per CTA.  Same mathematics as guided_terms, ~3x fewer FP64
+// instructions per chain and step; differences are rounding-level.
 struct FhnK {
     double ie, s, gam, bet, sig, sig2, isig;  // per law
-    double c1, c2;                            // per interval
+    double aB0, c2;                            // per interval
     __device__ __forceinline__ void set_law(const Theta &th) {
         ie = 1.0 / th.v[0]; s = th.v[1]; gam = th.v[2]; bet = th.v[3]; sig = th.v[4];
         sig2 = sig * sig; isig = 1.0 / sig;
     }
-    __device__ __forceinline__ void set_interval(const double *aB, const double *abeta) {
-        c1 = ie - aB[0];
-        c2 = abeta[0] - s * ie;
-    }
-    // Girsanov increment and guiding term r_2 at state (y, x)
-    template <bool PSI>
-    __device__ __forceinline__ void terms(const double *rec, const double *F, double y, double x,
-                                          double dt, double &dll, double &r2) const {
-        using R = Rec<2, PSI>;
-        const double r1 = fma(-rec[R::OFF_H + 1], x, fma(-rec[R::OFF_H], y, F[0]));
-        r2 = fma(-rec[R::OFF_H + 2], x, fma(-rec[R::OFF_H + 1], y, F[1]));
-        const double y3 = (y * y) * y;
-        const double d1 = fma(-ie, y3, fma(c1, y, -c2));
-        dll = (d1 * r1) * dt;
+    __device__ __forceinline__ void set_interval(const double *auxB, const double *auxbeta) {
+        aB0 = auxB[0];
+        c2 = auxbeta[0] - s * ie;
     }
 };
 
-template <int REC>
-__device__ __forceinline__ void load_rec(const double *__restrict__ p, double *r) {
-#pragma unroll
-    for (int i = 0; i < REC / 2; ++i) {
-        const double2 v = __ldg(reinterpret_cast<const double2 *>(p) + i);
-        r[2 * i] = v.x;
-        r[2 * i + 1] = v.y;
+// derived record: [A1, B1, C1, dt/eps, dt H11, dt H12, dt F0_1, lam sqrt(dt) | dt s2 Psi21, dt s2 Psi22, dt Psi11, dt Psi12]
+enum { FD_A1 = 0, FD_B1, FD_C1, FD_KIE, FD_G00, FD_G01, FD_R0, FD_LSQ, FD_Q10, FD_Q11, FD_T00, FD_T01 };
+
+template <bool PSI>
+__device__ __forceinline__ void fhn_derive(double *r, const FhnK &fk, double lam) {
+    using R = Rec<2, PSI>;
+    const double dt = r[0], sq = r[1];
+    const double H00 = r[R::OFF_H], H01 = r[R::OFF_H + 1], H11 = r[R::OFF_H + 2];
+    const double F0 = r[R::OFF_F], F1 = r[R::OFF_F + 1];
+    double P00 = 0.0, P01 = 0.0, P10 = 0.0, P11 = 0.0;
+    if constexpr (PSI) { P00 = r[R::OFF_PSI]; P01 = r[R::OFF_PSI + 1]; P10 = r[R::OFF_PSI + 2]; P11 = r[R::OFF_PSI + 3]; }
+    const double ds2 = dt * fk.sig2;
+    r[FD_A1] = fma(-ds2, H11, 1.0 - dt);
+    r[FD_B1] = fma(-ds2, H01, dt * fk.gam);
+    r[FD_C1] = fma(ds2, F1, dt * fk.bet);
+    r[FD_KIE] = dt * fk.ie;
+    r[FD_G00] = dt * H00;
+    r[FD_G01] = dt * H01;
+    r[FD_R0] = dt * F0;
+    r[FD_LSQ] = lam * sq;
+    if constexpr (PSI) {
+        r[FD_Q10] = ds2 * P10; r[FD_Q11] = ds2 * P11;
+        r[FD_T00] = dt * P00;  r[FD_T01] = dt * P01;
     }
 }
 
-// end point of interval j (value after its last Euler step) in the accepted container
-template <int D>
-__device__ __forceinline__ void load_end(const SolveParams &p, int chain, int j, double *x) {
-    const int s = p.selX_in[(size_t)j * p.C + chain];
-    const int k = p.iv_N[j] - 1;
-    const size_t tile = (size_t)p.iv_tile_off[j] + (k >> 3);
-    const double *X = p.X[s];
-#pragma unroll
-    for (int c = 0; c < D; ++c)
-        x[c] = X[x_off(tile, chain, c, p.C, D) + (k & 7)];
-}
-
-template <int D>
-__device__ __forceinline__ void load_start(const SolveParams &p, int chain, int j, double *x) {
-    if (p.iv_first[j]) {
-        const int rec = p.iv_rec[j];
-#pragma unroll
-        for (int c = 0; c < D; ++c) x[c] = p.x0[((size_t)rec * D + c) * p.C + chain];
-    } else {
-        load_end<D>(p, chain, j - 1, x);
-    }
+// adds the Girsanov increment G dt at state (y, x) to ll; g = y - y^3 is returned for the drift
+__device__ __forceinline__ void fhn_dll(const FhnK &fk, const double *rec, double R0c, double y, double x, double &g, double &ll) {
+    const double y2 = y * y;
+    g = fma(-y2, y, y);
+    const double d1 = fma(fk.ie, g, fma(-fk.aB0, y, -fk.c2));
+    const double r1dt = fma(-rec[FD_G00], y, fma(-rec[FD_G01], x, R0c));
+    ll = fma(d1, r1dt, ll);
 }
 
 // ---- TMA bulk copy + mbarrier plumbing (sm_90+/sm_100a PTX) -------------------------------------
@@ -177,24 +180,105 @@ __device__ __forceinline__ void load_rec_smem(const double *p, double *r) {
     }
 }
 
-constexpr int CHUNK_TILES = 16;  // table records staged per bulk copy: 16 tiles = 128 Euler steps
+// state after the last Euler step of interval j in the accepted container
+template <int D>
+__device__ __forceinline__ void load_end(const SolveParams &p, int chain, int j, double *x) {
+    const int s = p.selX_in[(size_t)j * p.C + chain];
+    const double *X = p.X[s] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j] + (size_t)(p.iv_N[j] - 1) * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) x[c] = X[c];
+}
 
-// One CTA = one layout block x blockDim.x consecutive chains; one thread = one (chain, block)
-// unit.  The block's backward-filter table is streamed through shared memory in chunks of
-// CHUNK_TILES tiles by TMA bulk copies (double-buffered, mbarrier-signalled), so the per-step
-// H/F/Psi record is an LDS broadcast instead of a dependent global load.
+template <int D>
+__device__ __forceinline__ void load_start(const SolveParams &p, int chain, int j, double *x) {
+    if (p.iv_first[j]) {
+        const int rec = p.iv_rec[j];
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c] = p.x0[((size_t)rec * D + c) * p.C + chain];
+    } else {
+        load_end<D>(p, chain, j - 1, x);
+    }
+}
+
+constexpr int TS = 16;        // Euler steps per staged tile: 256 contiguous bytes per chain for d = 2
+constexpr int MAX_DEPTH = 8;  // deepest software pipeline (tiles in flight) of the table / input stages
+
+// ---- shared-memory stage of a chain's input stream (accepted path, or stored accepted noise) ------
+// The stream of one (chain, tile) is cut into 16-byte pieces that 16 (d = 2) consecutive lanes copy
+// with one LDGSTS each: 256 contiguous bytes per chain in HBM and in shared memory.
+//   XA = true : accepted path,  stream index of (step k, component c) = k * D + c
+//   XA = false: accepted noise, stream index of (step k, Wiener comp w) = ((k / 8) * M + w) * 8 + k % 8
+//               (two tiles of the W container)
+// d = 2 path stages are unpadded (256 B per chain, 8 KB per warp: six CTAs per SM) and XOR-swizzled:
+// piece pc of chain r sits in 16-byte slot pc ^ (r & 7) of its record, so that the eight lanes of an
+// LDS.128 phase (same step, eight chains) hit eight different bank groups.  Other shapes pad the
+// record by 16 bytes instead.
+template <int D, int M, bool XA>
+struct InStage {
+    static constexpr int NPT = XA ? TS * D / 2 : (TS / TILE) * M * 4;  // pieces per (tile, chain)
+    static constexpr bool SWZ = XA && D == 2;
+    static constexpr int RECW = 2 * NPT + (SWZ ? 0 : 2);               // doubles per chain
+    static constexpr int WARP = 32 * RECW;                             // doubles per warp and stage
+    __device__ static __forceinline__ int piece(int r, int pc) {
+        return SWZ ? r * RECW + ((pc ^ (r & 7)) << 1) : r * RECW + pc * 2;
+    }
+    // per-lane read cursor of a stage: byte address with the swizzle folded in (stage is 256-byte aligned)
+    __device__ static __forceinline__ uint32_t cursor(const double *stage, int lane) {
+        const uint32_t a = smem_u32(stage) + (uint32_t)lane * RECW * 8u;
+        return SWZ ? a ^ ((uint32_t)(lane & 7) << 4) : a;
+    }
+    // state after step k of the tile (XA)
+    __device__ static __forceinline__ void state(uint32_t cur, int k, double *x) {
+        if constexpr (SWZ) {
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "r"(cur ^ ((uint32_t)k << 4)));
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c)
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x[c]) : "r"(cur + (uint32_t)(k * D + c) * 8u));
+        }
+    }
+    // accepted noise increment of step k (!XA)
+    __device__ static __forceinline__ void noise(uint32_t cur, int k, double *dw) {
+#pragma unroll
+        for (int w = 0; w < M; ++w)
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dw[w]) : "r"(cur + (uint32_t)(((k >> 3) * M + w) * 8 + (k & 7)) * 8u));
+    }
+};
+
+__device__ __forceinline__ void cp_async_wait_depth(int depth) {  // allow depth - 2 groups in flight
+    if (depth == 2) cp_async_wait<0>();
+    else if (depth == 4) cp_async_wait<2>();
+    else cp_async_wait<6>();
+}
+
+// One CTA = one layout block x blockDim.x consecutive chains; one thread = one (chain, block) unit.
 //   MODE   : see SolveMode
 //   PHILOX : in-register counter-based noise (production) vs explicit Z/E from HBM (parity)
 //   REINV  : the accepted noise increment and the accepted ll are recovered on the fly from the
 //            accepted path X (fused layout switch; no W traffic) instead of read from W
 //   FAST   : model-specific fused step (FitzHugh-Nagumo with its built-in aux law)
+// p.depth (2, 4 or 8) = tiles in flight of the table and input pipelines: 2 when the grid fills the
+// machine (latency is hidden by the other warps), deeper when a few long units run alone.
 template <class MD, bool PSI, int MODE, bool PHILOX, bool REINV, bool FAST>
 __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     constexpr int D = MD::D, M = MD::M;
     using R = Rec<D, PSI>;
-    constexpr int STAGE = CHUNK_TILES * TILE * R::SIZE;  // doubles per stage
-    __shared__ alignas(128) double stab[2][STAGE];
-    __shared__ alignas(8) uint64_t full[2];
+    constexpr int RS = R::SIZE;
+    constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
+    constexpr bool NEED_XA = !SOLVE || REINV;   // walk the accepted path
+    constexpr bool NEED_WA = SOLVE && !REINV;   // read the stored accepted noise
+    using IS = InStage<D, M, NEED_XA>;          // exactly one of the two streams is staged
+    // the proposal noise is kept exactly when it is not recovered from X later (store_w == !reinvert)
+    constexpr bool STORE_W_MODE = ((MODE == MODE_IMPUTE && !REINV) || MODE == MODE_RELAYOUT);
+    using ZT = typename std::conditional<PHILOX, float, double>::type;  // Philox normals carry float resolution
+    static_assert(!FAST || (D == 2 && M == 1), "the fused step is FitzHugh-Nagumo's");
+
+    extern __shared__ __align__(256) double dsm[];
+    __shared__ alignas(8) uint64_t full[MAX_DEPTH];
+    const int depth = p.depth, dmask = depth - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *stab = dsm;                                                            // [depth][TS][RS]
+    double *sinp = dsm + (size_t)depth * TS * RS + (size_t)warp * depth * IS::WARP;  // [depth][NPT][32][2]
 
     const int groups = (p.C + (int)blockDim.x - 1) / (int)blockDim.x;
     const int blk = (int)(blockIdx.x / groups);
@@ -207,20 +291,28 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     const bool active = in_range && !masked;
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < depth; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int j, int c0, int q) {  // thread 0: stage chunk (j, c0) of the table
-        const int nt = (p.iv_N[j] + TILE - 1) >> 3;
-        const int ntl = min(CHUNK_TILES, nt - c0);
-        const uint32_t bytes = (uint32_t)(ntl * TILE * R::SIZE * sizeof(double));
+
+    // ---- table pipeline (issue side, thread 0): TMA bulk copy of one tile's records per stage ----
+    int tj = i1, ttl = 0, tq = 0;
+    auto issue_table = [&]() {
+        if (tj > i2) return;
+        const int Nj = p.iv_N[tj];
+        const int npad = ((Nj + TILE - 1) >> 3) * TILE;  // records the table holds for this interval
+        const int nrec = min(TS, npad - ttl * TS);
+        const uint32_t bytes = (uint32_t)(nrec * RS * sizeof(double));
+        uint64_t *bar = &full[tq & dmask];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full[q & 1], bytes);
-        bulk_g2s(stab[q & 1], p.table + ((size_t)p.iv_tile_off[j] + c0) * TILE * R::SIZE, bytes, &full[q & 1]);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stab + (size_t)(tq & dmask) * TS * RS, p.table + ((size_t)p.iv_tile_off[tj] * TILE + (size_t)ttl * TS) * RS, bytes, bar);
+        ++tq;
+        if (++ttl * TS >= Nj) { ttl = 0; ++tj; }
     };
-    if (threadIdx.x == 0) issue(i1, 0, 0);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < depth - 1; ++i) issue_table();
 
     const bool pinned = PSI && p.blk_pinned[blk];
     double x[D], xb[D], xa[D];  // proposal state, pinned end point, accepted state (REINV / RELAYOUT)
@@ -233,74 +325,102 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     if constexpr (FAST) fk.set_law(p.th);
 
     double llp = 0.0, lla = 0.0;  // proposal ll, accepted-path ll (recomputed when REINV)
+    double lsum = 0.0, lsum_a = 0.0;
     bool ok = true;
     const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
-    int q = 0;
 
-    constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
-    constexpr bool NEED_XA = !SOLVE || REINV;   // walk the accepted path
-    constexpr bool NEED_WA = SOLVE && !REINV;   // read the stored accepted noise
+    // ---- input pipeline (issue side): LDGSTS, runs depth-1 tiles ahead of the solve, across intervals ----
+    const double *src[IS::NPT];  // per piece: its chain's accepted record of the interval, this lane's 16 bytes
+    int ij = i1, itl = 0, int_ = 0, ilim = 0, iq = 0;
+    size_t iadv = 0;
+    const int chain0 = chain_raw - lane;  // first chain of this warp
+    auto setup_issue = [&](int j) {
+        const int Nj = p.iv_N[j];
+        int_ = (Nj + TS - 1) / TS;
+        const uint8_t *selp = NEED_XA ? p.selX_in : p.selW_in;
+        const unsigned selmask = __ballot_sync(0xffffffffu, selp[(size_t)j * p.C + chain]);
+        if constexpr (NEED_XA) {
+            const size_t xo = (size_t)p.iv_xoff[j];
+            const int xs = p.iv_xs[j];
+            ilim = Nj * D;  // live doubles of the chain's stream in this interval
+            iadv = (size_t)TS * D;
+#pragma unroll
+            for (int q = 0; q < IS::NPT; ++q) {
+                const int g = q * 32 + lane, r = g / IS::NPT, pc = g % IS::NPT;
+                const int cr = min(chain0 + r, p.C - 1);
+                src[q] = p.X[(selmask >> r) & 1] + xo + (size_t)cr * xs + pc * 2;
+            }
+        } else {
+            const size_t t0 = (size_t)p.iv_tile_off[j];
+            ilim = (Nj + TILE - 1) >> 3;  // W tiles of this interval
+            iadv = (size_t)(TS / TILE) * p.C * M * TILE;
+#pragma unroll
+            for (int q = 0; q < IS::NPT; ++q) {
+                const int g = q * 32 + lane, r = g / IS::NPT, pc = g % IS::NPT;
+                const int cr = min(chain0 + r, p.C - 1);
+                const int t8 = pc / (4 * M), rem = pc % (4 * M);
+                src[q] = p.W[(selmask >> r) & 1] + ((t0 + t8) * p.C + cr) * (size_t)(M * TILE) + rem * 2;
+            }
+        }
+    };
+    auto issue_in = [&]() {  // copy tile (ij, itl) into its stage, advance; always commits a group
+        if (ij <= i2) {
+            const uint32_t sbase = smem_u32(sinp + (size_t)(iq & dmask) * IS::WARP);
+            const size_t toff = (size_t)itl * iadv;
+#pragma unroll
+            for (int q = 0; q < IS::NPT; ++q) {
+                const int g = q * 32 + lane, r = g / IS::NPT, pc = g % IS::NPT;
+                bool lv;
+                if constexpr (NEED_XA) lv = itl * TS * D + pc * 2 < ilim;
+                else lv = itl * (TS / TILE) + pc / (4 * M) < ilim;
+                if (lv) cp_async16(sbase + (uint32_t)IS::piece(r, pc) * 8u, src[q] + toff);
+            }
+            if (++itl == int_) {
+                itl = 0;
+                if (++ij <= i2) setup_issue(ij);
+            }
+        }
+        ++iq;
+        cp_async_commit();
+    };
+    setup_issue(i1);
+    for (int i = 0; i < depth - 1; ++i) issue_in();
 
+    int q = 0;  // tiles consumed so far
     for (int j = i1; j <= i2; ++j) {
         const int N = p.iv_N[j];
-        const size_t toff = (size_t)p.iv_tile_off[j];
-        const int nt = (N + TILE - 1) >> 3;
+        const int nt = (N + TS - 1) / TS;
         const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
-        double aB[D * D], abeta[D], aatil[MD::CONST_SIGMA ? 1 : D * D];
+        double aB[FAST ? 1 : D * D], abeta[FAST ? 1 : D], aatil[MD::CONST_SIGMA ? 1 : D * D];
+        if constexpr (FAST) {
+            fk.set_interval(p.auxB + (size_t)j * D * D, p.auxbeta + (size_t)j * D);
+        } else {
 #pragma unroll
-        for (int i = 0; i < D * D; ++i) aB[i] = p.auxB[(size_t)j * D * D + i];
+            for (int i = 0; i < D * D; ++i) aB[i] = p.auxB[(size_t)j * D * D + i];
 #pragma unroll
-        for (int i = 0; i < D; ++i) abeta[i] = p.auxbeta[(size_t)j * D + i];
+            for (int i = 0; i < D; ++i) abeta[i] = p.auxbeta[(size_t)j * D + i];
+        }
         if constexpr (!MD::CONST_SIGMA) {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
         }
-        if constexpr (FAST) fk.set_interval(aB, abeta);
         const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
         const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
-        const double *Wa = p.W[sw];
-        double *Wp = p.W[1 - sw];
-        // pair-cooperative access to the X containers (see PairX): lanes 2i / 2i+1 share both chains' pointers
-        PairX<D> px;
-        {
-            const int odd = threadIdx.x & 1;
-            const int sx_o = __shfl_xor_sync(0xffffffffu, sx, 1);
-            const int chain_o = __shfl_xor_sync(0xffffffffu, chain, 1);
-            const int act_o = __shfl_xor_sync(0xffffffffu, (int)active, 1);
-            const int sA = odd ? sx_o : sx, sB = odd ? sx : sx_o;
-            px.odd = odd; px.C = p.C;
-            px.cA = odd ? chain_o : chain; px.cB = odd ? chain : chain_o;
-            px.accA = p.X[sA]; px.accB = p.X[sB];
-            px.prpA = p.X[1 - sA]; px.prpB = p.X[1 - sB];
-            px.storeA = odd ? act_o : (int)active; px.storeB = odd ? (int)active : act_o;
-        }
-        double lsum = 0.0, lsum_a = 0.0;
+        double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : p.W[1 - sw];
+        double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];  // this chain's proposal record
+        const bool store_w = active && STORE_W_MODE;
+        const size_t wtile0 = (size_t)p.iv_tile_off[j];
 
-        // software prefetch of the x-independent streams, one tile ahead
-        double dwn[NEED_WA ? M : 1][TILE];
-        double xnA[NEED_XA ? D : 1][4], xnB[NEED_XA ? D : 1][4];  // raw halves of the next accepted-X tile
-        {
-            const size_t base = (toff * p.C + chain) * TILE;
-            if constexpr (NEED_WA) {
-#pragma unroll
-                for (int w = 0; w < M; ++w) ld_tile(Wa + x_off(toff, chain, w, p.C, M), dwn[w]);
-            }
-            if constexpr (NEED_XA) px.load(toff, xnA, xnB);
-        }
-
-        for (int c0 = 0; c0 < nt; c0 += CHUNK_TILES, ++q) {
-            __syncthreads();  // every thread is done with chunk q-1: its stage may be refilled
-            if (threadIdx.x == 0) {
-                if (c0 + CHUNK_TILES < nt) issue(j, c0 + CHUNK_TILES, q + 1);
-                else if (j + 1 <= i2) issue(j + 1, 0, q + 1);
-            }
-            mbar_wait(&full[q & 1], (uint32_t)((q >> 1) & 1));
-            const double *srec = stab[q & 1];
-
+        for (int tl = 0; tl < nt; ++tl, ++q) {
+            // ---- table records of this tile: wait, refill the stage freed by the previous tile, derive (FAST) ----
+            __syncthreads();  // every thread is done with tile q-1
+            if (threadIdx.x == 0) issue_table();
+            mbar_wait(&full[q & dmask], (uint32_t)((q / depth) & 1));
+            double *srec = stab + (size_t)(q & dmask) * TS * RS;
             if (q == 0) {
                 // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
-                double rec[R::SIZE], F[D];
-                load_rec_smem<R::SIZE>(srec, rec);
+                double rec[RS], F[D];
+                load_rec_smem<RS>(srec, rec);
                 guiding_F<D, PSI>(rec, xb, F);
                 double c = p.blk_c0[blk];
                 if (pinned) {
@@ -326,96 +446,102 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                 }
                 llp = -c - 0.5 * xHx + Fx;
                 lla = llp;
+                if constexpr (FAST) __syncthreads();  // everyone has read the raw first record
             }
+            if constexpr (FAST) {
+                if (threadIdx.x < TS) fhn_derive<PSI>(srec + threadIdx.x * RS, fk, lam);
+                __syncthreads();
+            }
+            // ---- this tile's input has landed; refill the stage freed by the previous tile ----
+            cp_async_wait_depth(depth);
+            __syncwarp();  // all lanes' pieces are visible, and all lanes are done with tile q-1's stage
+            issue_in();
+            const double *sst = sinp + (size_t)(q & dmask) * IS::WARP;
 
-            const int tl_end = min(nt, c0 + CHUNK_TILES);
-            for (int tl = c0; tl < tl_end; ++tl) {
-                const size_t tile = toff + tl;
-                const size_t base = (tile * p.C + chain) * TILE;
-                double dwa[NEED_WA ? M : 1][TILE], xat[NEED_XA ? D : 1][TILE];
-                if constexpr (NEED_WA) {
-#pragma unroll
-                    for (int w = 0; w < M; ++w)
-#pragma unroll
-                        for (int s = 0; s < TILE; ++s) dwa[w][s] = dwn[w][s];
-                    if (tl + 1 < nt) {
-#pragma unroll
-                        for (int w = 0; w < M; ++w)
-                            ld_tile(Wa + x_off(tile + 1, chain, w, p.C, M), dwn[w]);
-                    }
-                }
-                if constexpr (NEED_XA) {
-                    px.unpack(xnA, xnB, xat);
-                    if (tl + 1 < nt) px.load(tile + 1, xnA, xnB);
-                }
-                double z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
+            // eight Euler steps; CHECK = the half-tile may run past the interval's last step
+            auto eight = [&](auto check_tag, int half) {
+                constexpr bool CHECK = decltype(check_tag)::value;
+                const int kh = tl * TS + half * TILE;
+                const size_t wtile = wtile0 + (size_t)(kh >> 3);
+                const double *hrec = srec + (size_t)half * TILE * RS;
+                const uint32_t hst = IS::cursor(sst, lane);
+                double *xph = Xp + (size_t)kh * D;
+                double dwo[STORE_W_MODE ? M : 1][TILE];
+                ZT z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
                 if constexpr (MODE == MODE_IMPUTE) {
                     if constexpr (PHILOX) {
 #pragma unroll
                         for (int w = 0; w < M; ++w)
 #pragma unroll
                             for (int h = 0; h < TILE / 4; ++h)
-                                philox_normal4(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w,
-                                               (uint32_t)(tl * (TILE / 4) + h), &z[w][4 * h]);
+                                philox_normal4f(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w,
+                                                (uint32_t)((kh >> 2) + h), (float *)&z[w][4 * h]);
                     } else {
 #pragma unroll
-                        for (int w = 0; w < M; ++w) ld_tile_stream(p.Z + x_off(tile, chain, w, p.C, M), z[w]);
+                        for (int w = 0; w < M; ++w) ld_tile_stream(p.Z + w_off(wtile, chain, w, p.C, M), (double *)z[w]);
                     }
                 }
-                double xo[SOLVE ? D : 1][TILE], dwo[M][TILE];
-                const double *trec = srec + (size_t)(tl - c0) * TILE * R::SIZE;
+                double xprev[D];  // proposal state after the previous (even) step: stored together with the odd one
+#pragma unroll
+                for (int c = 0; c < D; ++c) xprev[c] = 0.0;
 #pragma unroll
                 for (int s = 0; s < TILE; ++s) {
-                    double rec[R::SIZE], F[D];
-                    load_rec_smem<R::SIZE>(trec + s * R::SIZE, rec);
-                    guiding_F<D, PSI>(rec, xb, F);
-                    const double dt = rec[0];
-                    const bool live = tl * TILE + s < N;
+                    const int ks = half * TILE + s;  // step within the tile
+                    const bool live = !CHECK || (kh + s < N);  // CTA-uniform
+                    const double *rp = hrec + s * RS;
                     double dw[M];
 #pragma unroll
                     for (int w = 0; w < M; ++w) dw[w] = 0.0;
-                    if constexpr (NEED_XA) {  // recover the accepted noise increment from the accepted path
-                        if (live) {
-                            if constexpr (FAST) {
-                                double dll, r2;
-                                fk.terms<PSI>(rec, F, xa[0], xa[1], dt, dll, r2);
-                                lsum_a += dll;
-                                const double u = fma(fk.sig2, r2, fma(fk.gam, xa[0], fk.bet - xa[1]));
-                                dw[0] = fma(-u, dt, xat[1][s] - xa[1]) * fk.isig;
-                            } else {
-                                double dr[D], res[D], dll;
+                    if (live) {
+                        if constexpr (FAST) {
+                            double rec[RS];
+                            load_rec_smem<RS>(rp, rec);
+                            double Cf = rec[FD_C1], R0c = rec[FD_R0];
+                            if constexpr (PSI) {
+                                Cf = fma(rec[FD_Q10], xb[0], fma(rec[FD_Q11], xb[1], Cf));
+                                R0c = fma(rec[FD_T00], xb[0], fma(rec[FD_T01], xb[1], R0c));
+                            }
+                            if constexpr (NEED_XA) {  // recover the accepted noise increment from the accepted path
+                                double xn[2], g;
+                                IS::state(hst, ks, xn);
+                                fhn_dll(fk, rec, R0c, xa[0], xa[1], g, lsum_a);
+                                const double pred = fma(rec[FD_A1], xa[1], fma(rec[FD_B1], xa[0], Cf));
+                                dw[0] = (xn[1] - pred) * fk.isig;
+                                xa[0] = xn[0]; xa[1] = xn[1];
+                            } else if constexpr (NEED_WA) {
+                                IS::noise(hst, ks, dw);
+                            }
+                            if constexpr (MODE == MODE_IMPUTE) dw[0] = fma(rec[FD_LSQ], (double)z[0][s], rho * dw[0]);  // pCN
+                            if constexpr (SOLVE) {
+                                double g;
+                                fhn_dll(fk, rec, R0c, x[0], x[1], g, lsum);
+                                const double ynew = fma(rec[FD_KIE], g + (fk.s - x[1]), x[0]);
+                                x[1] = fma(rec[FD_A1], x[1], fma(rec[FD_B1], x[0], fma(fk.sig, dw[0], Cf)));
+                                x[0] = ynew;
+                            }
+                        } else {
+                            double rec[RS], F[D];
+                            load_rec_smem<RS>(rp, rec);
+                            guiding_F<D, PSI>(rec, xb, F);
+                            const double dt = rec[0];
+                            if constexpr (NEED_XA) {
+                                double xn[D], dr[D], res[D], dll;
+                                IS::state(hst, ks, xn);
                                 guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, xa, dt, dr, dll);
                                 lsum_a += dll;
 #pragma unroll
-                                for (int c = 0; c < D; ++c) res[c] = xat[c][s] - xa[c] - dr[c];
+                                for (int c = 0; c < D; ++c) res[c] = xn[c] - xa[c] - dr[c];
                                 MD::sigma_solve(p.th, xa, res, dw);
+#pragma unroll
+                                for (int c = 0; c < D; ++c) xa[c] = xn[c];
+                            } else if constexpr (NEED_WA) {
+                                IS::noise(hst, ks, dw);
                             }
+                            if constexpr (MODE == MODE_IMPUTE) {  // pCN: W deg = sqrt(1-rho^2) W_fresh + rho W
 #pragma unroll
-                            for (int c = 0; c < D; ++c) xa[c] = xat[c][s];
-                        }
-                    } else if constexpr (NEED_WA) {
-#pragma unroll
-                        for (int w = 0; w < M; ++w) dw[w] = dwa[w][s];
-                    }
-                    if constexpr (MODE == MODE_IMPUTE) {  // pCN: W deg = sqrt(1-rho^2) W_fresh + rho W
-#pragma unroll
-                        for (int w = 0; w < M; ++w) dw[w] = lam * (rec[1] * z[w][s]) + rho * dw[w];
-                    }
-#pragma unroll
-                    for (int w = 0; w < M; ++w) dwo[w][s] = dw[w];
-                    if constexpr (SOLVE) {
-                        if (live) {
-                            if constexpr (FAST) {
-                                double dll, r2;
-                                fk.terms<PSI>(rec, F, x[0], x[1], dt, dll, r2);
-                                lsum += dll;
-                                const double y3 = (x[0] * x[0]) * x[0];
-                                const double wy = (x[0] - y3) + (fk.s - x[1]);
-                                const double u = fma(fk.sig2, r2, fma(fk.gam, x[0], fk.bet - x[1]));
-                                const double ynew = fma(wy, dt * fk.ie, x[0]);
-                                x[1] = fma(u, dt, fma(fk.sig, dw[0], x[1]));
-                                x[0] = ynew;
-                            } else {
+                                for (int w = 0; w < M; ++w) dw[w] = lam * (rec[1] * (double)z[w][s]) + rho * dw[w];
+                            }
+                            if constexpr (SOLVE) {
                                 double dr[D], sdw[D], dll;
                                 guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, dt, dr, dll);
                                 lsum += dll;
@@ -425,97 +551,153 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                                 ok = ok && MD::bound_ok(x);
                             }
                         }
+                    }
+                    if constexpr (STORE_W_MODE) {
 #pragma unroll
-                        for (int c = 0; c < D; ++c) xo[c][s] = x[c];
+                        for (int w = 0; w < M; ++w) dwo[w][s] = dw[w];
+                    }
+                    if constexpr (SOLVE) {
+                        if (s & 1) {  // two steps per store: 16-byte aligned (32 for d = 2)
+                            if (live && active) {
+                                double *dst = xph + (s - 1) * D;
+                                if constexpr (D == 2) {
+                                    st_v4(dst, xprev[0], xprev[1], x[0], x[1]);
+                                } else {
+                                    double pr[2 * D];
+#pragma unroll
+                                    for (int c = 0; c < D; ++c) { pr[c] = xprev[c]; pr[D + c] = x[c]; }
+#pragma unroll
+                                    for (int c = 0; c < D; ++c) st_v2(dst + 2 * c, pr[2 * c], pr[2 * c + 1]);
+                                }
+                            }
+                        } else {
+                            if (CHECK && live && kh + s == N - 1 && active) {  // odd N: the last state goes out alone
+#pragma unroll
+                                for (int c = 0; c < D; ++c) xph[s * D + c] = x[c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < D; ++c) xprev[c] = x[c];
+                        }
                     }
                 }
-                if constexpr (SOLVE) {
-                    if (pinned && j == i2 && tl == nt - 1) {  // pin the block's right end to x_b
-                        const int last = (N - 1) & 7;
+                if constexpr (STORE_W_MODE) {
+                    if (store_w) {
 #pragma unroll
-                        for (int s = 0; s < TILE; ++s)
-#pragma unroll
-                            for (int c = 0; c < D; ++c) xo[c][s] = (s == last) ? xb[c] : xo[c][s];
-                    }
-                    px.store(tile, xo);  // every lane takes part (shuffles); stores are predicated per chain
-                }
-                if (active) {
-                    if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
-                        double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
-#pragma unroll
-                        for (int w = 0; w < M; ++w) st_tile(Wdst + x_off(tile, chain, w, p.C, M), dwo[w]);
+                        for (int w = 0; w < M; ++w) st_tile(Wdst + w_off(wtile, chain, w, p.C, M), dwo[w]);
                     }
                 }
+            };
+#pragma unroll 1
+            for (int half = 0; half < TS / TILE; ++half) {
+                const int kh = tl * TS + half * TILE;
+                if (kh + TILE <= N) eight(std::false_type{}, half);
+                else if (kh < N) eight(std::true_type{}, half);
             }
         }
-        llp += lsum;
-        lla += lsum_a;
     }
+    llp += lsum;
+    lla += lsum_a;
     if (!ok) llp = -INFINITY;
+    cp_async_wait<0>();  // nothing of ours may still be in flight when the CTA retires
+    if constexpr (SOLVE) {
+        if (pinned && active) {  // pin the proposal's last point to x_b (glued paths stay continuous)
+            const int sx2 = p.selX_in[(size_t)i2 * p.C + chain];
+            double *xe = p.X[1 - sx2] + p.iv_xoff[i2] + (size_t)chain * p.iv_xs[i2] + (size_t)(p.iv_N[i2] - 1) * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) xe[c] = xb[c];
+        }
+    }
 
     if constexpr (MODE == MODE_IMPUTE) {
-        if (!in_range) return;
-        if (masked) {
-            for (int j = i1; j <= i2; ++j) {
-                const size_t o = (size_t)j * p.C + chain;
-                p.selX_out[o] = p.selX_in[o];
-                p.selW_out[o] = p.selW_in[o];
-            }
-            if (p.blk_active && !p.blk_active[blk]) {  // block owned by a neighbouring shard
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = nan;
-                if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = nan;
-                if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = 0;
-            }
-            return;
-        }
         double llcur = REINV ? lla : p.ll[uo];
         const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain) : p.E[uo];
         // accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!)
-        const bool acc = p.force_accept ? ok : (e > -(llp - llcur));
-        for (int j = i1; j <= i2; ++j) {  // swap_paths!: flip the accepted-container selectors
-            const size_t o = (size_t)j * p.C + chain;
-            p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
-            p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && p.store_w);
+        const bool acc = active && (p.force_accept ? ok : (e > -(llp - llcur)));
+        if (in_range) {
+            for (int j = i1; j <= i2; ++j) {  // swap_paths!: flip the accepted-container selectors
+                const size_t o = (size_t)j * p.C + chain;
+                p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
+                p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && STORE_W_MODE);
+            }
         }
-        if (acc) {
-            llcur = llp;
-            if (p.acc_count) atomicAdd(p.acc_count + blk, 1ULL);
+        // acceptance counters of the block: one atomic per warp
+        const unsigned accm = __ballot_sync(0xffffffffu, acc), actm = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) {
+            if (p.acc_count && accm) atomicAdd(p.acc_count + blk, (unsigned long long)__popc(accm));
+            if (p.prop_count && actm) atomicAdd(p.prop_count + blk, (unsigned long long)__popc(actm));
         }
-        p.ll[uo] = llcur;
-        if (p.prop_count && chain == 0) atomicAdd(p.prop_count + blk, (unsigned long long)p.C);
-        if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = llp;
-        if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = llcur;
-        if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = (uint8_t)acc;
+        if (active) {
+            if (acc) llcur = llp;
+            p.ll[uo] = llcur;
+            if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = llp;
+            if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = llcur;
+            if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = (uint8_t)acc;
+        } else if (in_range && p.blk_active && !p.blk_active[blk]) {  // block owned by a neighbouring shard
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = nan;
+            if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = nan;
+            if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = 0;
+        }
     } else if constexpr (MODE == MODE_PARAM) {
-        if (!in_range) return;
-        if (p.out_llprop) p.out_llprop[uo] = llp;
-        if (p.out_acc) p.out_acc[uo] = (uint8_t)ok;
+        if (in_range) {
+            if (p.out_llprop) p.out_llprop[uo] = llp;
+            if (p.out_acc) p.out_acc[uo] = (uint8_t)ok;
+        }
     } else {
         if (in_range) p.ll[uo] = lla;
     }
 }
 
 // ---- launch dispatch ---------------------------------------------------------------------------
+template <class MD, bool PSI, int MODE, bool PHILOX, bool REINV, bool FAST>
+static cudaError_t launch_one(const SolveParams &p0, int threads, cudaStream_t s) {
+    constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
+    constexpr bool NEED_XA = !SOLVE || REINV;
+    using IS = InStage<MD::D, MD::M, NEED_XA>;
+    SolveParams p = p0;
+    // few long units (e.g. one block per chain): one warp per CTA so that more SMs take part
+    const long long units = (long long)p.C * p.nblk;
+    if (units < 148LL * 64 * 2) threads = 32;
+    const unsigned groups = (unsigned)((p.C + threads - 1) / threads);
+    const unsigned grid = groups * (unsigned)p.nblk;
+    auto smem_for = [&](int depth) {
+        return sizeof(double) * (size_t)depth * ((size_t)TS * Rec<MD::D, PSI>::SIZE + (size_t)(threads / 32) * IS::WARP);
+    };
+    // pipeline depth: 2 when the grid fills the machine; deeper when few CTAs run alone per SM
+    const int cta_per_sm = (int)std::min<long long>(6, (grid + 147) / 148);
+    int depth = 2;
+    if (cta_per_sm <= 4)
+        for (int d = MAX_DEPTH; d > 2; d >>= 1)
+            if ((smem_for(d) + 1024) * cta_per_sm <= 200 * 1024) { depth = d; break; }
+    p.depth = depth;
+    auto kern = solve_kernel<MD, PSI, MODE, PHILOX, REINV, FAST>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, threads, smem_for(depth), s>>>(p);
+    return cudaGetLastError();
+}
+
 template <class MD, bool PSI, bool FAST>
 static cudaError_t launch_model(int mode, const SolveParams &p, int threads, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
-    const unsigned groups = (unsigned)((p.C + threads - 1) / threads);
-    const unsigned grid = groups * (unsigned)p.nblk;
+    threads = ((threads + 31) / 32) * 32;
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
-#define DMCMC_LAUNCH(MODE_, PH_, RE_) solve_kernel<MD, PSI, MODE_, PH_, RE_, FAST><<<grid, threads, 0, s>>>(p)
     switch (mode) {
     case MODE_IMPUTE:
-        if (philox) { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, true, true); else DMCMC_LAUNCH(MODE_IMPUTE, true, false); }
-        else        { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, false, true); else DMCMC_LAUNCH(MODE_IMPUTE, false, false); }
-        break;
-    case MODE_PARAM: DMCMC_LAUNCH(MODE_PARAM, false, false); break;
-    case MODE_RELAYOUT: DMCMC_LAUNCH(MODE_RELAYOUT, false, false); break;
-    case MODE_LOGLIK: DMCMC_LAUNCH(MODE_LOGLIK, false, false); break;
-    default: return cudaErrorInvalidValue;
+        if (philox) return reinv ? launch_one<MD, PSI, MODE_IMPUTE, true, true, FAST>(p, threads, s)
+                                 : launch_one<MD, PSI, MODE_IMPUTE, true, false, FAST>(p, threads, s);
+        return reinv ? launch_one<MD, PSI, MODE_IMPUTE, false, true, FAST>(p, threads, s)
+                     : launch_one<MD, PSI, MODE_IMPUTE, false, false, FAST>(p, threads, s);
+    case MODE_PARAM: return launch_one<MD, PSI, MODE_PARAM, false, false, FAST>(p, threads, s);
+    case MODE_RELAYOUT: return launch_one<MD, PSI, MODE_RELAYOUT, false, false, FAST>(p, threads, s);
+    case MODE_LOGLIK: return launch_one<MD, PSI, MODE_LOGLIK, false, false, FAST>(p, threads, s);
     }
-#undef DMCMC_LAUNCH
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 template <class MD, bool FAST = false>
@@ -543,7 +725,6 @@ __global__ void gather_kernel(const GatherParams g) {
     if (u >= (long long)g.J * g.C) return;
     const int j = (int)(u / g.C), chain = (int)(u - (long long)j * g.C);
     const int N = g.iv_N[j];
-    const size_t cs = (size_t)g.TT * g.C * TILE;
     const size_t o = (size_t)j * g.C + chain;
     const int sx = g.selX[o] ^ g.which, sw = g.selW[o] ^ g.which;
     const size_t pt0 = (size_t)chain * g.P + g.iv_pt_off[j];
@@ -558,19 +739,17 @@ __global__ void gather_kernel(const GatherParams g) {
             const int jp = j - 1;
             const bool same_blk = g.which && g.iv_blk[jp] == g.iv_blk[j];
             const int sp = g.selX[(size_t)jp * g.C + chain] ^ (same_blk ? 1 : 0);
-            const int k = g.iv_N[jp] - 1;
-            const size_t tile = (size_t)g.iv_tile_off[jp] + (k >> 3);
-            v = g.X[sp][x_off(tile, chain, c, g.C, g.D) + (k & 7)];
+            v = g.X[sp][g.iv_xoff[jp] + (size_t)chain * g.iv_xs[jp] + (size_t)(g.iv_N[jp] - 1) * g.D + c];
         }
         g.outX[(pt0)*g.D + c] = v;
     }
     for (int w = 0; w < g.M; ++w) g.outW[pt0 * g.M + w] = 0.0;
+    const double *X = g.X[sx] + g.iv_xoff[j] + (size_t)chain * g.iv_xs[j];
     for (int k = 0; k < N; ++k) {
         const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
-        const size_t e = (tile * g.C + chain) * TILE + (k & 7);
-        for (int c = 0; c < g.D; ++c) g.outX[(pt0 + k + 1) * g.D + c] = g.X[sx][x_off(tile, chain, c, g.C, g.D) + (k & 7)];
+        for (int c = 0; c < g.D; ++c) g.outX[(pt0 + k + 1) * g.D + c] = X[(size_t)k * g.D + c];
         for (int w = 0; w < g.M; ++w)
-            g.outW[(pt0 + k + 1) * g.M + w] = g.outW[(pt0 + k) * g.M + w] + g.W[sw][x_off(tile, chain, w, g.C, g.M) + (k & 7)];
+            g.outW[(pt0 + k + 1) * g.M + w] = g.outW[(pt0 + k) * g.M + w] + g.W[sw][w_off(tile, chain, w, g.C, g.M) + (k & 7)];
     }
 }
 
@@ -579,28 +758,14 @@ __global__ void segment_kernel(const SegmentParams g) {
     const int nj = g.j1 - g.j0;
     if (u >= (long long)nj * g.C) return;
     const int j = g.j0 + (int)(u / g.C), chain = (int)(u % g.C);
-    const size_t cs = (size_t)g.TT * g.C * TILE;
-    double *X = g.X[g.selX[(size_t)j * g.C + chain]];
+    double *X = g.X[g.selX[(size_t)j * g.C + chain]] + g.iv_xoff[j] + (size_t)chain * g.iv_xs[j];
     const int off = g.iv_st_off[j] - g.iv_st_off[g.j0];
-    for (int k = 0; k < g.iv_N[j]; ++k) {
-        const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
-        const size_t e = (tile * g.C + chain) * TILE + (k & 7);
+    for (int k = 0; k < g.iv_N[j]; ++k)
         for (int c = 0; c < g.D; ++c) {
             double *pk = g.packed + ((size_t)chain * g.steps + off + k) * g.D + c;
-            const size_t xe = x_off(tile, chain, c, g.C, g.D) + (k & 7);
-            if (g.upload) X[xe] = *pk;
-            else *pk = X[xe];
+            if (g.upload) X[(size_t)k * g.D + c] = *pk;
+            else *pk = X[(size_t)k * g.D + c];
         }
-    }
-    if (g.upload) {  // pad slots repeat the last value (they are no-ops for the solve kernels)
-        const int N = g.iv_N[j];
-        for (int k = N; k < ((N + TILE - 1) / TILE) * TILE; ++k) {
-            const size_t tile = (size_t)g.iv_tile_off[j] + (k >> 3);
-            const size_t e = (tile * g.C + chain) * TILE + (k & 7);
-            for (int c = 0; c < g.D; ++c)
-                X[x_off(tile, chain, c, g.C, g.D) + (k & 7)] = g.packed[((size_t)chain * g.steps + off + N - 1) * g.D + c];
-        }
-    }
 }
 
 cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s) {

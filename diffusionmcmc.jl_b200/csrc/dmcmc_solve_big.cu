@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
     auto end_value = [&](int j, int c) {
         const int s = p.selX_in[(size_t)j * p.C + chain];
         const int k = p.iv_N[j] - 1;
-        return p.X[s][x_off((size_t)p.iv_tile_off[j] + (k >> 3), chain, c, p.C, D) + (k & 7)];
+        return p.X[s][p.iv_xoff[j] + (size_t)chain * p.iv_xs[j] + (size_t)k * D + c];
     };
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
         const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
         const double *Wa = p.W[sw];
         double *Wp = p.W[1 - sw];
-        const double *Xa = p.X[sx];
-        double *Xp = p.X[1 - sx];
+        // this chain's accepted / proposal record of the interval: [step][component], lanes = components
+        const double *Xa = p.X[sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];
+        double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];
         const double *aB = p.auxB + (size_t)j * D * D, *abeta = p.auxbeta + (size_t)j * D;
 
         for (int tl = 0; tl < nt; ++tl) {
@@ -147,8 +148,14 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
 #pragma unroll
             for (int s = 0; s < NS; ++s)
                 if (has[s]) {
-                    if constexpr (NEED_XA) ld_tile(Xa + x_off(tile, chain, idx[s], p.C, D), cur[s]);
-                    if constexpr (NEED_WA) ld_tile(Wa + x_off(tile, chain, idx[s], p.C, D), cur[s]);
+                    if constexpr (NEED_XA) {
+#pragma unroll
+                        for (int st = 0; st < TILE; ++st) {
+                            const int k = tl * TILE + st;
+                            cur[s][st] = (k < N) ? Xa[(size_t)k * D + idx[s]] : 0.0;
+                        }
+                    }
+                    if constexpr (NEED_WA) ld_tile(Wa + w_off(tile, chain, idx[s], p.C, D), cur[s]);
                     if constexpr (MODE == MODE_IMPUTE) {
                         if constexpr (PHILOX) {
 #pragma unroll
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
                                 philox_normal4(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain,
                                                (uint32_t)idx[s], (uint32_t)(tl * (TILE / 4) + h), &z[s][4 * h]);
                         } else {
-                            ld_tile_stream(p.Z + x_off(tile, chain, idx[s], p.C, D), z[s]);
+                            ld_tile_stream(p.Z + w_off(tile, chain, idx[s], p.C, D), z[s]);
                         }
                     }
                 }
@@ -280,11 +287,13 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolvePa
 #pragma unroll
                                 for (int st = 0; st < TILE; ++st) xo[s][st] = (st == last) ? xbs[idx[s]] : xo[s][st];
                             }
-                            st_tile(Xp + x_off(tile, chain, idx[s], p.C, D), xo[s]);
+#pragma unroll
+                            for (int st = 0; st < TILE; ++st)
+                                if (st < nlive) Xp[(size_t)(tl * TILE + st) * D + idx[s]] = xo[s][st];
                         }
                         if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
                             double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
-                            st_tile(Wdst + x_off(tile, chain, idx[s], p.C, D), dwo[s]);
+                            st_tile(Wdst + w_off(tile, chain, idx[s], p.C, D), dwo[s]);
                         }
                     }
             }
