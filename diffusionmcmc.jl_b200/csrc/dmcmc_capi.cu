@@ -43,6 +43,8 @@ struct DevBuf {
 // tables and block constants of one (law, layout) pair
 struct Tables {
     DevBuf<double> table, blk_c0, blk_g, blk_Qc;
+    DevBuf<double> ftable;   // FitzHugh-Nagumo fused step: per-step coefficients derived from `table` and theta
+    bool fvalid = false;
     DevBuf<double> ptH, ptF0, ptPsi, ptc0;  // per grid point, for download / parity
     bool valid = false;
 };
@@ -249,7 +251,7 @@ int build_aux(dmcmc_ctx *ctx, int slot) {
     if (upload(ctx, law.d_auxB, law.auxB)) return -1;
     if (upload(ctx, law.d_auxbeta, law.auxbeta)) return -1;
     if (upload(ctx, law.d_auxatil, law.auxatil)) return -1;
-    for (auto &lay : ctx->layout) lay.tab[slot].valid = false;
+    for (auto &lay : ctx->layout) lay.tab[slot].valid = lay.tab[slot].fvalid = false;
     return 0;
 }
 
@@ -294,6 +296,7 @@ int run_backward_filter(dmcmc_ctx *ctx, int slot) {
     b.blk_c0 = tb.blk_c0.p; b.blk_g = tb.blk_g.p; b.blk_Qc = tb.blk_Qc.p;
     CK(launch_backward_filter(b, ctx->stream));
     tb.valid = true;
+    tb.fvalid = false;
     return 0;
 }
 
@@ -315,7 +318,7 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     sp.iv_xoff = ctx->d_xoff.p; sp.iv_xs = ctx->d_xs.p;
     sp.rho = ctx->d_rho.p;
     sp.auxB = law.d_auxB.p; sp.auxbeta = law.d_auxbeta.p; sp.auxatil = law.d_auxatil.p;
-    sp.table = tb.table.p; sp.blk_c0 = tb.blk_c0.p; sp.blk_g = tb.blk_g.p; sp.blk_Qc = tb.blk_Qc.p;
+    sp.table = sp.table_raw = tb.table.p; sp.blk_c0 = tb.blk_c0.p; sp.blk_g = tb.blk_g.p; sp.blk_Qc = tb.blk_Qc.p;
     sp.has_psi = lay.has_psi;
     for (int b = 0; b < 2; ++b) { sp.X[b] = ctx->d_X[b].p; sp.W[b] = ctx->d_W[b].p; }
     sp.selX_in = ctx->d_selX[ctx->sel_cur].p; sp.selW_in = ctx->d_selW[ctx->sel_cur].p;
@@ -326,6 +329,16 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     sp.reinvert = 0;
     sp.store_w = 1;
     sp.fast_ok = (!law.custom_aux && ctx->fast_step) ? 1 : 0;
+    if (ctx->cfg.model == DMCMC_MODEL_FHN && sp.fast_ok) {  // fused step streams the derived coefficient table
+        if (!tb.fvalid) {
+            Theta th{};
+            for (int i = 0; i < DMCMC_MAX_THETA; ++i) th.v[i] = law.theta[i];
+            CK(tb.ftable.ensure(tb.table.n));
+            CK(launch_fhn_derive(tb.table.p, tb.ftable.p, (long long)ctx->TT * TILE, lay.has_psi, th, ctx->stream));
+            tb.fvalid = true;
+        }
+        sp.table = tb.ftable.p;
+    }
     for (int i = 0; i < DMCMC_MAX_THETA; ++i) sp.th.v[i] = law.theta[i];
     return 0;
 }
@@ -443,6 +456,7 @@ int select_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t
         upload(ctx, l.d_iv_blk, l.iv_blk))
         return -1;
     l.tab[0].valid = l.tab[1].valid = false;
+    l.tab[0].fvalid = l.tab[1].fvalid = false;
     l.has_mask = false;
     l.last_used = ++ctx->lay_clock;
     ctx->lay_cur = s;
@@ -504,11 +518,12 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     for (auto &l : ctx->layout) {
         l.d_i1.release(); l.d_i2.release(); l.d_pinned.release(); l.d_iv_blk.release(); l.d_active.release();
         for (auto &t : l.tab) {
-            t.table.release(); t.blk_c0.release(); t.blk_g.release(); t.blk_Qc.release();
+            t.table.release(); t.ftable.release(); t.blk_c0.release(); t.blk_g.release(); t.blk_Qc.release();
             t.ptH.release(); t.ptF0.release(); t.ptPsi.release(); t.ptc0.release();
         }
     }
     ctx->d_N.release(); ctx->d_tile_off.release(); ctx->d_first.release(); ctx->d_rec.release();
+    ctx->d_xoff.release(); ctx->d_xs.release();
     ctx->d_pt_off.release(); ctx->d_st_off.release(); ctx->d_t.release(); ctx->d_rho.release(); ctx->d_Hobs.release();
     ctx->d_Fobs.release(); ctx->d_cobs.release(); ctx->d_x0.release(); ctx->d_ll.release();
     ctx->d_Z.release(); ctx->d_E.release();
@@ -783,6 +798,7 @@ int dmcmc_upload_tables(dmcmc_ctx *ctx, int32_t which, const double *H, const do
     }
     CK(cudaMemcpy(tb.ptc0.p, c0, (size_t)ctx->P * sizeof(double), cudaMemcpyHostToDevice));
     tb.valid = true;
+    tb.fvalid = false;
     return 0;
 }
 
@@ -1059,6 +1075,7 @@ int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta,
         CK(cp(tp.blk_Qc, tc.blk_Qc)); CK(cp(tp.ptH, tc.ptH)); CK(cp(tp.ptF0, tc.ptF0));
         CK(cp(tp.ptPsi, tc.ptPsi)); CK(cp(tp.ptc0, tc.ptc0));
         tp.valid = true;
+        tp.fvalid = false;
     }
     // the solve needs the accepted W under the CURRENT law: recover it first when it is stale
     if (!ctx->w_valid && materialize_async(ctx)) return -1;

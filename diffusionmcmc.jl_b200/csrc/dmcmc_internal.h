@@ -31,7 +31,8 @@ struct SolveParams {
     const double *auxbeta;  // [J][D]
     const double *auxatil;  // [J][D*D]
     // tables of the law the kernel solves under
-    const double *table;    // [TT*8][REC]
+    const double *table;    // [TT*8][REC] records the kernel streams (FitzHugh-Nagumo fused step: derived coefficients)
+    const double *table_raw; // [TT*8][REC] dt, sqrt(dt), H, F0, Psi (== table unless the fused step is used)
     const double *blk_c0;   // [nblk] c0 at the block's first grid point
     const double *blk_g;    // [nblk][D]
     const double *blk_Qc;   // [nblk][D*D]
@@ -68,6 +69,7 @@ struct SolveParams {
 // launchers (dmcmc_solve.cu); return the CUDA error of the launch
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s);
 cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_big.cu
+cudaError_t launch_fhn_derive(const double *raw, double *out, long long nrec, int has_psi, const Theta &th, cudaStream_t s);
 
 // state gather for read-outs (dmcmc_solve.cu)
 struct GatherParams {

@@ -101,7 +101,7 @@ __device__ __forceinline__ void guided_terms(const Theta &th, const double *__re
 //     x' = A1 x + B1 y + Cf + sigma dW ,   A1 = 1 - dt (1 + sigma^2 H_22),  B1 = dt (gamma - sigma^2 H_12),
 //     Cf = dt (beta + sigma^2 F_2) ,       F = F0 + Psi x_b .
 // A1, B1 and the dt-scaled rows of H, F0, Psi are the same for every chain: fhn_derive rewrites
-// the staged table records once per CTA.  Same mathematics as guided_terms, ~3x fewer FP64
+// the table once per (layout, law) into p.table (fhn_derive_kernel); p.table_raw keeps H, F0, Psi.  Same mathematics as guided_terms, ~3x fewer FP64
 // instructions per chain and step; differences are rounding-level.
 struct FhnK {
     double ie, s, gam, bet, sig, sig2, isig;  // per law
@@ -116,17 +116,17 @@ struct FhnK {
     }
 };
 
-// derived record: [A1, B1, C1, dt/eps, dt H11, dt H12, dt F0_1, lam sqrt(dt) | dt s2 Psi21, dt s2 Psi22, dt Psi11, dt Psi12]
-enum { FD_A1 = 0, FD_B1, FD_C1, FD_KIE, FD_G00, FD_G01, FD_R0, FD_LSQ, FD_Q10, FD_Q11, FD_T00, FD_T01 };
+// derived record: [A1, B1, C1, dt/eps, dt H11, dt H12, dt F0_1, sqrt(dt) | dt s2 Psi21, dt s2 Psi22, dt Psi11, dt Psi12]
+enum { FD_A1 = 0, FD_B1, FD_C1, FD_KIE, FD_G00, FD_G01, FD_R0, FD_SQ, FD_Q10, FD_Q11, FD_T00, FD_T01 };
 
 template <bool PSI>
-__device__ __forceinline__ void fhn_derive(double *r, const FhnK &fk, double lam) {
+__device__ __forceinline__ void fhn_derive(const double *raw, double *r, const FhnK &fk) {
     using R = Rec<2, PSI>;
-    const double dt = r[0], sq = r[1];
-    const double H00 = r[R::OFF_H], H01 = r[R::OFF_H + 1], H11 = r[R::OFF_H + 2];
-    const double F0 = r[R::OFF_F], F1 = r[R::OFF_F + 1];
+    const double dt = raw[0], sq = raw[1];
+    const double H00 = raw[R::OFF_H], H01 = raw[R::OFF_H + 1], H11 = raw[R::OFF_H + 2];
+    const double F0 = raw[R::OFF_F], F1 = raw[R::OFF_F + 1];
     double P00 = 0.0, P01 = 0.0, P10 = 0.0, P11 = 0.0;
-    if constexpr (PSI) { P00 = r[R::OFF_PSI]; P01 = r[R::OFF_PSI + 1]; P10 = r[R::OFF_PSI + 2]; P11 = r[R::OFF_PSI + 3]; }
+    if constexpr (PSI) { P00 = raw[R::OFF_PSI]; P01 = raw[R::OFF_PSI + 1]; P10 = raw[R::OFF_PSI + 2]; P11 = raw[R::OFF_PSI + 3]; }
     const double ds2 = dt * fk.sig2;
     r[FD_A1] = fma(-ds2, H11, 1.0 - dt);
     r[FD_B1] = fma(-ds2, H01, dt * fk.gam);
@@ -135,7 +135,7 @@ __device__ __forceinline__ void fhn_derive(double *r, const FhnK &fk, double lam
     r[FD_G00] = dt * H00;
     r[FD_G01] = dt * H01;
     r[FD_R0] = dt * F0;
-    r[FD_LSQ] = lam * sq;
+    r[FD_SQ] = sq;
     if constexpr (PSI) {
         r[FD_Q10] = ds2 * P10; r[FD_Q11] = ds2 * P11;
         r[FD_T00] = dt * P00;  r[FD_T01] = dt * P01;
@@ -155,6 +155,9 @@ __device__ __forceinline__ void fhn_dll(const FhnK &fk, const double *rec, doubl
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
@@ -324,16 +327,57 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     FhnK fk;
     if constexpr (FAST) fk.set_law(p.th);
 
-    double llp = 0.0, lla = 0.0;  // proposal ll, accepted-path ll (recomputed when REINV)
+    double llp, lla;  // proposal ll, accepted-path ll (recomputed when REINV)
+    {
+        // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
+        double rec[RS], F[D];
+        const double *r0 = p.table_raw + (size_t)p.iv_tile_off[i1] * TILE * RS;
+#pragma unroll
+        for (int i = 0; i < RS; ++i) rec[i] = __ldg(r0 + i);
+        guiding_F<D, PSI>(rec, xb, F);
+        double c = p.blk_c0[blk];
+        if (pinned) {
+            double gx = 0.0, qq = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                gx += p.blk_g[(size_t)blk * D + i] * xb[i];
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += p.blk_Qc[(size_t)blk * D * D + i * D + k] * xb[k];
+                qq += xb[i] * s;
+            }
+            c += gx + 0.5 * qq;
+        }
+        double xHx = 0.0, Fx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s += rec[R::OFF_H + hidx(D, i, k)] * x[k];
+            xHx += x[i] * s;
+            Fx += F[i] * x[i];
+        }
+        llp = -c - 0.5 * xHx + Fx;
+        lla = llp;
+    }
     double lsum = 0.0, lsum_a = 0.0;
     bool ok = true;
     const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
 
     // ---- input pipeline (issue side): LDGSTS, runs depth-1 tiles ahead of the solve, across intervals ----
-    const double *src[IS::NPT];  // per piece: its chain's accepted record of the interval, this lane's 16 bytes
+    // Lane l copies piece pc of chain r = q * RPI + l / NPT in its q-th request (RPI chains per request),
+    // so the piece index, the live test and the swizzle are per-lane constants; src[q] walks the record.
+    constexpr bool PO2 = (32 % IS::NPT == 0);          // d = 2 path, m = 1, 2 noise
+    constexpr int RPI = PO2 ? 32 / IS::NPT : 1;
+    const double *src[IS::NPT];  // per request: its chain's accepted record of the interval, this lane's 16 bytes
     int ij = i1, itl = 0, int_ = 0, ilim = 0, iq = 0;
     size_t iadv = 0;
     const int chain0 = chain_raw - lane;  // first chain of this warp
+    const int pcl = lane % IS::NPT, rl = lane / IS::NPT;  // PO2: this lane's piece and first chain
+    auto piece_of = [&](int q, int &r, int &pc) {
+        if constexpr (PO2) { r = q * RPI + rl; pc = pcl; }
+        else { const int g = q * 32 + lane; r = g / IS::NPT; pc = g % IS::NPT; }
+    };
     auto setup_issue = [&](int j) {
         const int Nj = p.iv_N[j];
         int_ = (Nj + TS - 1) / TS;
@@ -346,7 +390,8 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
             iadv = (size_t)TS * D;
 #pragma unroll
             for (int q = 0; q < IS::NPT; ++q) {
-                const int g = q * 32 + lane, r = g / IS::NPT, pc = g % IS::NPT;
+                int r, pc;
+                piece_of(q, r, pc);
                 const int cr = min(chain0 + r, p.C - 1);
                 src[q] = p.X[(selmask >> r) & 1] + xo + (size_t)cr * xs + pc * 2;
             }
@@ -356,24 +401,51 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
             iadv = (size_t)(TS / TILE) * p.C * M * TILE;
 #pragma unroll
             for (int q = 0; q < IS::NPT; ++q) {
-                const int g = q * 32 + lane, r = g / IS::NPT, pc = g % IS::NPT;
+                int r, pc;
+                piece_of(q, r, pc);
                 const int cr = min(chain0 + r, p.C - 1);
                 const int t8 = pc / (4 * M), rem = pc % (4 * M);
                 src[q] = p.W[(selmask >> r) & 1] + ((t0 + t8) * p.C + cr) * (size_t)(M * TILE) + rem * 2;
             }
         }
     };
+    // per-lane destination offsets inside a stage (bytes); with the d = 2 swizzle they repeat every 4 requests
+    uint32_t dsto[IS::SWZ ? 4 : 1];
+    if constexpr (IS::SWZ) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dsto[i] = (uint32_t)IS::piece(i * RPI + rl, pcl) * 8u;
+    } else if constexpr (PO2) {
+        dsto[0] = (uint32_t)IS::piece(rl, pcl) * 8u;
+    }
     auto issue_in = [&]() {  // copy tile (ij, itl) into its stage, advance; always commits a group
         if (ij <= i2) {
             const uint32_t sbase = smem_u32(sinp + (size_t)(iq & dmask) * IS::WARP);
-            const size_t toff = (size_t)itl * iadv;
-#pragma unroll
-            for (int q = 0; q < IS::NPT; ++q) {
-                const int g = q * 32 + lane, r = g / IS::NPT, pc = g % IS::NPT;
+            if constexpr (PO2) {
                 bool lv;
-                if constexpr (NEED_XA) lv = itl * TS * D + pc * 2 < ilim;
-                else lv = itl * (TS / TILE) + pc / (4 * M) < ilim;
-                if (lv) cp_async16(sbase + (uint32_t)IS::piece(r, pc) * 8u, src[q] + toff);
+                if constexpr (NEED_XA) lv = itl * TS * D + pcl * 2 < ilim;
+                else lv = itl * (TS / TILE) + pcl / (4 * M) < ilim;
+                uint32_t db[IS::SWZ ? 4 : 1];
+#pragma unroll
+                for (int i = 0; i < (IS::SWZ ? 4 : 1); ++i) db[i] = sbase + dsto[i];
+#pragma unroll
+                for (int q = 0; q < IS::NPT; ++q) {
+                    // chain r = q * RPI + rl: record offset r * RECW * 8 bytes; the swizzle term has period 4 in q (RPI = 2)
+                    const uint32_t dst = IS::SWZ ? db[q & 3] + (uint32_t)((q & ~3) * RPI * IS::RECW * 8)
+                                                 : db[0] + (uint32_t)(q * RPI * IS::RECW * 8);
+                    if (lv) cp_async16(dst, src[q]);
+                    src[q] += iadv;
+                }
+            } else {
+                const size_t toff = (size_t)itl * iadv;
+#pragma unroll
+                for (int q = 0; q < IS::NPT; ++q) {
+                    int r, pc;
+                    piece_of(q, r, pc);
+                    bool lv;
+                    if constexpr (NEED_XA) lv = itl * TS * D + pc * 2 < ilim;
+                    else lv = itl * (TS / TILE) + pc / (4 * M) < ilim;
+                    if (lv) cp_async16(sbase + (uint32_t)IS::piece(r, pc) * 8u, src[q] + toff);
+                }
             }
             if (++itl == int_) {
                 itl = 0;
@@ -387,10 +459,22 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     for (int i = 0; i < depth - 1; ++i) issue_in();
 
     int q = 0;  // tiles consumed so far
+    uint32_t sxbits = 0, swbits = 0;  // selectors of the block's first 32 intervals (re-used by the swap below)
+    double *xp_end = nullptr;         // last point of the block in the proposal container
     for (int j = i1; j <= i2; ++j) {
         const int N = p.iv_N[j];
         const int nt = (N + TS - 1) / TS;
         const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
+        if (j - i1 < 32) { sxbits |= (uint32_t)sx << (j - i1); swbits |= (uint32_t)sw << (j - i1); }
+        if (j < i2) {
+            // the next interval's metadata is needed by the issue side one tile before this interval ends
+            // and by the solve right after it: pull the lines into L1 now, under a loaded memory system
+            // each of these dependent loads would otherwise cost microseconds at the switch
+            const int jn = j + 1;
+            prefetch_l1(p.iv_N + jn); prefetch_l1(p.iv_tile_off + jn); prefetch_l1(p.iv_xoff + jn); prefetch_l1(p.iv_xs + jn);
+            prefetch_l1(p.selX_in + (size_t)jn * p.C + chain); prefetch_l1(p.selW_in + (size_t)jn * p.C + chain);
+            prefetch_l1(p.rho + jn); prefetch_l1(p.auxB + (size_t)jn * D * D); prefetch_l1(p.auxbeta + (size_t)jn * D);
+        }
         double aB[FAST ? 1 : D * D], abeta[FAST ? 1 : D], aatil[MD::CONST_SIGMA ? 1 : D * D];
         if constexpr (FAST) {
             fk.set_interval(p.auxB + (size_t)j * D * D, p.auxbeta + (size_t)j * D);
@@ -409,49 +493,15 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
         double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : p.W[1 - sw];
         double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];  // this chain's proposal record
         const bool store_w = active && STORE_W_MODE;
+        xp_end = Xp + (size_t)(N - 1) * D;
         const size_t wtile0 = (size_t)p.iv_tile_off[j];
 
         for (int tl = 0; tl < nt; ++tl, ++q) {
-            // ---- table records of this tile: wait, refill the stage freed by the previous tile, derive (FAST) ----
-            __syncthreads();  // every thread is done with tile q-1
+            // ---- table records of this tile: wait, refill the stage freed by the previous tile ----
+            __syncthreads();  // every thread is done with tile q-1 (a full/empty mbarrier handshake was measured: no faster)
             if (threadIdx.x == 0) issue_table();
             mbar_wait(&full[q & dmask], (uint32_t)((q / depth) & 1));
-            double *srec = stab + (size_t)(q & dmask) * TS * RS;
-            if (q == 0) {
-                // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
-                double rec[RS], F[D];
-                load_rec_smem<RS>(srec, rec);
-                guiding_F<D, PSI>(rec, xb, F);
-                double c = p.blk_c0[blk];
-                if (pinned) {
-                    double gx = 0.0, qq = 0.0;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) {
-                        gx += p.blk_g[(size_t)blk * D + i] * xb[i];
-                        double s = 0.0;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) s += p.blk_Qc[(size_t)blk * D * D + i * D + k] * xb[k];
-                        qq += xb[i] * s;
-                    }
-                    c += gx + 0.5 * qq;
-                }
-                double xHx = 0.0, Fx = 0.0;
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) s += rec[R::OFF_H + hidx(D, i, k)] * x[k];
-                    xHx += x[i] * s;
-                    Fx += F[i] * x[i];
-                }
-                llp = -c - 0.5 * xHx + Fx;
-                lla = llp;
-                if constexpr (FAST) __syncthreads();  // everyone has read the raw first record
-            }
-            if constexpr (FAST) {
-                if (threadIdx.x < TS) fhn_derive<PSI>(srec + threadIdx.x * RS, fk, lam);
-                __syncthreads();
-            }
+            const double *srec = stab + (size_t)(q & dmask) * TS * RS;
             // ---- this tile's input has landed; refill the stage freed by the previous tile ----
             cp_async_wait_depth(depth);
             __syncwarp();  // all lanes' pieces are visible, and all lanes are done with tile q-1's stage
@@ -511,7 +561,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                             } else if constexpr (NEED_WA) {
                                 IS::noise(hst, ks, dw);
                             }
-                            if constexpr (MODE == MODE_IMPUTE) dw[0] = fma(rec[FD_LSQ], (double)z[0][s], rho * dw[0]);  // pCN
+                            if constexpr (MODE == MODE_IMPUTE) dw[0] = fma(lam * rec[FD_SQ], (double)z[0][s], rho * dw[0]);  // pCN
                             if constexpr (SOLVE) {
                                 double g;
                                 fhn_dll(fk, rec, R0c, x[0], x[1], g, lsum);
@@ -601,10 +651,8 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     cp_async_wait<0>();  // nothing of ours may still be in flight when the CTA retires
     if constexpr (SOLVE) {
         if (pinned && active) {  // pin the proposal's last point to x_b (glued paths stay continuous)
-            const int sx2 = p.selX_in[(size_t)i2 * p.C + chain];
-            double *xe = p.X[1 - sx2] + p.iv_xoff[i2] + (size_t)chain * p.iv_xs[i2] + (size_t)(p.iv_N[i2] - 1) * D;
 #pragma unroll
-            for (int c = 0; c < D; ++c) xe[c] = xb[c];
+            for (int c = 0; c < D; ++c) xp_end[c] = xb[c];
         }
     }
 
@@ -616,8 +664,11 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
         if (in_range) {
             for (int j = i1; j <= i2; ++j) {  // swap_paths!: flip the accepted-container selectors
                 const size_t o = (size_t)j * p.C + chain;
-                p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
-                p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && STORE_W_MODE);
+                const int b = j - i1;
+                const uint8_t sxj = b < 32 ? (uint8_t)((sxbits >> b) & 1u) : p.selX_in[o];
+                const uint8_t swj = b < 32 ? (uint8_t)((swbits >> b) & 1u) : p.selW_in[o];
+                p.selX_out[o] = sxj ^ (uint8_t)acc;
+                p.selW_out[o] = swj ^ (uint8_t)(acc && STORE_W_MODE);
             }
         }
         // acceptance counters of the block: one atomic per warp
@@ -646,6 +697,30 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     } else {
         if (in_range) p.ll[uo] = lla;
     }
+}
+
+// ---- FitzHugh-Nagumo: rewrite a (layout, law) table into the fused step's coefficients -----------
+template <bool PSI>
+__global__ void fhn_derive_kernel(const double *__restrict__ raw, double *__restrict__ out, long long nrec, Theta th) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrec) return;
+    constexpr int RS = Rec<2, PSI>::SIZE;
+    FhnK fk;
+    fk.set_law(th);
+    double r[RS], o[RS];
+#pragma unroll
+    for (int k = 0; k < RS; ++k) { r[k] = raw[i * RS + k]; o[k] = 0.0; }
+    fhn_derive<PSI>(r, o, fk);
+#pragma unroll
+    for (int k = 0; k < RS; ++k) out[i * RS + k] = o[k];
+}
+
+cudaError_t launch_fhn_derive(const double *raw, double *out, long long nrec, int has_psi, const Theta &th, cudaStream_t s) {
+    if (nrec <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((nrec + 127) / 128);
+    if (has_psi) fhn_derive_kernel<true><<<grid, 128, 0, s>>>(raw, out, nrec, th);
+    else fhn_derive_kernel<false><<<grid, 128, 0, s>>>(raw, out, nrec, th);
+    return cudaGetLastError();
 }
 
 // ---- launch dispatch ---------------------------------------------------------------------------
