@@ -231,9 +231,10 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
         k_adapt = min([u.adpt.v[0].adapt_every_k_steps for u in updates
                        if isinstance(u.adpt, AdaptationMultiPathImputation)] or [save_every])
         max_sw = max(1, min(k_adapt, save_every, num_mcmc_steps)) * nu
-        rho_buf = eng.pinned((max_sw, J), np.float64)
-        hist_buf = (eng.pinned((max_sw, C, stride), np.float64), eng.pinned((max_sw, C, stride), np.float64),
-                    eng.pinned((max_sw, C, stride), np.uint8))
+        # ordinary host arrays: the library stages through its own pinned rings (dmcmc_run_sweeps)
+        rho_buf = np.empty((max_sw, J), np.float64)
+        hist_buf = (np.empty((max_sw, C, stride), np.float64), np.empty((max_sw, C, stride), np.float64),
+                    np.empty((max_sw, C, stride), np.uint8))
         it = 0
         while it < num_mcmc_steps:
             chunk = min(num_mcmc_steps - it, max(1, min(k_adapt, save_every - (it % save_every))))
@@ -317,12 +318,13 @@ class ImputationRunner:
         self.sweeps += n
 
     def reserve_host(self, n):
-        """Pinned host buffers for n sweeps of rho schedule and history rows (allocated once)."""
+        """Host buffers (ordinary NumPy arrays, as a Julia caller would pass) for n sweeps of rho
+        schedule and history rows, allocated and touched once."""
         e = self.e
         if self._host is None or self._host[0].shape[0] < n:
-            self._host = (e.pinned((n, e.J), np.float64), e.pinned((n, e.C, self.stride), np.float64),
-                          e.pinned((n, e.C, self.stride), np.float64),
-                          e.pinned((n, e.C, self.stride), np.uint8))
+            self._host = (np.empty((n, e.J), np.float64), np.empty((n, e.C, self.stride), np.float64),
+                          np.empty((n, e.C, self.stride), np.float64),
+                          np.empty((n, e.C, self.stride), np.uint8))
             for a in self._host:
                 a[...] = 0  # touch the pages
 

@@ -1,10 +1,12 @@
 // dmcmc_capi.cu -- the C ABI of include/dmcmc.h: context, problem upload, launches, read-outs.
 // Host-side logic only; the arithmetic of the hot path is in dmcmc_solve.cu / dmcmc_bf.cu.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -68,6 +70,18 @@ struct Law {
 };
 }  // namespace
 
+// staging rings and streams of dmcmc_run_sweeps (allocated on first use, kept for the context's lifetime)
+struct SweepIO {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t kernel_done[8] = {}, rho_ready[8] = {}, copied[8] = {};
+    DevBuf<uint8_t> d_hist;   // [R][ll deg row | ll row | accepted row]
+    DevBuf<double> d_rho;     // [R][J]
+    uint8_t *h_hist = nullptr;  // pinned mirror of d_hist
+    size_t h_hist_bytes = 0;
+    double *h_rho = nullptr;    // pinned [R][J]
+    size_t h_rho_n = 0;
+};
+
 struct dmcmc_ctx {
     dmcmc_config cfg{};
     int d = 0, m = 0, nth = 0, C = 0, R = 0, J = 0, p = 0;
@@ -102,6 +116,7 @@ struct dmcmc_ctx {
     bool w_valid = false;  // stored accepted W is consistent with the accepted X under the current law/layout
     int threads = 64;
     bool fast_step = true;  // allow model-specific fused steps (dmcmc_set_option)
+    SweepIO io;
 };
 
 namespace {
@@ -512,6 +527,17 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
+    {
+        SweepIO &io = ctx->io;
+        if (io.s_in) {
+            cudaStreamSynchronize(io.s_in); cudaStreamSynchronize(io.s_out);
+            for (int i = 0; i < 8; ++i) { cudaEventDestroy(io.kernel_done[i]); cudaEventDestroy(io.rho_ready[i]); cudaEventDestroy(io.copied[i]); }
+            cudaStreamDestroy(io.s_in); cudaStreamDestroy(io.s_out);
+        }
+        io.d_hist.release(); io.d_rho.release();
+        if (io.h_hist) cudaFreeHost(io.h_hist);
+        if (io.h_rho) cudaFreeHost(io.h_rho);
+    }
     auto rel_law = [](Law &l) { l.d_auxB.release(); l.d_auxbeta.release(); l.d_auxatil.release(); };
     rel_law(ctx->law[0]);
     rel_law(ctx->law[1]);
@@ -945,6 +971,13 @@ static int relayout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const
     return materialize_async(ctx);
 }
 
+// Host side of the sweep loop.  The caller's buffers are ordinary host memory (Julia arrays); the
+// library stages through its own small pinned rings, which stay hot in the IOMMU/TLB (DMA into a
+// fresh multi-hundred-MB pinned history buffer was measured 3-6x slower than into a re-used ring):
+//   copy-in stream : rho row of sweep k   host ring -> device ring          (waits for kernel k-R)
+//   compute stream : kernel k                                               (waits for rho k, and for D2H k-R)
+//   copy-out stream: history rows of k    device ring -> pinned host ring   (waits for kernel k)
+//   drainer thread : pinned host ring -> caller's arrays, then frees the ring slot
 int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
                      int32_t first_pattern, const double *rho_sched, int32_t nblk_stride,
                      double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted) {
@@ -966,65 +999,119 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
     }
     const int nbmax = std::max(nb[0], nb[1]);
     REQUIRE(!want_hist || nblk_stride >= nbmax, "dmcmc_run_sweeps: nblk_stride smaller than the number of blocks");
-    const size_t row = (size_t)ctx->C * (want_hist ? nblk_stride : nbmax);
-    // device-side history ring: D2H of sweep k overlaps the kernels of sweeps k+1..
-    const int ring = 4;
-    DevBuf<double> h_llp, h_ll;
-    DevBuf<uint8_t> h_acc;
-    cudaStream_t cs = nullptr;
-    std::vector<cudaEvent_t> done(ring, nullptr), freed(ring, nullptr);
+    const size_t row = (size_t)ctx->C * (want_hist ? nblk_stride : nbmax);  // units per history row
+    const int R = 8;                                                        // ring slots
+    const size_t slot_bytes = 2 * row * sizeof(double) + ((row + 15) & ~(size_t)15);  // [ll deg | ll | accepted], 16-byte aligned
+    const size_t J = (size_t)ctx->J;
+    SweepIO &io = ctx->io;
     if (want_hist) {
-        CK(h_llp.ensure(row * ring));
-        CK(h_ll.ensure(row * ring));
-        CK(h_acc.ensure(row * ring));
-        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        for (int i = 0; i < ring; ++i) {
-            CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+        CK(io.d_hist.ensure(slot_bytes * R));
+        if (io.h_hist_bytes < slot_bytes * R) {
+            if (io.h_hist) cudaFreeHost(io.h_hist);
+            io.h_hist = nullptr; io.h_hist_bytes = 0;
+            CK(cudaHostAlloc((void **)&io.h_hist, slot_bytes * R, cudaHostAllocDefault));
+            io.h_hist_bytes = slot_bytes * R;
         }
     }
-    for (int it = 0; it < n_sweeps; ++it) {
-        const int pat = (first_pattern + it) & 1;
-        if (rho_sched) {  // this sweep's pCN memory, host -> device on the compute stream
-            CK(cudaMemcpyAsync(ctx->d_rho.p, rho_sched + (size_t)it * ctx->J, ctx->J * sizeof(double),
-                               cudaMemcpyHostToDevice, ctx->stream));
-        }
-        if (half_len > 0 && switch_layout_async(ctx, nb[pat], li1[pat].data(), li2[pat].data(), lpin[pat].data()))
-            return -1;
-        SolveParams sp;
-        if (fill_params(ctx, sp, ctx->law_cur)) return -1;
-        const int slot = it % ring;
-        if (want_hist && it >= ring) CK(cudaStreamWaitEvent(ctx->stream, freed[slot], 0));
-        sp.iter = iter0 + (uint32_t)it;
-        sp.reinvert = !ctx->w_valid;  // fused layout switch: noise and ll recovered from the accepted X
-        sp.store_w = ctx->w_valid;
-        sp.out_stride = want_hist ? nblk_stride : sp.nblk;
-        sp.acc_count = ctx->d_counts.p;
-        sp.prop_count = ctx->d_counts.p + ctx->J;
-        sp.out_llprop = hist_ll_prop ? h_llp.p + row * slot : nullptr;
-        sp.out_ll = hist_ll ? h_ll.p + row * slot : nullptr;
-        sp.out_acc = hist_accepted ? h_acc.p + row * slot : nullptr;
-        if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
-        ctx->sel_cur ^= 1;
-        if (want_hist) {
-            CK(cudaEventRecord(done[slot], ctx->stream));
-            CK(cudaStreamWaitEvent(cs, done[slot], 0));
-            // the kernel wrote rows with the host's stride, so each history is one contiguous copy
-            const size_t hrow = (size_t)ctx->C * nblk_stride;
-            if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + hrow * it, h_llp.p + row * slot, hrow * sizeof(double), cudaMemcpyDeviceToHost, cs));
-            if (hist_ll) CK(cudaMemcpyAsync(hist_ll + hrow * it, h_ll.p + row * slot, hrow * sizeof(double), cudaMemcpyDeviceToHost, cs));
-            if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + hrow * it, h_acc.p + row * slot, hrow, cudaMemcpyDeviceToHost, cs));
-            CK(cudaEventRecord(freed[slot], cs));
+    if (rho_sched) {
+        CK(io.d_rho.ensure(J * R));
+        if (!io.h_rho || io.h_rho_n < J * R) {
+            if (io.h_rho) cudaFreeHost(io.h_rho);
+            io.h_rho = nullptr; io.h_rho_n = 0;
+            CK(cudaHostAlloc((void **)&io.h_rho, J * R * sizeof(double), cudaHostAllocDefault));
+            io.h_rho_n = J * R;
         }
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (want_hist) {
-        CK(cudaStreamSynchronize(cs));
-        for (int i = 0; i < ring; ++i) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
-        cudaStreamDestroy(cs);
-        h_llp.release(); h_ll.release(); h_acc.release();
+    if (!io.s_in) {
+        CK(cudaStreamCreateWithFlags(&io.s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&io.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < R; ++i) {
+            CK(cudaEventCreateWithFlags(&io.kernel_done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&io.rho_ready[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&io.copied[i], cudaEventDisableTiming));
+        }
     }
-    return 0;
+    // drainer: pinned ring -> caller's arrays
+    std::atomic<int> recorded{0}, drained{0};
+    std::atomic<bool> failed{false};
+    std::thread drainer;
+    if (want_hist && n_sweeps > 0) {
+        drainer = std::thread([&]() {
+            cudaSetDevice(ctx->cfg.device);
+            for (int it = 0; it < n_sweeps; ++it) {
+                while (recorded.load(std::memory_order_acquire) <= it) {
+                    if (failed.load(std::memory_order_relaxed)) return;
+                    std::this_thread::yield();
+                }
+                const int slot = it % R;
+                if (cudaEventSynchronize(io.copied[slot]) != cudaSuccess) { failed = true; return; }
+                const uint8_t *src = io.h_hist + slot_bytes * slot;
+                if (hist_ll_prop) std::memcpy(hist_ll_prop + row * it, src, row * sizeof(double));
+                if (hist_ll) std::memcpy(hist_ll + row * it, src + row * sizeof(double), row * sizeof(double));
+                if (hist_accepted) std::memcpy(hist_accepted + row * it, src + 2 * row * sizeof(double), row);
+                drained.store(it + 1, std::memory_order_release);
+            }
+        });
+    }
+    int rc = 0;
+    auto body = [&]() -> int {
+        for (int it = 0; it < n_sweeps; ++it) {
+            const int pat = (first_pattern + it) & 1;
+            const int slot = it % R;
+            if (want_hist) {  // the slot's previous rows have left the pinned ring (and hence the device ring)
+                while (drained.load(std::memory_order_acquire) < it - R + 1) {
+                    if (failed.load(std::memory_order_relaxed)) return fail(ctx, "dmcmc_run_sweeps: history copy failed");
+                    std::this_thread::yield();
+                }
+            }
+            if (rho_sched) {  // this sweep's pCN memory: caller -> pinned ring -> device ring, on the copy-in stream
+                if (it >= R) {
+                    CK(cudaEventSynchronize(io.rho_ready[slot]));                 // the ring row's last upload has left the host
+                    CK(cudaStreamWaitEvent(io.s_in, io.kernel_done[slot], 0));   // and its kernel no longer reads the device row
+                }
+                std::memcpy(io.h_rho + J * slot, rho_sched + J * it, J * sizeof(double));
+                CK(cudaMemcpyAsync(io.d_rho.p + J * slot, io.h_rho + J * slot, J * sizeof(double), cudaMemcpyHostToDevice, io.s_in));
+                CK(cudaEventRecord(io.rho_ready[slot], io.s_in));
+                CK(cudaStreamWaitEvent(ctx->stream, io.rho_ready[slot], 0));
+            }
+            if (half_len > 0 && switch_layout_async(ctx, nb[pat], li1[pat].data(), li2[pat].data(), lpin[pat].data()))
+                return -1;
+            SolveParams sp;
+            if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+            if (rho_sched) sp.rho = io.d_rho.p + J * slot;
+            sp.iter = iter0 + (uint32_t)it;
+            sp.reinvert = !ctx->w_valid;  // fused layout switch: noise and ll recovered from the accepted X
+            sp.store_w = ctx->w_valid;
+            sp.out_stride = want_hist ? nblk_stride : sp.nblk;
+            sp.acc_count = ctx->d_counts.p;
+            sp.prop_count = ctx->d_counts.p + ctx->J;
+            if (want_hist) {
+                uint8_t *d = io.d_hist.p + slot_bytes * slot;
+                sp.out_llprop = hist_ll_prop ? (double *)d : nullptr;
+                sp.out_ll = hist_ll ? (double *)(d + row * sizeof(double)) : nullptr;
+                sp.out_acc = hist_accepted ? d + 2 * row * sizeof(double) : nullptr;
+                if (it >= R) CK(cudaStreamWaitEvent(ctx->stream, io.copied[slot], 0));  // device ring slot is free
+            }
+            if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
+            ctx->sel_cur ^= 1;
+            if (want_hist || rho_sched) CK(cudaEventRecord(io.kernel_done[slot], ctx->stream));
+            if (want_hist) {
+                CK(cudaStreamWaitEvent(io.s_out, io.kernel_done[slot], 0));
+                // the kernel wrote its rows with the caller's stride: one contiguous copy per sweep
+                CK(cudaMemcpyAsync(io.h_hist + slot_bytes * slot, io.d_hist.p + slot_bytes * slot, slot_bytes, cudaMemcpyDeviceToHost, io.s_out));
+                CK(cudaEventRecord(io.copied[slot], io.s_out));
+                recorded.store(it + 1, std::memory_order_release);
+            }
+        }
+        return 0;
+    };
+    rc = body();
+    if (rc) failed = true;
+    if (drainer.joinable()) drainer.join();
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, "dmcmc_run_sweeps: stream synchronisation failed");
+    if (io.s_in) { cudaStreamSynchronize(io.s_in); cudaStreamSynchronize(io.s_out); }
+    if (!rc && failed) rc = fail(ctx, "dmcmc_run_sweeps: history copy failed");
+    return rc;
 }
 
 void *dmcmc_host_alloc(size_t bytes) {

@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     double lsum = 0.0, lsum_a = 0.0;
     bool ok = true;
     const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
+    PhiloxKeys pkeys;
+    pkeys.set(p.seed);
 
     // ---- input pipeline (issue side): LDGSTS, runs depth-1 tiles ahead of the solve, across intervals ----
     // Lane l copies piece pc of chain r = q * RPI + l / NPT in its q-th request (RPI chains per request),
@@ -432,7 +434,9 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                     // chain r = q * RPI + rl: record offset r * RECW * 8 bytes; the swizzle term has period 4 in q (RPI = 2)
                     const uint32_t dst = IS::SWZ ? db[q & 3] + (uint32_t)((q & ~3) * RPI * IS::RECW * 8)
                                                  : db[0] + (uint32_t)(q * RPI * IS::RECW * 8);
+#ifndef DMCMC_EXP_NOLOAD
                     if (lv) cp_async16(dst, src[q]);
+#endif
                     src[q] += iadv;
                 }
             } else {
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                         for (int w = 0; w < M; ++w)
 #pragma unroll
                             for (int h = 0; h < TILE / 4; ++h)
-                                philox_normal4f(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w,
+                                philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w,
                                                 (uint32_t)((kh >> 2) + h), (float *)&z[w][4 * h]);
                     } else {
 #pragma unroll
@@ -611,7 +615,11 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                             if (live && active) {
                                 double *dst = xph + (s - 1) * D;
                                 if constexpr (D == 2) {
+#ifndef DMCMC_EXP_NOSTORE
                                     st_v4(dst, xprev[0], xprev[1], x[0], x[1]);
+#else
+                                    if (x[0] == 1.2345e300) st_v4(dst, xprev[0], xprev[1], x[0], x[1]);
+#endif
                                 } else {
                                     double pr[2 * D];
 #pragma unroll
