@@ -35,6 +35,16 @@ METRIC, UNIT = "bridge path-steps/sec", "path-steps/s"
 CPU_SAMPLE_CHAINS, CPU_SAMPLE_SWEEPS = 512, 24  # ~1.2e8 path-steps: 10-30 s of CPU work over the host cores
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    committed ncu --set full capture of this workload (profiles/r1_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return int(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -236,7 +246,7 @@ def main():
             "gpu_launches": kern["launches"],
             "kernels": kern,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak, "traffic": profiled_traffic(), "peak_source": which,
                          "kernel": "solve_kernel<ModelFHN, PSI, MODE_IMPUTE, PHILOX, REINV, FAST>",
                          "algorithmic_bytes_per_launch": BYTES_PER_STEP * steps_per_sweep},
             "clocks": clocks,
