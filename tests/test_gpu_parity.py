@@ -300,3 +300,95 @@ def test_run_sweeps_histories_and_counts(pkg):
     X1, _ = e.download_state(0)
     X2, _ = e2.download_state(0)
     assert np.array_equal(X1, X2)
+
+
+def _ragged_fhn(pkg, C):
+    """Irregular observation times => ragged grids: N_j in {1, 3, 17, 16, 33, 8, 40, 5} (single
+    steps, odd counts, exact / one-over multiples of the 8-step W tile and the 16-step staged tile)."""
+    P = pkg.problems
+    rng = np.random.default_rng(77)
+    steps = np.array([1, 3, 17, 16, 33, 8, 40, 5])
+    dt = 0.004
+    times = np.cumsum(steps * dt)
+    x0 = np.array([-1.0, -1.0])
+    tt, X = P.simulate(P.MODEL_FHN, P.FHN_THETA, x0, times[-1] + 1e-3, 1e-4, rng)
+    idx = np.round(times / 1e-4).astype(int)
+    v = X[idx, 0] + 0.1 * rng.standard_normal(len(steps))
+    spec = P.make_spec(P.MODEL_FHN, P.FHN_THETA, x0, times, v[:, None], [[1.0, 0.0]], [[0.01]], dt, C=C, rho=0.9)
+    assert list(spec["N"]) == list(steps)
+    return spec
+
+
+def test_ragged_grid_parity(pkg, orc):
+    """Ragged inputs (edge cases of the record layout): stored-noise sweeps, fused layout switches in
+    both chequerboard patterns, explicit noise and Philox noise, against the oracle."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = _ragged_fhn(pkg, C=45)
+    o, e = _pair(pkg, orc, spec)
+    P = pkg.problems
+    rng = np.random.default_rng(31)
+    Z0 = rng.standard_normal((o.C, o.S, o.m))
+    o.init_paths(Z=Z0)
+    e.init_paths(Z=Z0)
+    assert close(e.get_ll(), o.ll), maxrel(e.get_ll(), o.ll)
+    _compare_state(o, e, 0, "init")
+    for it in range(2):  # unblocked, stored noise
+        Z = rng.standard_normal((o.C, o.S, o.m))
+        E = rng.exponential(size=(o.C, o.nblk))
+        llp_o, ll_o, acc_o = o.impute(Z, E)
+        llp_g, ll_g, acc_g = e.impute(it, Z, E)
+        assert close(llp_g, llp_o) and np.array_equal(acc_g, acc_o)
+        _compare_state(o, e, 0, f"unblocked {it}")
+        _compare_state(o, e, 1, f"unblocked {it}")
+    im = interior_mask(o.N)
+    for it in range(4):  # fused layout switch, both patterns
+        lay = P.chequerboard_layout(o.rec_nobs, 1 + it // 2, it % 2)
+        o.relayout(*lay)
+        e.set_layout(*lay)
+        e.upload_tables(o.H, o.F0, o.Psi, o.c0, o.blk_g, o.blk_Qc)
+        Z = rng.standard_normal((o.C, o.S, o.m))
+        E = rng.exponential(size=(o.C, o.nblk))
+        ll_before = o.ll.copy()
+        llp_o, ll_o, acc_o = o.impute(Z, E)
+        llp_g, ll_g, acc_g = e.impute(10 + it, Z, E)
+        assert close(llp_g, llp_o, 1e-9), maxrel(llp_g, llp_o)
+        assert accept_mismatch_is_tie(acc_g, acc_o, E, llp_o, ll_before, 1e-9)
+        assert np.array_equal(acc_g, acc_o)
+        Xg, _ = e.download_state(0)
+        assert close(Xg[:, im], o.accepted_X()[:, im], 1e-9), maxrel(Xg[:, im], o.accepted_X()[:, im])
+        assert close(e.download_path(7), o.glue_path(7), 1e-9)
+    # Philox noise on the ragged grid
+    o2 = orc.Oracle(spec)
+    e2 = Engine(spec, seed=4242)
+    e2.upload_tables(o2.H, o2.F0, None, o2.c0)
+    o2.init_paths(seed=4242)
+    e2.init_paths()
+    for it in range(3):
+        llp_o, ll_o, acc_o = o2.impute(seed=4242, it=it)
+        llp_g, ll_g, acc_g = e2.impute(it)
+        assert close(llp_g, llp_o), maxrel(llp_g, llp_o)
+        assert np.array_equal(acc_g, acc_o)
+        _compare_state(o2, e2, 0, f"philox {it}")
+
+
+def test_block_ll_additivity_full_size(pkg):
+    """Size-independent property at BASELINE size: after a sweep the per-block log-likelihoods of the
+    blocked layout are finite for every (chain, block), the glued path is continuous across block
+    edges (pinned end points), and an unblocked re-evaluation of the same accepted path is
+    reproducible bit for bit (init_ll! twice)."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = pkg.problems.fhn_spec(n_obs=100, C=1024, dt=1e-3)
+    e = Engine(spec, seed=11)
+    e.init_paths()
+    e.run_sweeps(0, 4, half_len=1)
+    ll = e.get_ll()
+    assert ll.shape[0] == 1024 and np.isfinite(ll).all()
+    p = e.download_path(1023)
+    assert np.isfinite(p).all()
+    # consecutive points stay within a few Euler steps' worth of motion: no jump at block edges
+    assert np.abs(np.diff(p, axis=0)).max() < 0.5
+    P = pkg.problems
+    e.relayout(*P.chequerboard_layout(e.rec_nobs, 0, 0))
+    ll1 = e.get_ll().copy()
+    e.init_ll()
+    assert np.array_equal(ll1, e.get_ll())
