@@ -248,6 +248,21 @@ struct InStage {
     }
 };
 
+// per-interval metadata of one unit, held in registers one interval ahead: under a loaded memory
+// system every dependent global load at an interval switch costs microseconds
+struct IvMeta {
+    int N, tile_off, xs, sx, sw;
+    long long xoff;
+    double rho, aB0, ab0;
+};
+__device__ __forceinline__ IvMeta load_meta(const SolveParams &p, int j, int chain, int D) {
+    IvMeta m;
+    m.N = p.iv_N[j]; m.tile_off = p.iv_tile_off[j]; m.xs = p.iv_xs[j]; m.xoff = p.iv_xoff[j];
+    m.sx = p.selX_in[(size_t)j * p.C + chain]; m.sw = p.selW_in[(size_t)j * p.C + chain];
+    m.rho = p.rho[j]; m.aB0 = p.auxB[(size_t)j * D * D]; m.ab0 = p.auxbeta[(size_t)j * D];
+    return m;
+}
+
 __device__ __forceinline__ void cp_async_wait_depth(int depth) {  // allow depth - 2 groups in flight
     if (depth == 2) cp_async_wait<0>();
     else if (depth == 4) cp_async_wait<2>();
@@ -300,17 +315,21 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     __syncthreads();
 
     // ---- table pipeline (issue side, thread 0): TMA bulk copy of one tile's records per stage ----
+    IvMeta mc = load_meta(p, i1, chain, D), mn = mc;  // current interval of the solve, and the next one
+    if (i1 < i2) mn = load_meta(p, i1 + 1, chain, D);
+    int jc = i1;                                      // interval the solve is in
     int tj = i1, ttl = 0, tq = 0;
     auto issue_table = [&]() {
         if (tj > i2) return;
-        const int Nj = p.iv_N[tj];
+        const int Nj = tj == jc ? mc.N : (tj == jc + 1 ? mn.N : p.iv_N[tj]);
+        const int toffj = tj == jc ? mc.tile_off : (tj == jc + 1 ? mn.tile_off : p.iv_tile_off[tj]);
         const int npad = ((Nj + TILE - 1) >> 3) * TILE;  // records the table holds for this interval
         const int nrec = min(TS, npad - ttl * TS);
         const uint32_t bytes = (uint32_t)(nrec * RS * sizeof(double));
         uint64_t *bar = &full[tq & dmask];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(stab + (size_t)(tq & dmask) * TS * RS, p.table + ((size_t)p.iv_tile_off[tj] * TILE + (size_t)ttl * TS) * RS, bytes, bar);
+        bulk_g2s(stab + (size_t)(tq & dmask) * TS * RS, p.table + ((size_t)toffj * TILE + (size_t)ttl * TS) * RS, bytes, bar);
         ++tq;
         if (++ttl * TS >= Nj) { ttl = 0; ++tj; }
     };
@@ -381,13 +400,13 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
         else { const int g = q * 32 + lane; r = g / IS::NPT; pc = g % IS::NPT; }
     };
     auto setup_issue = [&](int j) {
-        const int Nj = p.iv_N[j];
+        const IvMeta mi = j == jc ? mc : (j == jc + 1 ? mn : load_meta(p, j, chain, D));
+        const int Nj = mi.N;
         int_ = (Nj + TS - 1) / TS;
-        const uint8_t *selp = NEED_XA ? p.selX_in : p.selW_in;
-        const unsigned selmask = __ballot_sync(0xffffffffu, selp[(size_t)j * p.C + chain]);
+        const unsigned selmask = __ballot_sync(0xffffffffu, NEED_XA ? mi.sx : mi.sw);
         if constexpr (NEED_XA) {
-            const size_t xo = (size_t)p.iv_xoff[j];
-            const int xs = p.iv_xs[j];
+            const size_t xo = (size_t)mi.xoff;
+            const int xs = mi.xs;
             ilim = Nj * D;  // live doubles of the chain's stream in this interval
             iadv = (size_t)TS * D;
 #pragma unroll
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                 src[q] = p.X[(selmask >> r) & 1] + xo + (size_t)cr * xs + pc * 2;
             }
         } else {
-            const size_t t0 = (size_t)p.iv_tile_off[j];
+            const size_t t0 = (size_t)mi.tile_off;
             ilim = (Nj + TILE - 1) >> 3;  // W tiles of this interval
             iadv = (size_t)(TS / TILE) * p.C * M * TILE;
 #pragma unroll
@@ -411,14 +430,10 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
             }
         }
     };
-    // per-lane destination offsets inside a stage (bytes); with the d = 2 swizzle they repeat every 4 requests
-    uint32_t dsto[IS::SWZ ? 4 : 1];
-    if constexpr (IS::SWZ) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dsto[i] = (uint32_t)IS::piece(i * RPI + rl, pcl) * 8u;
-    } else if constexpr (PO2) {
-        dsto[0] = (uint32_t)IS::piece(rl, pcl) * 8u;
-    }
+    // per-lane destination offset inside a stage (bytes).  d = 2 swizzle: request q copies piece pcl of chain
+    // r = 2q + rl into slot pcl ^ (r & 7) = (pcl ^ rl) ^ 2(q & 3) of its 256-byte record, i.e. byte offset
+    // q * 512 + (dst0 ^ ((q & 3) << 5)): one register, three XORs with immediates per tile
+    const uint32_t dst0 = IS::SWZ ? (uint32_t)(rl * IS::RECW * 8 + ((pcl ^ rl) << 4)) : (uint32_t)IS::piece(rl, pcl) * 8u;
     auto issue_in = [&]() {  // copy tile (ij, itl) into its stage, advance; always commits a group
         if (ij <= i2) {
             const uint32_t sbase = smem_u32(sinp + (size_t)(iq & dmask) * IS::WARP);
@@ -426,14 +441,11 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                 bool lv;
                 if constexpr (NEED_XA) lv = itl * TS * D + pcl * 2 < ilim;
                 else lv = itl * (TS / TILE) + pcl / (4 * M) < ilim;
-                uint32_t db[IS::SWZ ? 4 : 1];
-#pragma unroll
-                for (int i = 0; i < (IS::SWZ ? 4 : 1); ++i) db[i] = sbase + dsto[i];
+                const uint32_t da = sbase + dst0;  // stage bases are 256-byte aligned: the XOR below never carries
 #pragma unroll
                 for (int q = 0; q < IS::NPT; ++q) {
-                    // chain r = q * RPI + rl: record offset r * RECW * 8 bytes; the swizzle term has period 4 in q (RPI = 2)
-                    const uint32_t dst = IS::SWZ ? db[q & 3] + (uint32_t)((q & ~3) * RPI * IS::RECW * 8)
-                                                 : db[0] + (uint32_t)(q * RPI * IS::RECW * 8);
+                    const uint32_t dst = IS::SWZ ? (da ^ (uint32_t)((q & 3) << 5)) + (uint32_t)(q * RPI * IS::RECW * 8)
+                                                 : da + (uint32_t)(q * RPI * IS::RECW * 8);
 #ifndef DMCMC_EXP_NOLOAD
                     if (lv) cp_async16(dst, src[q]);
 #endif
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
                     if (lv) cp_async16(sbase + (uint32_t)IS::piece(r, pc) * 8u, src[q] + toff);
                 }
             }
-            if (++itl == int_) {
+            if (__builtin_expect(++itl == int_, 0)) {  // next interval (rare: keep it a branch, not predicated code)
                 itl = 0;
                 if (++ij <= i2) setup_issue(ij);
             }
@@ -466,22 +478,19 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
     uint32_t sxbits = 0, swbits = 0;  // selectors of the block's first 32 intervals (re-used by the swap below)
     double *xp_end = nullptr;         // last point of the block in the proposal container
     for (int j = i1; j <= i2; ++j) {
-        const int N = p.iv_N[j];
-        const int nt = (N + TS - 1) / TS;
-        const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
-        if (j - i1 < 32) { sxbits |= (uint32_t)sx << (j - i1); swbits |= (uint32_t)sw << (j - i1); }
-        if (j < i2) {
-            // the next interval's metadata is needed by the issue side one tile before this interval ends
-            // and by the solve right after it: pull the lines into L1 now, under a loaded memory system
-            // each of these dependent loads would otherwise cost microseconds at the switch
-            const int jn = j + 1;
-            prefetch_l1(p.iv_N + jn); prefetch_l1(p.iv_tile_off + jn); prefetch_l1(p.iv_xoff + jn); prefetch_l1(p.iv_xs + jn);
-            prefetch_l1(p.selX_in + (size_t)jn * p.C + chain); prefetch_l1(p.selW_in + (size_t)jn * p.C + chain);
-            prefetch_l1(p.rho + jn); prefetch_l1(p.auxB + (size_t)jn * D * D); prefetch_l1(p.auxbeta + (size_t)jn * D);
+        if (j > i1) {  // the metadata of this interval arrived while the previous one was solved
+            mc = mn;
+            jc = j;
+            if (j < i2) mn = load_meta(p, j + 1, chain, D);  // in flight for the whole interval
         }
+        const int N = mc.N;
+        const int nt = (N + TS - 1) / TS;
+        const int sx = mc.sx, sw = mc.sw;
+        if (j - i1 < 32) { sxbits |= (uint32_t)sx << (j - i1); swbits |= (uint32_t)sw << (j - i1); }
         double aB[FAST ? 1 : D * D], abeta[FAST ? 1 : D], aatil[MD::CONST_SIGMA ? 1 : D * D];
         if constexpr (FAST) {
-            fk.set_interval(p.auxB + (size_t)j * D * D, p.auxbeta + (size_t)j * D);
+            fk.aB0 = mc.aB0;
+            fk.c2 = mc.ab0 - fk.s * fk.ie;
         } else {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) aB[i] = p.auxB[(size_t)j * D * D + i];
@@ -492,13 +501,13 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
         }
-        const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
+        const double rho = (MODE == MODE_IMPUTE) ? mc.rho : 1.0;
         const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
         double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : p.W[1 - sw];
-        double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];  // this chain's proposal record
+        double *Xp = p.X[1 - sx] + mc.xoff + (size_t)chain * mc.xs;  // this chain's proposal record
         const bool store_w = active && STORE_W_MODE;
         xp_end = Xp + (size_t)(N - 1) * D;
-        const size_t wtile0 = (size_t)p.iv_tile_off[j];
+        const size_t wtile0 = (size_t)mc.tile_off;
 
         for (int tl = 0; tl < nt; ++tl, ++q) {
             // ---- table records of this tile: wait, refill the stage freed by the previous tile ----
