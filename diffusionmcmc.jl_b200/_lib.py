@@ -58,6 +58,10 @@ SYMBOLS = {
     "dmcmc_kernel_times": (C.c_int, [C.c_void_p, _dp, _lp]),
     "dmcmc_device_bytes": (C.c_int64, [C.c_void_p]),
     "dmcmc_set_threads": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dmcmc_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dmcmc_launch_count": (C.c_int64, [C.c_void_p]),
+    "dmcmc_timer_start": (C.c_int, [C.c_void_p]),
+    "dmcmc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "dmcmc_set_fast_step": (C.c_int, [C.c_void_p, C.c_int32]),
 }
 

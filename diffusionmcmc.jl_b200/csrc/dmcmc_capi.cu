@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -92,6 +93,9 @@ struct dmcmc_ctx {
     std::vector<int> ev_mode;     // SolveMode of each pair
     size_t ev_used = 0;
     bool timing = true;
+    int time_every = 8;   // kernel-duration events around every n-th solve launch (0: never)
+    uint64_t launches = 0, launches_reported = 0;
+    cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // stop-watch (dmcmc_timer_start / stop)
     // host copies
     std::vector<int32_t> rec_nobs, N, pt_off, st_off, tile_off, iv_first, iv_rec, xs;
     std::vector<int64_t> xoff;  // [J+1] X container layout: interval j starts at xoff[j], chain stride xs[j]
@@ -360,7 +364,9 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
 
 int timed_launch(dmcmc_ctx *ctx, int mode, const SolveParams &sp) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->timing) {
+    const bool timed = ctx->timing && ctx->time_every > 0 && (ctx->launches % ctx->time_every) == 0;
+    ++ctx->launches;
+    if (timed) {
         if (ctx->ev_used >= 65536) ctx->ev_used = 0;  // nobody is reading the timings
         if (ctx->ev_used + 2 > ctx->ev.size()) {
             for (int i = 0; i < 2; ++i) {
@@ -377,7 +383,7 @@ int timed_launch(dmcmc_ctx *ctx, int mode, const SolveParams &sp) {
         CK(cudaEventRecord(e0, ctx->stream));
     }
     CK(launch_solve(ctx->cfg.model, mode, sp, ctx->threads, ctx->stream));
-    if (ctx->timing) CK(cudaEventRecord(e1, ctx->stream));
+    if (timed) CK(cudaEventRecord(e1, ctx->stream));
     return 0;
 }
 
@@ -513,6 +519,7 @@ int dmcmc_create(const dmcmc_config *cfg, dmcmc_ctx **out) {
     ctx = new dmcmc_ctx();
     ctx->cfg = *cfg;
     ctx->d = d; ctx->m = m; ctx->nth = nth; ctx->C = cfg->n_chains;
+    if (const char *t = getenv("DMCMC_TIMING_EVERY")) ctx->time_every = std::max(0, atoi(t));
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
@@ -527,6 +534,7 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->sw0) { cudaEventDestroy(ctx->sw0); cudaEventDestroy(ctx->sw1); }
     {
         SweepIO &io = ctx->io;
         if (io.s_in) {
@@ -1000,7 +1008,7 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
     const int nbmax = std::max(nb[0], nb[1]);
     REQUIRE(!want_hist || nblk_stride >= nbmax, "dmcmc_run_sweeps: nblk_stride smaller than the number of blocks");
     const size_t row = (size_t)ctx->C * (want_hist ? nblk_stride : nbmax);  // units per history row
-    const int R = 8;                                                        // ring slots
+    constexpr int R = 8;                                                    // ring slots
     const size_t slot_bytes = 2 * row * sizeof(double) + ((row + 15) & ~(size_t)15);  // [ll deg | ll | accepted], 16-byte aligned
     const size_t J = (size_t)ctx->J;
     SweepIO &io = ctx->io;
@@ -1031,27 +1039,32 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             CK(cudaEventCreateWithFlags(&io.copied[i], cudaEventDisableTiming));
         }
     }
-    // drainer: pinned ring -> caller's arrays
-    std::atomic<int> recorded{0}, drained{0};
+    // drainers: pinned ring -> caller's arrays.  One core copies ~10 GB/s, which is just the rate the C3
+    // histories arrive at (879 KB per 80 us sweep), so two threads take alternate sweeps.
+    constexpr int NDRAIN = 2;
+    std::atomic<int> recorded{0};
+    std::atomic<int> drained[NDRAIN];  // per thread: sweeps it = t, t + NDRAIN, ... finished so far
+    for (auto &d : drained) d.store(0);
     std::atomic<bool> failed{false};
-    std::thread drainer;
+    std::thread drainer[NDRAIN];
     if (want_hist && n_sweeps > 0) {
-        drainer = std::thread([&]() {
-            cudaSetDevice(ctx->cfg.device);
-            for (int it = 0; it < n_sweeps; ++it) {
-                while (recorded.load(std::memory_order_acquire) <= it) {
-                    if (failed.load(std::memory_order_relaxed)) return;
-                    std::this_thread::yield();
+        for (int t = 0; t < NDRAIN; ++t)
+            drainer[t] = std::thread([&, t]() {
+                cudaSetDevice(ctx->cfg.device);
+                for (int it = t; it < n_sweeps; it += NDRAIN) {
+                    while (recorded.load(std::memory_order_acquire) <= it) {
+                        if (failed.load(std::memory_order_relaxed)) return;
+                        std::this_thread::yield();
+                    }
+                    const int slot = it % R;
+                    if (cudaEventSynchronize(io.copied[slot]) != cudaSuccess) { failed = true; return; }
+                    const uint8_t *src = io.h_hist + slot_bytes * slot;
+                    if (hist_ll_prop) std::memcpy(hist_ll_prop + row * it, src, row * sizeof(double));
+                    if (hist_ll) std::memcpy(hist_ll + row * it, src + row * sizeof(double), row * sizeof(double));
+                    if (hist_accepted) std::memcpy(hist_accepted + row * it, src + 2 * row * sizeof(double), row);
+                    drained[t].fetch_add(1, std::memory_order_release);
                 }
-                const int slot = it % R;
-                if (cudaEventSynchronize(io.copied[slot]) != cudaSuccess) { failed = true; return; }
-                const uint8_t *src = io.h_hist + slot_bytes * slot;
-                if (hist_ll_prop) std::memcpy(hist_ll_prop + row * it, src, row * sizeof(double));
-                if (hist_ll) std::memcpy(hist_ll + row * it, src + row * sizeof(double), row * sizeof(double));
-                if (hist_accepted) std::memcpy(hist_accepted + row * it, src + 2 * row * sizeof(double), row);
-                drained.store(it + 1, std::memory_order_release);
-            }
-        });
+            });
     }
     int rc = 0;
     auto body = [&]() -> int {
@@ -1059,7 +1072,9 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             const int pat = (first_pattern + it) & 1;
             const int slot = it % R;
             if (want_hist) {  // the slot's previous rows have left the pinned ring (and hence the device ring)
-                while (drained.load(std::memory_order_acquire) < it - R + 1) {
+                static_assert(R % NDRAIN == 0, "a ring slot is always drained by the same thread");
+                const int prev = it - R;  // the sweep that used this slot before
+                while (prev >= 0 && drained[prev % NDRAIN].load(std::memory_order_acquire) < prev / NDRAIN + 1) {
                     if (failed.load(std::memory_order_relaxed)) return fail(ctx, "dmcmc_run_sweeps: history copy failed");
                     std::this_thread::yield();
                 }
@@ -1107,7 +1122,8 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
     };
     rc = body();
     if (rc) failed = true;
-    if (drainer.joinable()) drainer.join();
+    for (auto &d : drainer)
+        if (d.joinable()) d.join();
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, "dmcmc_run_sweeps: stream synchronisation failed");
     if (io.s_in) { cudaStreamSynchronize(io.s_in); cudaStreamSynchronize(io.s_out); }
     if (!rc && failed) rc = fail(ctx, "dmcmc_run_sweeps: history copy failed");
@@ -1331,6 +1347,38 @@ int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx) {
 extern "C" int dmcmc_set_fast_step(dmcmc_ctx *ctx, int32_t on) {
     REQUIRE(ctx, "dmcmc_set_fast_step: null context");
     ctx->fast_step = on != 0;
+    return 0;
+}
+
+extern "C" int dmcmc_set_timing(dmcmc_ctx *ctx, int32_t every) {
+    REQUIRE(ctx && every >= 0, "dmcmc_set_timing: bad argument");
+    ctx->time_every = every;
+    return 0;
+}
+
+extern "C" int64_t dmcmc_launch_count(dmcmc_ctx *ctx) {
+    if (!ctx) return -1;
+    const int64_t n = (int64_t)(ctx->launches - ctx->launches_reported);
+    ctx->launches_reported = ctx->launches;
+    return n;
+}
+
+extern "C" int dmcmc_timer_start(dmcmc_ctx *ctx) {
+    REQUIRE(ctx, "dmcmc_timer_start: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->sw0) { CK(cudaEventCreate(&ctx->sw0)); CK(cudaEventCreate(&ctx->sw1)); }
+    CK(cudaEventRecord(ctx->sw0, ctx->stream));
+    return 0;
+}
+
+extern "C" int dmcmc_timer_stop(dmcmc_ctx *ctx, double *ms) {
+    REQUIRE(ctx && ms && ctx->sw0, "dmcmc_timer_stop: no running timer");
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(cudaEventRecord(ctx->sw1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->sw1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, ctx->sw0, ctx->sw1));
+    *ms = (double)f;
     return 0;
 }
 

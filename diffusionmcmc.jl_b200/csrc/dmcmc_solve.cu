@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // everything below reads what the previous kernel in the stream wrote (selectors, paths, ll)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- table pipeline (issue side, thread 0): TMA bulk copy of one tile's records per stage ----
     IvMeta mc = load_meta(p, i1, chain, D), mn = mc;  // current interval of the solve, and the next one
@@ -662,6 +664,7 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
             }
         }
     }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     llp += lsum;
     lla += lsum_a;
     if (!ok) llp = -INFINITY;
@@ -770,8 +773,19 @@ static cudaError_t launch_one(const SolveParams &p0, int threads, cudaStream_t s
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, threads, smem_for(depth), s>>>(p);
-    return cudaGetLastError();
+    // programmatic dependent launch: the next sweep's CTAs may be scheduled (and set up their shared
+    // memory) while this grid drains; they block in griddepcontrol.wait before touching global memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem_for(depth);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <class MD, bool PSI, bool FAST>

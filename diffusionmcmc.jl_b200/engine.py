@@ -267,6 +267,21 @@ class Engine:
         self._ck(self.lib.dmcmc_kernel_times(self.h, _dp(ms), n.ctypes.data_as(_lib._lp)))
         return ms, n
 
+    def set_timing(self, every):
+        """Per-kernel duration events around every n-th solve launch (default 8; 0 = never)."""
+        self._ck(self.lib.dmcmc_set_timing(self.h, int(every)))
+
+    def launch_count(self):
+        return int(self.lib.dmcmc_launch_count(self.h))
+
+    def timer_start(self):
+        self._ck(self.lib.dmcmc_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.lib.dmcmc_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def kernel_ms(self):
         ms, n = self.kernel_times()
         return float(ms[0]), int(n[0])

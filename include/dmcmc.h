@@ -175,6 +175,15 @@ int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted /* [nblk] */, int64_t 
  * since the previous call, per kernel mode: [0] imputation, [1] parameter-step solve,
  * [2] layout switch (W re-inversion + ll), [3] ll only. */
 int dmcmc_kernel_times(dmcmc_ctx *ctx, double ms[4], int64_t launches[4]);
+/* The event pair costs about 5 us of stream time per launch, so only every n-th solve launch is
+ * timed (default 8; 1 = every launch, 0 = never).  `launches` of dmcmc_kernel_times counts the timed
+ * launches only; dmcmc_launch_count counts all solve launches since the previous call. */
+int dmcmc_set_timing(dmcmc_ctx *ctx, int32_t every);
+int64_t dmcmc_launch_count(dmcmc_ctx *ctx);
+/* Stop-watch on the context's stream: CUDA events bracketing everything enqueued between the two
+ * calls (dmcmc_timer_stop synchronises the stream). */
+int dmcmc_timer_start(dmcmc_ctx *ctx);
+int dmcmc_timer_stop(dmcmc_ctx *ctx, double *ms);
 int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
 /* Threads per CTA of the solve kernels (32..128, multiple of 32; default 64). */
 int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
