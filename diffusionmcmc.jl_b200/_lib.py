@@ -51,6 +51,10 @@ SYMBOLS = {
     "dmcmc_set_block_mask": (C.c_int, [C.c_void_p, _ip]),
     "dmcmc_download_segment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
     "dmcmc_upload_segment": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp]),
+    "dmcmc_segment_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32]),
+    "dmcmc_set_start_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "dmcmc_stream": (C.c_void_p, [C.c_void_p]),
+    "dmcmc_impute_async": (C.c_int, [C.c_void_p, C.c_uint32]),
     "dmcmc_n_blocks": (C.c_int32, [C.c_void_p]),
     "dmcmc_get_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_set_ll": (C.c_int, [C.c_void_p, _dp]),

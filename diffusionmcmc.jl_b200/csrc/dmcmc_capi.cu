@@ -57,7 +57,8 @@ struct Layout {
     int32_t nblk = 0;
     bool has_psi = false;
     DevBuf<int32_t> d_i1, d_i2, d_pinned, d_iv_blk, d_active;
-    bool has_mask = false;
+    bool has_mask = false, has_mask_copy = false;
+    std::vector<int32_t> active_host;
     Tables tab[2];  // per law slot
     uint64_t last_used = 0;
     bool used = false;
@@ -466,6 +467,7 @@ int select_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t
     Layout &l = ctx->layout[s];
     l.used = true;
     l.nblk = nblk;
+    l.has_mask = l.has_mask_copy = false;
     l.i1.assign(i1, i1 + nblk);
     l.i2.assign(i2, i2 + nblk);
     l.pinned.assign(pinned, pinned + nblk);
@@ -715,7 +717,7 @@ int dmcmc_set_layout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int3
     if (select_layout(ctx, nblk, i1, i2, pinned)) return -1;
     if (resize_ll(ctx)) return -1;
     if (before != ctx->lay_cur) ctx->w_valid = false;
-    return sync(ctx);
+    return 0;  // stream-ordered: no host synchronisation
 }
 
 int dmcmc_set_block_mask(dmcmc_ctx *ctx, const int32_t *active) {
@@ -727,9 +729,13 @@ int dmcmc_set_block_mask(dmcmc_ctx *ctx, const int32_t *active) {
         return 0;
     }
     std::vector<int32_t> a(active, active + l.nblk);
-    if (upload(ctx, l.d_active, a)) return -1;
+    if (!(l.has_mask_copy && a == l.active_host)) {  // masks alternate with the layouts: upload only when changed
+        if (upload(ctx, l.d_active, a)) return -1;
+        l.active_host = a;
+        l.has_mask_copy = true;
+    }
     l.has_mask = true;
-    return sync(ctx);
+    return 0;  // stream-ordered: no host synchronisation
 }
 
 static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool up) {
@@ -747,12 +753,64 @@ static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool 
     g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
     g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
     g.selX = ctx->d_selX[ctx->sel_cur].p;
-    g.packed = pk.p; g.upload = up;
+    g.packed = pk.p; g.upload = up; g.pk_stride = (int64_t)steps * ctx->d;
     CK(launch_segment(g, ctx->stream));
     if (!up) CK(cudaMemcpyAsync(X, pk.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (sync(ctx)) return -1;
     pk.release();
     if (up) ctx->w_valid = false;
+    return 0;
+}
+
+// device-side variant: `dev` is a caller-owned DEVICE buffer, element (chain, step, comp) at
+// dev[chain * chain_stride + step * d + comp]; enqueued on the context's stream, no host sync
+int dmcmc_segment_device(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *dev, int64_t chain_stride, int32_t upload_) {
+    REQUIRE(ctx && dev && j0 >= 0 && j1 > j0 && j1 <= ctx->J, "dmcmc_segment_device: bad interval range");
+    REQUIRE(ctx->have_grid, "dmcmc_segment_device: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int steps = ctx->st_off[j1] - ctx->st_off[j0];
+    REQUIRE(chain_stride >= (int64_t)steps * ctx->d, "dmcmc_segment_device: chain_stride too small");
+    SegmentParams g{};
+    g.C = ctx->C; g.D = ctx->d; g.j0 = j0; g.j1 = j1; g.steps = steps; g.TT = ctx->TT;
+    g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_st_off = ctx->d_st_off.p;
+    g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
+    g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
+    g.selX = ctx->d_selX[ctx->sel_cur].p;
+    g.packed = dev; g.upload = upload_; g.pk_stride = chain_stride;
+    CK(launch_segment(g, ctx->stream));
+    if (upload_) ctx->w_valid = false;
+    return 0;
+}
+
+// starting points from a DEVICE buffer: x0 of (chain, recording r) at dev[chain * chain_stride + r * d + comp]
+int dmcmc_set_start_device(dmcmc_ctx *ctx, const double *dev, int64_t chain_stride) {
+    REQUIRE(ctx && dev && ctx->have_start, "dmcmc_set_start_device: context not initialised");
+    CK(cudaSetDevice(ctx->cfg.device));
+    CK(launch_set_start(ctx->d_x0.p, dev, chain_stride, ctx->C, ctx->R, ctx->d, ctx->stream));
+    ctx->w_valid = false;
+    return 0;
+}
+
+void *dmcmc_stream(dmcmc_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// one imputation update with Philox noise, current layout and block mask: enqueued, not awaited;
+// results stay on the device (ll, selectors, accept counters)
+int dmcmc_impute_async(dmcmc_ctx *ctx, uint32_t iter) {
+    REQUIRE(ctx, "dmcmc_impute_async: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    Layout &lay0 = ctx->layout[ctx->lay_cur];
+    if (!lay0.tab[ctx->law_cur].valid && run_backward_filter(ctx, ctx->law_cur)) return -1;
+    SolveParams sp;
+    if (fill_params(ctx, sp, ctx->law_cur)) return -1;
+    if (ensure_unit_buffers(ctx)) return -1;
+    sp.iter = iter;
+    sp.reinvert = (!ctx->w_valid || !ctx->cfg.store_noise) ? 1 : 0;
+    sp.store_w = !sp.reinvert;
+    sp.out_llprop = ctx->d_out_llprop.p; sp.out_ll = ctx->d_out_ll.p; sp.out_acc = ctx->d_out_acc.p;
+    sp.acc_count = ctx->d_counts.p;
+    sp.prop_count = ctx->d_counts.p + ctx->J;
+    if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
+    ctx->sel_cur ^= 1;
     return 0;
 }
 

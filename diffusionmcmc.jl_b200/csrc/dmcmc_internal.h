@@ -98,10 +98,12 @@ struct SegmentParams {
     const int32_t *iv_xs;
     double *X[2];
     const uint8_t *selX;
-    double *packed;   // device [C][steps][D]
+    double *packed;   // device: element (chain, step, comp) at packed[chain * pk_stride + step * D + comp]
+    int64_t pk_stride;
     int32_t upload;   // 0: X -> packed, 1: packed -> X
 };
 cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s);
+cudaError_t launch_set_start(double *x0, const double *src, int64_t chain_stride, int C, int R, int D, cudaStream_t s);
 
 // noise transposition [C][S][M] -> [M][TT][C][8] is done on the host in the C-ABI layer.
 

@@ -868,10 +868,25 @@ __global__ void segment_kernel(const SegmentParams g) {
     const int off = g.iv_st_off[j] - g.iv_st_off[g.j0];
     for (int k = 0; k < g.iv_N[j]; ++k)
         for (int c = 0; c < g.D; ++c) {
-            double *pk = g.packed + ((size_t)chain * g.steps + off + k) * g.D + c;
+            double *pk = g.packed + (size_t)chain * g.pk_stride + (size_t)(off + k) * g.D + c;
             if (g.upload) X[(size_t)k * g.D + c] = *pk;
             else *pk = X[(size_t)k * g.D + c];
         }
+}
+
+// x0[(rec * D + comp) * C + chain] = src[chain * chain_stride + rec * D + comp]
+__global__ void set_start_kernel(double *x0, const double *src, long long chain_stride, int C, int R, int D) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= (long long)C * R * D) return;
+    const int chain = (int)(u % C), rc = (int)(u / C);
+    x0[(size_t)rc * C + chain] = src[(size_t)chain * chain_stride + rc];
+}
+
+cudaError_t launch_set_start(double *x0, const double *src, int64_t chain_stride, int C, int R, int D, cudaStream_t s) {
+    const long long n = (long long)C * R * D;
+    if (n <= 0) return cudaSuccess;
+    set_start_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(x0, src, (long long)chain_stride, C, R, D);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s) {

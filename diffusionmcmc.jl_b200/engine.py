@@ -144,6 +144,19 @@ class Engine:
         assert X.shape == (self.C, int(self.N[j0:j1].sum()), self.d)
         self._ck(self.lib.dmcmc_upload_segment(self.h, j0, j1, _dp(X)))
 
+    # -- device-side exchange (block sharding over GPUs): raw device pointers, stream-ordered, no host sync --
+    def segment_device(self, j0, j1, dev_ptr, chain_stride, upload):
+        self._ck(self.lib.dmcmc_segment_device(self.h, j0, j1, C.c_void_p(dev_ptr), int(chain_stride), int(upload)))
+
+    def set_start_device(self, dev_ptr, chain_stride):
+        self._ck(self.lib.dmcmc_set_start_device(self.h, C.c_void_p(dev_ptr), int(chain_stride)))
+
+    def stream(self):
+        return int(self.lib.dmcmc_stream(self.h) or 0)
+
+    def impute_async(self, it):
+        self._ck(self.lib.dmcmc_impute_async(self.h, it))
+
     def backward_filter(self, which=0):
         self._ck(self.lib.dmcmc_backward_filter(self.h, which))
 

@@ -109,6 +109,7 @@ class BlockShardedSampler:
         seg = full_path[:, st_off[self.a] + 1:st_off[self.b_ext] + 1, :]
         self.engine.upload_segment(0, self.b_ext - self.a, seg)
         self.lays = local_layouts(self.a, self.b, self.b_ext, self.n, half_len, rank)
+        self.N_left_edge = int(N[self.a - 1]) if self.a > 0 else 0
         self.sweeps = 0
 
     # -- one PathImputation update under pattern `pat` (layout switch fused into the kernel) ---
@@ -120,6 +121,15 @@ class BlockShardedSampler:
         out = e.impute(it)
         self.sweeps += 1
         return out, act
+
+    def sweep_async(self, pat, it):
+        """The same update, enqueued on the engine's stream: nothing comes back to the host."""
+        i1, i2, pin, act = self.lays[pat]
+        e = self.engine
+        e.set_layout(i1, i2, pin)
+        e.set_block_mask(act)
+        e.impute_async(it)
+        self.sweeps += 1
 
     # -- halo messages ------------------------------------------------------------------------
     def pack_for_left(self):
@@ -188,6 +198,83 @@ def take_b(s, comm, C, d):
         steps = int(s.Nloc[:min(s.h, s.b - s.a)].sum())
         s.unpack_from_left(comm.recv((C, 1 + steps, d), s.rank - 1))
     comm.flush()
+
+
+class DeviceHalo:
+    """Device-resident halo exchange of a BlockShardedSampler (GPU only): the packed segments live in
+    CUDA tensors, pack/unpack kernels and the imputation sweeps are enqueued on the engine's stream,
+    and the NCCL send/recv (`batch_isend_irecv`) is ordered on that same stream -- an iteration never
+    synchronises with the host.  Messages are those of `iterate` (module docstring):
+      after sweep A : rank r -> r-1   my first h intervals
+      after sweep B : rank r -> r+1   my last owned interval (its end point is the neighbour's new
+                                       starting point) followed by the halo intervals."""
+
+    def __init__(self, sampler):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.s = torch, dist, sampler
+        s, e = sampler, sampler.engine
+        self.stream = torch.cuda.ExternalStream(e.stream())
+        C, d = e.C, e.d
+        mk = lambda steps: torch.empty((C, int(steps), d), dtype=torch.float64, device="cuda")
+        n_own = s.b - s.a
+        self.h_first = min(s.h, n_own)
+        self.n_first = int(s.Nloc[:self.h_first].sum())            # my first h intervals
+        self.n_halo = int(s.Nloc[n_own:s.b_ext - s.a].sum())       # my halo (the right neighbour's first h)
+        self.n_edge = int(s.Nloc[n_own - 1])                       # my last owned interval
+        self.n_edge_left = int(s.N_left_edge) if s.rank > 0 else 0  # the left neighbour's last owned interval
+        self.to_left = mk(self.n_first) if s.rank > 0 else None
+        self.from_right = mk(self.n_halo) if s.rank < s.world - 1 else None
+        self.to_right = mk(self.n_edge + self.n_halo) if s.rank < s.world - 1 else None
+        self.from_left = mk(self.n_edge_left + self.n_first) if s.rank > 0 else None
+
+    def _exchange(self, send, dst, recv, src):
+        ops = []
+        if send is not None:
+            ops.append(self.dist.P2POp(self.dist.isend, send, dst))
+        if recv is not None:
+            ops.append(self.dist.P2POp(self.dist.irecv, recv, src))
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()  # orders the current (= the engine's) stream after the transfer; the host does not block
+
+    # the four phases of an iteration (tests drive them rank by rank on one device)
+    def sweep_a(self, it):
+        s, e, d = self.s, self.s.engine, self.s.engine.d
+        s.sweep_async(0, 2 * it)
+        if s.rank > 0:
+            e.segment_device(0, self.h_first, self.to_left.data_ptr(), self.n_first * d, 0)
+
+    def take_a(self):
+        s, e, d = self.s, self.s.engine, self.s.engine.d
+        if s.rank < s.world - 1:
+            e.segment_device(s.b - s.a, s.b_ext - s.a, self.from_right.data_ptr(), self.n_halo * d, 1)
+
+    def sweep_b(self, it):
+        s, e, d = self.s, self.s.engine, self.s.engine.d
+        s.sweep_async(1, 2 * it + 1)
+        if s.rank < s.world - 1:
+            e.segment_device(s.b - s.a - 1, s.b_ext - s.a, self.to_right.data_ptr(), (self.n_edge + self.n_halo) * d, 0)
+
+    def take_b(self):
+        s, e, d = self.s, self.s.engine, self.s.engine.d
+        if s.rank > 0:
+            stride = (self.n_edge_left + self.n_first) * d
+            base = self.from_left.data_ptr()
+            e.set_start_device(base + (self.n_edge_left - 1) * d * 8, stride)
+            e.segment_device(0, self.h_first, base + self.n_edge_left * d * 8, stride, 1)
+
+    def iterate(self, it):
+        s = self.s
+        with self.torch.cuda.stream(self.stream):
+            self.sweep_a(it)
+            if s.world > 1:
+                self._exchange(self.to_left, s.rank - 1, self.from_right, s.rank + 1)
+            self.take_a()
+            self.sweep_b(it)
+            if s.world > 1:
+                self._exchange(self.to_right, s.rank + 1, self.from_left, s.rank - 1)
+            self.take_b()
 
 
 class TorchComm:

@@ -170,6 +170,21 @@ int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll);
 /* Device-side accept counters per block since the last call (src/adaptation.jl:100-103). */
 int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted /* [nblk] */, int64_t *proposed);
 
+/* -- device-side exchange for a block-sharded recording ------------------------------
+ * The halo / end-point messages between neighbouring GPUs never have to touch the host: the caller
+ * (NCCL send/recv, or a peer copy) works on DEVICE buffers, ordered on the context's stream.
+ * Element (chain, step, comp) of a segment buffer sits at dev[chain * chain_stride + step * d + comp]. */
+int dmcmc_segment_device(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *dev, int64_t chain_stride,
+                         int32_t upload /* 0: accepted X -> dev, 1: dev -> accepted X */);
+/* Starting points from a device buffer: x0 of (chain, recording r) at dev[chain * chain_stride + r * d + comp]. */
+int dmcmc_set_start_device(dmcmc_ctx *ctx, const double *dev, int64_t chain_stride);
+/* The context's CUDA stream (cudaStream_t), for ordering the caller's collectives with the kernels. */
+void *dmcmc_stream(dmcmc_ctx *ctx);
+/* One PathImputation update with in-register Philox noise under the current layout and block mask:
+ * enqueued, not awaited; ll, selectors and accept counters stay on the device
+ * (dmcmc_get_ll / dmcmc_accept_counts read them later). */
+int dmcmc_impute_async(dmcmc_ctx *ctx, uint32_t iter);
+
 /* -- measurement helpers (bench.py) ----------------------------------------------------------- */
 /* Device time (ms, CUDA events on the context's stream) and launch count of the solve kernels
  * since the previous call, per kernel mode: [0] imputation, [1] parameter-step solve,

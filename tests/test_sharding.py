@@ -155,6 +155,43 @@ def test_block_sharding_gpu_emulated_ranks(pkg):
 
 
 @pytest.mark.gpu
+def test_device_halo_exchange_emulated_ranks(pkg):
+    """The device-resident exchange (packed segments in CUDA tensors, dmcmc_segment_device /
+    dmcmc_set_start_device / dmcmc_impute_async, no host staging): 3 contexts on one device, the
+    NCCL transfer replaced by a device-to-device copy, against the unsharded run, bit for bit."""
+    import torch
+    from diffusionmcmc_jl_b200 import parallel
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = pkg.problems.l63_spec(n_obs=48, C=3, dt=2e-3, rho=0.9)
+    mk = lambda sp, off: Engine(sp, seed=SEED, interval_offset=off)
+    Xref, _ = _reference_run(mk, spec, pkg)
+    world = 3
+    full0 = parallel.initial_full_path(spec, mk)
+    ss = [parallel.BlockShardedSampler(spec, r, world, H, mk, full0) for r in range(world)]
+    hs = [parallel.DeviceHalo(s) for s in ss]
+    for it in range(ITERS):
+        for h in hs:
+            h.sweep_a(it)
+        torch.cuda.synchronize()
+        for r in range(world - 1):
+            hs[r].from_right.copy_(hs[r + 1].to_left)
+        torch.cuda.synchronize()
+        for h in hs:
+            h.take_a()
+            h.sweep_b(it)
+        torch.cuda.synchronize()
+        for r in range(1, world):
+            hs[r].from_left.copy_(hs[r - 1].to_right)
+        torch.cuda.synchronize()
+        for h in hs:
+            h.take_b()
+    X = np.concatenate([s.owned_path() for s in ss], axis=1)
+    assert np.array_equal(X, Xref), np.abs(X - Xref).max()
+    for s in ss:
+        s.engine.close()
+
+
+@pytest.mark.gpu
 def test_chain_sharding_gpu(pkg):
     from diffusionmcmc_jl_b200 import parallel
     from diffusionmcmc_jl_b200.engine import Engine
