@@ -181,6 +181,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # rank 0 prints exactly one line: no NCCL version banner on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     pkg, spec = make_spec(N_CHAINS)

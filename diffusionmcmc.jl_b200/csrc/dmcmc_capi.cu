@@ -2,6 +2,7 @@
 // Host-side logic only; the arithmetic of the hot path is in dmcmc_solve.cu / dmcmc_bf.cu.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1094,7 +1095,7 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
         for (int i = 0; i < R; ++i) {
             CK(cudaEventCreateWithFlags(&io.kernel_done[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&io.rho_ready[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&io.copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&io.copied[i], cudaEventDisableTiming | cudaEventBlockingSync));
         }
     }
     // drainers: pinned ring -> caller's arrays.  One core copies ~10 GB/s, which is just the rate the C3
@@ -1110,9 +1111,9 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             drainer[t] = std::thread([&, t]() {
                 cudaSetDevice(ctx->cfg.device);
                 for (int it = t; it < n_sweeps; it += NDRAIN) {
-                    while (recorded.load(std::memory_order_acquire) <= it) {
-                        if (failed.load(std::memory_order_relaxed)) return;
-                        std::this_thread::yield();
+                    while (recorded.load(std::memory_order_acquire) <= it) {  // sleep, do not spin: one process per GPU
+                        if (failed.load(std::memory_order_relaxed)) return;  // shares the host cores with 7 others
+                        std::this_thread::sleep_for(std::chrono::microseconds(20));
                     }
                     const int slot = it % R;
                     if (cudaEventSynchronize(io.copied[slot]) != cudaSuccess) { failed = true; return; }
@@ -1134,7 +1135,7 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
                 const int prev = it - R;  // the sweep that used this slot before
                 while (prev >= 0 && drained[prev % NDRAIN].load(std::memory_order_acquire) < prev / NDRAIN + 1) {
                     if (failed.load(std::memory_order_relaxed)) return fail(ctx, "dmcmc_run_sweeps: history copy failed");
-                    std::this_thread::yield();
+                    std::this_thread::sleep_for(std::chrono::microseconds(20));
                 }
             }
             if (rho_sched) {  // this sweep's pCN memory: caller -> pinned ring -> device ring, on the copy-in stream
