@@ -18,7 +18,7 @@ class Config(C.Structure):
                 ("seed", C.c_uint64), ("pin_eps", C.c_double), ("store_noise", C.c_int32)]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); every symbol include/dmcmc.h declares
 SYMBOLS = {

@@ -527,12 +527,12 @@ __global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
             auto eight = [&](auto check_tag, int half) {
                 constexpr bool CHECK = decltype(check_tag)::value;
                 const int kh = tl * TS + half * TILE;
-                const size_t wtile = wtile0 + (size_t)(kh >> 3);
+                [[maybe_unused]] const size_t wtile = wtile0 + (size_t)(kh >> 3);
                 const double *hrec = srec + (size_t)half * TILE * RS;
                 const uint32_t hst = IS::cursor(sst, lane);
-                double *xph = Xp + (size_t)kh * D;
-                double dwo[STORE_W_MODE ? M : 1][TILE];
-                ZT z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
+                [[maybe_unused]] double *xph = Xp + (size_t)kh * D;
+                [[maybe_unused]] double dwo[STORE_W_MODE ? M : 1][TILE];
+                [[maybe_unused]] ZT z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
                 if constexpr (MODE == MODE_IMPUTE) {
                     if constexpr (PHILOX) {
 #pragma unroll

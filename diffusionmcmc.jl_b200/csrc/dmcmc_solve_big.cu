@@ -1,30 +1,24 @@
 // dmcmc_solve_big.cu -- the imputation hot path for large state dimension (Lorenz-96, d = 40).
 //
-// One WARP owns one (chain, block) unit; lanes own state components (lane l: components l and
-// l+32).  The per-step work is three dense mat-vecs (Psi x_b, H x, and H x_acc when the accepted
-// noise is recovered on the fly), each a loop over columns k in which every lane accumulates its
-// rows -- H and Psi' are read column-contiguous (coalesced, and shared through L1/L2 by the warps
-// of the CTA, which all work on the same block), the state vector is broadcast from shared
-// memory.  Log-likelihood terms are accumulated per lane and reduced with warp shuffles once per
-// block; the accept decision is taken by lane 0 and broadcast.  The path record of one
-// (tile, chain) is 40 x 64 contiguous bytes, read and written by the warp as a whole.
+// One WARP owns four (chain, block) units of the same layout block: lane l works for chain l / 8 and
+// owns the five state components g, g+8, .., g+32 (g = l % 8), so the warp's 160 rows sit on 32
+// lanes with none idle.  The per-step work is three dense 40 x 40 mat-vecs (H x, H x_acc when the
+// accepted noise is recovered on the fly, Psi' x_b), done as one sweep over the columns in which
+// every H / Psi' element read from shared memory serves the four chains (multicast LDS).  The CTA
+// (1-8 warps, all on the same block) walks the Euler steps in lockstep: the step's table record
+// (H, F0, Psi': 26 KB) is brought into shared memory ONCE per CTA by a TMA bulk copy, double-buffered
+// one step ahead.  Path I/O is per step and coalesced (a chain's state is 320 contiguous bytes).
+// Log-likelihood terms are accumulated per lane and reduced over the chain's eight lanes once per
+// block.  Bound: FP64 pipe (3 x 1600 FMA per chain and step); shared-memory bandwidth was the limit
+// of the first mapping (one chain per warp, 11 wavefronts per chain and column; now 3.3).
 //
 // Same rows of SURVEY.md section 8a as dmcmc_solve.cu (a1-a7, a9, layout switch, init_ll).
 #include <cmath>
-#include <cstdlib>
 
 #include "dmcmc_device.cuh"
 #include "dmcmc_internal.h"
 
 namespace dmcmc {
-
-constexpr int BIG_WARPS = 16;  // warps (= chains) per CTA; all of them work on the same layout block
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 __device__ __forceinline__ uint32_t smem_u32b(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init_b(uint64_t *b, uint32_t count) {
@@ -55,335 +49,6 @@ __device__ __forceinline__ double l96_aux_drift(const double *x, int i, double F
     return ((-x[i]) + c * x[ip] + (-c) * x[im2]) + F;  // B = -I + c (S_{+1} - S_{-2}), beta = F
 }
 
-// One CTA = one layout block x BIG_WARPS chains, one warp = one (chain, block) unit, lanes = state
-// components.  The CTA walks the block's Euler steps in lockstep: the step's table record
-// (H, F0, Psi': 26 KB for d = 40) is brought into shared memory ONCE per CTA by a TMA bulk copy,
-// double-buffered one step ahead, and read by every warp as conflict-free LDS.
-template <int D, bool PSI, int MODE, bool PHILOX, bool REINV>
-__global__ void __launch_bounds__(BIG_WARPS * 32) solve_big_kernel(const SolveParams p) {
-    constexpr int NS = (D + 31) / 32;
-    constexpr int REC = rec_size_big(D, PSI);
-    constexpr int OFF_H = 2, OFF_F = 2 + D * D, OFF_PSI = 2 + D * D + D;
-    constexpr bool SOLVE = (MODE == MODE_IMPUTE || MODE == MODE_PARAM);
-    constexpr bool NEED_XA = !SOLVE || REINV;
-    constexpr bool NEED_WA = SOLVE && !REINV;
-    extern __shared__ __align__(128) double dsm[];
-    double *stage0 = dsm, *stage1 = dsm + REC;
-    double *vecs = dsm + 2 * REC;  // [BIG_WARPS][3][D]
-    __shared__ __align__(8) uint64_t full[2];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int groups = (p.C + BIG_WARPS - 1) / BIG_WARPS;
-    const int blk = (int)(blockIdx.x / groups);
-    const int chain_raw = (int)(blockIdx.x % groups) * BIG_WARPS + warp;
-    const bool in_range = chain_raw < p.C;
-    const int chain = in_range ? chain_raw : p.C - 1;  // surplus warps shadow the last chain (stores off)
-    const size_t uo = (size_t)chain * p.nblk + blk;
-    const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
-    const bool masked = (MODE == MODE_IMPUTE) &&
-                        ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
-    const bool active = in_range && !masked;
-    double *xs = vecs + (size_t)warp * 3 * D, *xas = xs + D, *xbs = xas + D;
-    int idx[NS];
-    bool has[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) { idx[s] = lane + 32 * s; has[s] = idx[s] < D; }
-
-    const double Fth = p.th.v[0], sig = p.th.v[1], caux = p.th.v[2];
-    const double sig2 = sig * sig, isig = 1.0 / sig;
-    const bool fast_aux = p.fast_ok != 0;
-    const bool pinned = PSI && p.blk_pinned[blk];
-    const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
-
-    if (threadIdx.x == 0) {
-        mbar_init_b(&full[0], 1);
-        mbar_init_b(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](size_t step_index, int q) {  // thread 0: stage the record of one Euler step
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx_b(&full[q & 1], (uint32_t)(REC * sizeof(double)));
-        bulk_g2s_b((q & 1) ? stage1 : stage0, p.table + step_index * REC, (uint32_t)(REC * sizeof(double)), &full[q & 1]);
-    };
-    if (threadIdx.x == 0) issue((size_t)p.iv_tile_off[i1] * TILE, 0);
-
-    // ---- start point and pinned end point -----------------------------------------------------
-    auto end_value = [&](int j, int c) {
-        const int s = p.selX_in[(size_t)j * p.C + chain];
-        const int k = p.iv_N[j] - 1;
-        return p.X[s][p.iv_xoff[j] + (size_t)chain * p.iv_xs[j] + (size_t)k * D + c];
-    };
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-        if (has[s]) {
-            const int c = idx[s];
-            const double v = p.iv_first[i1] ? p.x0[((size_t)p.iv_rec[i1] * D + c) * p.C + chain] : end_value(i1 - 1, c);
-            xs[c] = v;
-            xas[c] = v;
-            xbs[c] = pinned ? end_value(i2, c) : 0.0;
-        }
-    __syncwarp();
-
-    double llp = 0.0, lla = 0.0;
-    double lsum = 0.0, lsum_a = 0.0;  // per-lane partial sums of the Girsanov integrals
-    int q = 0;                        // Euler steps staged so far (pipeline position)
-
-    for (int j = i1; j <= i2; ++j) {
-        const int N = p.iv_N[j];
-        const size_t toff = (size_t)p.iv_tile_off[j];
-        const int nt = (N + TILE - 1) >> 3;
-        const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
-        const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
-        const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
-        const double *Wa = p.W[sw];
-        double *Wp = p.W[1 - sw];
-        // this chain's accepted / proposal record of the interval: [step][component], lanes = components
-        const double *Xa = p.X[sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];
-        double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];
-        const double *aB = p.auxB + (size_t)j * D * D, *abeta = p.auxbeta + (size_t)j * D;
-
-        for (int tl = 0; tl < nt; ++tl) {
-            const size_t tile = toff + tl;
-            double cur[NS][TILE], z[NS][TILE], xo[NS][TILE], dwo[NS][TILE];
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-                if (has[s]) {
-                    if constexpr (NEED_XA) {
-#pragma unroll
-                        for (int st = 0; st < TILE; ++st) {
-                            const int k = tl * TILE + st;
-                            cur[s][st] = (k < N) ? Xa[(size_t)k * D + idx[s]] : 0.0;
-                        }
-                    }
-                    if constexpr (NEED_WA) ld_tile(Wa + w_off(tile, chain, idx[s], p.C, D), cur[s]);
-                    if constexpr (MODE == MODE_IMPUTE) {
-                        if constexpr (PHILOX) {
-#pragma unroll
-                            for (int h = 0; h < TILE / 4; ++h)
-                                philox_normal4(p.seed, p.iter, (uint32_t)(j + p.interval_offset), gchain,
-                                               (uint32_t)idx[s], (uint32_t)(tl * (TILE / 4) + h), &z[s][4 * h]);
-                        } else {
-                            ld_tile_stream(p.Z + w_off(tile, chain, idx[s], p.C, D), z[s]);
-                        }
-                    }
-                }
-            const int nlive = min(TILE, N - tl * TILE);
-#pragma unroll
-            for (int st = 0; st < TILE; ++st) {
-                double dw[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) dw[s] = 0.0;
-                if (st < nlive) {  // CTA-uniform
-                    // ---- pipeline: everyone is done with the other stage, refill it one step ahead ----
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        if (st + 1 < nlive) issue((tile * TILE) + st + 1, q + 1);
-                        else if (tl + 1 < nt) issue((tile + 1) * TILE, q + 1);
-                        else if (j + 1 <= i2) issue((size_t)p.iv_tile_off[j + 1] * TILE, q + 1);
-                    }
-                    mbar_wait_b(&full[q & 1], (uint32_t)((q >> 1) & 1));
-                    const double *rec = (q & 1) ? stage1 : stage0;
-                    ++q;
-                    if (q == 1) {
-                        // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point
-                        double part = 0.0;
-#pragma unroll
-                        for (int s = 0; s < NS; ++s)
-                            if (has[s]) {
-                                const int c = idx[s];
-                                double hx = 0.0, px = 0.0, qx = 0.0;
-                                for (int k = 0; k < D; ++k) {
-                                    hx += rec[OFF_H + k * D + c] * xs[k];
-                                    if (PSI) px += rec[OFF_PSI + k * D + c] * xbs[k];
-                                    if (pinned) qx += p.blk_Qc[(size_t)blk * D * D + (size_t)k * D + c] * xbs[k];
-                                }
-                                double f = rec[OFF_F + c];
-                                if (PSI) f += px;
-                                part += f * xs[c] - 0.5 * xs[c] * hx;
-                                if (pinned) part -= p.blk_g[(size_t)blk * D + c] * xbs[c] + 0.5 * xbs[c] * qx;
-                            }
-                        llp = warp_sum(part) - p.blk_c0[blk];
-                        lla = llp;
-                    }
-                    const double dt = rec[0], sq = rec[1];
-                    // the three mat-vecs share one sweep over the columns (LDS, conflict-free rows)
-                    double Hx[NS], Hxa[NS], Px[NS];
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) { Hx[s] = 0.0; Hxa[s] = 0.0; Px[s] = 0.0; }
-#pragma unroll 8
-                    for (int k = 0; k < D; ++k) {
-                        const double xk = xs[k], xak = xas[k], xbk = xbs[k];
-#pragma unroll
-                        for (int s = 0; s < NS; ++s)
-                            if (has[s]) {
-                                const double h = rec[OFF_H + k * D + idx[s]];
-                                if (SOLVE) Hx[s] += h * xk;
-                                if (NEED_XA) Hxa[s] += h * xak;
-                                if (PSI) Px[s] += rec[OFF_PSI + k * D + idx[s]] * xbk;
-                            }
-                    }
-                    double xnew[NS];
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) xnew[s] = 0.0;
-#pragma unroll
-                    for (int s = 0; s < NS; ++s)
-                        if (has[s]) {
-                            const int c = idx[s];
-                            double F = rec[OFF_F + c];
-                            if (PSI) F += Px[s];
-                            if constexpr (NEED_XA) {  // recover the accepted noise increment
-                                const double r = F - Hxa[s];
-                                const double b = l96_drift<D>(xas, c, Fth);
-                                double bt;
-                                if (fast_aux) bt = l96_aux_drift<D>(xas, c, Fth, caux);
-                                else {
-                                    double a = 0.0;
-                                    for (int k = 0; k < D; ++k) a += aB[(size_t)c * D + k] * xas[k];
-                                    bt = a + abeta[c];
-                                }
-                                lsum_a += ((b - bt) * r) * dt;
-                                const double res = cur[s][st] - xas[c] - (b + sig2 * r) * dt;
-                                dw[s] = res * isig;
-                            } else if constexpr (NEED_WA) {
-                                dw[s] = cur[s][st];
-                            }
-                            if constexpr (MODE == MODE_IMPUTE) dw[s] = lam * (sq * z[s][st]) + rho * dw[s];
-                            if constexpr (SOLVE) {
-                                const double r = F - Hx[s];
-                                const double b = l96_drift<D>(xs, c, Fth);
-                                double bt;
-                                if (fast_aux) bt = l96_aux_drift<D>(xs, c, Fth, caux);
-                                else {
-                                    double a = 0.0;
-                                    for (int k = 0; k < D; ++k) a += aB[(size_t)c * D + k] * xs[k];
-                                    bt = a + abeta[c];
-                                }
-                                lsum += ((b - bt) * r) * dt;
-                                xnew[s] = xs[c] + (b + sig2 * r) * dt + sig * dw[s];
-                            }
-                        }
-                    __syncwarp();  // everyone has read the old state
-#pragma unroll
-                    for (int s = 0; s < NS; ++s)
-                        if (has[s]) {
-                            if constexpr (SOLVE) xs[idx[s]] = xnew[s];
-                            if constexpr (NEED_XA) xas[idx[s]] = cur[s][st];
-                        }
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    dwo[s][st] = dw[s];
-                    if (SOLVE && has[s]) xo[s][st] = xs[idx[s]];
-                }
-            }
-            if (active) {
-#pragma unroll
-                for (int s = 0; s < NS; ++s)
-                    if (has[s]) {
-                        if constexpr (SOLVE) {
-                            if (pinned && j == i2 && tl == nt - 1) {
-                                const int last = (N - 1) & 7;
-#pragma unroll
-                                for (int st = 0; st < TILE; ++st) xo[s][st] = (st == last) ? xbs[idx[s]] : xo[s][st];
-                            }
-#pragma unroll
-                            for (int st = 0; st < TILE; ++st)
-                                if (st < nlive) Xp[(size_t)(tl * TILE + st) * D + idx[s]] = xo[s][st];
-                        }
-                        if ((MODE == MODE_IMPUTE && p.store_w) || MODE == MODE_RELAYOUT) {
-                            double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : Wp;
-                            st_tile(Wdst + w_off(tile, chain, idx[s], p.C, D), dwo[s]);
-                        }
-                    }
-            }
-        }
-    }
-    llp += warp_sum(lsum);
-    lla += warp_sum(lsum_a);
-    if (!in_range) return;
-
-    if constexpr (MODE == MODE_IMPUTE) {
-        if (masked) {
-            for (int j = i1 + lane; j <= i2; j += 32) {
-                const size_t o = (size_t)j * p.C + chain;
-                p.selX_out[o] = p.selX_in[o];
-                p.selW_out[o] = p.selW_in[o];
-            }
-            if (lane == 0 && p.blk_active && !p.blk_active[blk]) {
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = nan;
-                if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = nan;
-                if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = 0;
-            }
-            return;
-        }
-        double llcur = REINV ? lla : p.ll[uo];
-        const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain) : p.E[uo];
-        const bool ok = isfinite(llp);
-        const bool acc = p.force_accept ? ok : (e > -(llp - llcur));  // identical on every lane
-        for (int j = i1 + lane; j <= i2; j += 32) {
-            const size_t o = (size_t)j * p.C + chain;
-            p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
-            p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && p.store_w);
-        }
-        if (lane == 0) {
-            if (acc) {
-                llcur = llp;
-                if (p.acc_count) atomicAdd(p.acc_count + blk, 1ULL);
-            }
-            p.ll[uo] = llcur;
-            if (p.prop_count && chain == 0) atomicAdd(p.prop_count + blk, (unsigned long long)p.C);
-            if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = llp;
-            if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = llcur;
-            if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = (uint8_t)acc;
-        }
-    } else if constexpr (MODE == MODE_PARAM) {
-        if (lane == 0) {
-            if (p.out_llprop) p.out_llprop[uo] = llp;
-            if (p.out_acc) p.out_acc[uo] = (uint8_t)isfinite(llp);
-        }
-    } else {
-        if (lane == 0) p.ll[uo] = lla;
-    }
-}
-
-template <int D, bool PSI>
-static cudaError_t launch_big_model(int mode, const SolveParams &p, cudaStream_t s) {
-    if ((long long)p.nblk * p.C == 0) return cudaSuccess;
-    const unsigned groups = (unsigned)((p.C + BIG_WARPS - 1) / BIG_WARPS);
-    const unsigned grid = groups * (unsigned)p.nblk;
-    const unsigned threads = BIG_WARPS * 32;
-    const size_t smem = (size_t)(2 * rec_size_big(D, PSI) + BIG_WARPS * 3 * D) * sizeof(double);
-    const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
-#define DMCMC_LAUNCH(MODE_, PH_, RE_)                                                                      \
-    do {                                                                                                   \
-        cudaError_t e_ = cudaFuncSetAttribute(solve_big_kernel<D, PSI, MODE_, PH_, RE_>,                    \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        if (e_ != cudaSuccess) return e_;                                                                  \
-        solve_big_kernel<D, PSI, MODE_, PH_, RE_><<<grid, threads, smem, s>>>(p);                          \
-    } while (0)
-    switch (mode) {
-    case MODE_IMPUTE:
-        if (philox) { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, true, true); else DMCMC_LAUNCH(MODE_IMPUTE, true, false); }
-        else        { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, false, true); else DMCMC_LAUNCH(MODE_IMPUTE, false, false); }
-        break;
-    case MODE_PARAM: DMCMC_LAUNCH(MODE_PARAM, false, false); break;
-    case MODE_RELAYOUT: DMCMC_LAUNCH(MODE_RELAYOUT, false, false); break;
-    case MODE_LOGLIK: DMCMC_LAUNCH(MODE_LOGLIK, false, false); break;
-    default: return cudaErrorInvalidValue;
-    }
-#undef DMCMC_LAUNCH
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// v2 mapping: one WARP owns CH = 4 (chain, block) units of the same block; lane l works for chain
-// l / 8 and owns the five state components g, g+8, .., g+32 (g = l % 8) -- all 32 lanes carry 5 of
-// the warp's 160 rows, so the FP64 pipe sees no idle lanes (40 rows over 32 lanes left 37.5 % idle),
-// and every H / Psi' element read from shared memory is used by four chains (multicast LDS).
-// ---------------------------------------------------------------------------------------------
 constexpr int CH = 4;         // chains per warp
 constexpr int RPL = 5;        // rows (state components) per lane: D / 8
 
@@ -395,7 +60,7 @@ __device__ __forceinline__ double group_sum(double v) {  // over the 8 lanes of 
 }
 
 template <int D, bool PSI, int MODE, bool PHILOX, bool REINV>
-__global__ void __launch_bounds__(256, 2) solve_big2_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(256, 2) solve_big_kernel(const SolveParams p) {
     static_assert(D == 8 * RPL, "five rows per lane");
     constexpr int REC = rec_size_big(D, PSI);
     constexpr int OFF_H = 2, OFF_F = 2 + D * D, OFF_PSI = 2 + D * D + D;
@@ -667,7 +332,7 @@ __global__ void __launch_bounds__(256, 2) solve_big2_kernel(const SolveParams p)
 }
 
 template <int D, bool PSI>
-static cudaError_t launch_big2_model(int mode, const SolveParams &p, cudaStream_t s) {
+static cudaError_t launch_big_model(int mode, const SolveParams &p, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
     // warps per CTA: as many chains per CTA as possible (the per-step table record is staged once per
     // CTA) while the grid still fills the machine twice over
@@ -679,32 +344,30 @@ static cudaError_t launch_big2_model(int mode, const SolveParams &p, cudaStream_
     const unsigned threads = warps * 32;
     const size_t smem = (size_t)(2 * rec_size_big(D, PSI) + warps * CH * 3 * D) * sizeof(double);
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
-#define DMCMC_LAUNCH2(MODE_, PH_, RE_)                                                                     \
+#define DMCMC_LAUNCH(MODE_, PH_, RE_)                                                                     \
     do {                                                                                                   \
-        cudaError_t e_ = cudaFuncSetAttribute(solve_big2_kernel<D, PSI, MODE_, PH_, RE_>,                   \
+        cudaError_t e_ = cudaFuncSetAttribute(solve_big_kernel<D, PSI, MODE_, PH_, RE_>,                   \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);    \
         if (e_ != cudaSuccess) return e_;                                                                  \
-        solve_big2_kernel<D, PSI, MODE_, PH_, RE_><<<grid, threads, smem, s>>>(p);                         \
+        solve_big_kernel<D, PSI, MODE_, PH_, RE_><<<grid, threads, smem, s>>>(p);                         \
     } while (0)
     switch (mode) {
     case MODE_IMPUTE:
-        if (philox) { if (reinv) DMCMC_LAUNCH2(MODE_IMPUTE, true, true); else DMCMC_LAUNCH2(MODE_IMPUTE, true, false); }
-        else        { if (reinv) DMCMC_LAUNCH2(MODE_IMPUTE, false, true); else DMCMC_LAUNCH2(MODE_IMPUTE, false, false); }
+        if (philox) { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, true, true); else DMCMC_LAUNCH(MODE_IMPUTE, true, false); }
+        else        { if (reinv) DMCMC_LAUNCH(MODE_IMPUTE, false, true); else DMCMC_LAUNCH(MODE_IMPUTE, false, false); }
         break;
-    case MODE_PARAM: DMCMC_LAUNCH2(MODE_PARAM, false, false); break;
-    case MODE_RELAYOUT: DMCMC_LAUNCH2(MODE_RELAYOUT, false, false); break;
-    case MODE_LOGLIK: DMCMC_LAUNCH2(MODE_LOGLIK, false, false); break;
+    case MODE_PARAM: DMCMC_LAUNCH(MODE_PARAM, false, false); break;
+    case MODE_RELAYOUT: DMCMC_LAUNCH(MODE_RELAYOUT, false, false); break;
+    case MODE_LOGLIK: DMCMC_LAUNCH(MODE_LOGLIK, false, false); break;
     default: return cudaErrorInvalidValue;
     }
-#undef DMCMC_LAUNCH2
+#undef DMCMC_LAUNCH
     return cudaGetLastError();
 }
 
 cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s) {
     if (d != 40) return cudaErrorInvalidValue;
-    static const bool v1 = getenv("DMCMC_L96_V1") != nullptr;  // previous mapping (one chain per warp), kept for A/B runs
-    if (v1) return p.has_psi ? launch_big_model<40, true>(mode, p, s) : launch_big_model<40, false>(mode, p, s);
-    return p.has_psi ? launch_big2_model<40, true>(mode, p, s) : launch_big2_model<40, false>(mode, p, s);
+    return p.has_psi ? launch_big_model<40, true>(mode, p, s) : launch_big_model<40, false>(mode, p, s);
 }
 
 }  // namespace dmcmc

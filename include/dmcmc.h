@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMCMC_ABI_VERSION 3
+#define DMCMC_ABI_VERSION 4
 
 /* Built-in diffusion laws (DiffusionDefinition.jl `@load_diffusion`, src/DiffusionMCMC.jl:4). */
 enum dmcmc_model {

@@ -13,7 +13,7 @@ const eMCMC = ExtensibleMCMC
 const OBS = ObservationSchemes
 
 const LIB = get(ENV, "DMCMC_B200_LIB", "libdmcmc_b200.so")
-const ABI_VERSION = Int32(3)
+const ABI_VERSION = Int32(4)
 
 struct Config
     abi_version::Int32; model::Int32; d::Int32; n_chains::Int32
