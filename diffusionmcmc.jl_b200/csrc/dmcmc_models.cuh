@@ -34,7 +34,7 @@ struct ModelFHN {
     static constexpr int D = 2, M = 1, NTH = 5;
     static constexpr bool CONST_SIGMA = true;
     __host__ __device__ static __forceinline__ void drift(const Theta &th, const double *x, double *b) {
-        b[0] = (x[0] - x[0] * x[0] * x[0] - x[1] + th.v[1]) / th.v[0];
+        b[0] = (x[0] - x[0] * x[0] * x[0] - x[1] + th.v[1]) * (1.0 / th.v[0]);
         b[1] = th.v[2] * x[0] - x[1] + th.v[3];
     }
     // out = sigma(x) * w          (w has M entries)
@@ -49,7 +49,7 @@ struct ModelFHN {
     }
     // least-squares noise recovery: w = argmin |sigma w - res|
     __host__ __device__ static __forceinline__ void sigma_solve(const Theta &th, const double *, const double *res, double *w) {
-        w[0] = res[1] / th.v[4];
+        w[0] = res[1] * (1.0 / th.v[4]);  // loop-invariant reciprocal: no FP64 division (and its branches) per step
     }
     __host__ __device__ static __forceinline__ void a_full(const Theta &th, const double *, double *a) {
         a[0] = a[1] = a[2] = 0.0;
@@ -86,8 +86,8 @@ struct ModelLVT {
     __host__ __device__ static __forceinline__ void sigma_solve(const Theta &th, const double *x, const double *res, double *w) {
         double s[2];
         sig(th, x, s);
-        w[0] = res[0] / s[0];
-        w[1] = res[1] / s[1];
+        w[0] = res[0] * (1.0 / s[0]);
+        w[1] = res[1] * (1.0 / s[1]);
     }
     __host__ __device__ static __forceinline__ void a_full(const Theta &th, const double *x, double *a) {
         double s[2];
@@ -117,7 +117,8 @@ struct ModelL63 {
         for (int i = 0; i < 3; ++i) out[i] = th.v[3] * th.v[3] * r[i];
     }
     __host__ __device__ static __forceinline__ void sigma_solve(const Theta &th, const double *, const double *res, double *w) {
-        for (int i = 0; i < 3; ++i) w[i] = res[i] / th.v[3];
+        const double is = 1.0 / th.v[3];
+        for (int i = 0; i < 3; ++i) w[i] = res[i] * is;
     }
     __host__ __device__ static __forceinline__ void a_full(const Theta &th, const double *, double *a) {
         for (int i = 0; i < 9; ++i) a[i] = 0.0;
@@ -143,8 +144,8 @@ struct ModelLIN2 {
         out[1] = th.v[7] * th.v[7] * r[1];
     }
     __host__ __device__ static __forceinline__ void sigma_solve(const Theta &th, const double *, const double *res, double *w) {
-        w[0] = res[0] / th.v[6];
-        w[1] = res[1] / th.v[7];
+        w[0] = res[0] * (1.0 / th.v[6]);
+        w[1] = res[1] * (1.0 / th.v[7]);
     }
     __host__ __device__ static __forceinline__ void a_full(const Theta &th, const double *, double *a) {
         a[0] = th.v[6] * th.v[6];

@@ -278,7 +278,7 @@ __device__ __forceinline__ void cp_async_wait_depth(int depth) {  // allow depth
 // p.depth (2, 4 or 8) = tiles in flight of the table and input pipelines: 2 when the grid fills the
 // machine (latency is hidden by the other warps), deeper when a few long units run alone.
 template <class MD, bool PSI, int MODE, bool PHILOX, bool REINV, bool FAST>
-__global__ void __launch_bounds__(128, 3) solve_kernel(const SolveParams p) {
+__global__ void __launch_bounds__(128, MD::D == 2 ? 3 : 2) solve_kernel(const SolveParams p) {
     constexpr int D = MD::D, M = MD::M;
     using R = Rec<D, PSI>;
     constexpr int RS = R::SIZE;
