@@ -16,7 +16,7 @@ from .schedule import MCMCSchedule, Step, extra_transitions, init_block_layout  
 
 def __getattr__(name):
     # backend/engine bind the CUDA library lazily so that host-only logic imports without it
-    if name in ("DiffusionMCMCBackend", "PathImputation", "RandomWalkUpdate", "MCMC", "run_",
+    if name in ("DiffusionMCMCBackend", "PathImputation", "RandomWalkUpdate", "DiffusionConjugGsnUpdate", "MCMC", "run_",
                 "ImputationRunner", "DiffusionGlobalWorkspace", "DiffusionLocalWorkspace"):
         from . import backend
         return getattr(backend, name)

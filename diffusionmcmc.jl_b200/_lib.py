@@ -55,6 +55,8 @@ SYMBOLS = {
     "dmcmc_set_start_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "dmcmc_stream": (C.c_void_p, [C.c_void_p]),
     "dmcmc_impute_async": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "dmcmc_conjugate_dim": (C.c_int32, [C.c_void_p, _ip]),
+    "dmcmc_conjugate_sums": (C.c_int, [C.c_void_p, _dp, _dp]),
     "dmcmc_n_blocks": (C.c_int32, [C.c_void_p]),
     "dmcmc_get_ll": (C.c_int, [C.c_void_p, _dp]),
     "dmcmc_set_ll": (C.c_int, [C.c_void_p, _dp]),

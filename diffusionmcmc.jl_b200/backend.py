@@ -88,6 +88,43 @@ class RandomWalkUpdate:
         return 0.0
 
 
+class DiffusionConjugGsnUpdate:
+    """src/updates.jl:83-105: conjugate Gaussian update of the parameters `coords` (theta indices)
+    with prior N(prior_mu, prior_Sigma).  The path integrals mu, W (compute_mu_and_W, :241-262) are
+    reduced on the device (dmcmc_conjugate_sums); the posterior
+        Sigma = (W + prior_Sigma^-1)^-1,  mean = Sigma (mu + prior_Sigma^-1 prior_mu)   (:270-273)
+    and the draw stay on the host.  Chains are conditionally independent copies of the recording, so
+    their integrals add (like the reference's loop over recordings, :232-246)."""
+
+    def __init__(self, coords, prior_mu, prior_Sigma):
+        self.coords = list(np.atleast_1d(coords))
+        self.prior_mu = np.atleast_1d(np.asarray(prior_mu, float))
+        self.prior_Sigma = np.atleast_2d(np.asarray(prior_Sigma, float))
+        self.adpt = NoAdaptation()
+        self.critical = True
+
+    def posterior(self, engine, theta):
+        idx = list(engine.conjugate_coords())
+        if not set(self.coords) <= set(idx):
+            raise ValueError(f"parameters {self.coords} are not conjugate for this law (conjugate: {idx})")
+        mu, W = engine.conjugate_sums()
+        mu, W = mu.sum(axis=0), W.sum(axis=0)
+        S = [idx.index(c) for c in self.coords]
+        F = [k for k in range(len(idx)) if k not in S]
+        th = np.asarray(theta, float)
+        mu_S = mu[S] - W[np.ix_(S, F)] @ th[[idx[k] for k in F]]  # fixed members of the family enter phi_c
+        P0 = np.linalg.inv(self.prior_Sigma)
+        Sigma = np.linalg.inv(W[np.ix_(S, S)] + P0)
+        Sigma = 0.5 * (Sigma + Sigma.T)
+        return Sigma @ (mu_S + P0 @ self.prior_mu), Sigma
+
+    def proposal(self, engine, theta, rng):
+        m, Sigma = self.posterior(engine, theta)
+        th = np.array(theta, float)
+        th[self.coords] = rng.multivariate_normal(m, Sigma)
+        return th
+
+
 class MCMC:
     """eMCMC.MCMC(updates_and_decorators; backend) (docs/src/get_started/overview.md:72-82)."""
 
@@ -277,6 +314,16 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
             adapt(u, lay, mcmciter)
             if mcmciter % save_every == 0 and step.pidx == 1:   # save_path!, src/run!_alterations.jl:51-54
                 save_paths()
+        elif isinstance(u, DiffusionConjugGsnUpdate):
+            th_prop = u.proposal(eng, theta, rng)                              # proposal!: conjugate_draw, src/updates.jl:225-246
+            llp, ok = eng.param_loglik(th_prop, critical=True)                 # set_proposal! + compute_ll! (fixed W)
+            accepted = bool(ok.all())                                          # conjugate draws are always accepted
+            eng.param_commit(accepted)
+            if accepted:
+                theta = th_prop
+            w._llp[mcmciter - 1, :, 0] = llp.sum(axis=1)
+            w._ll[mcmciter - 1, :, 0] = llp.sum(axis=1) if accepted else eng.get_ll().sum(axis=1)
+            w._acc[mcmciter - 1, :, 0] = accepted
         else:
             th_prop = u.proposal(theta, rng)                                   # proposal!
             llp, ok = eng.param_loglik(th_prop, critical=u.critical)           # set_proposal!

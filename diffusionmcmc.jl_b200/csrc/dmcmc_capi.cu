@@ -1409,6 +1409,43 @@ extern "C" int dmcmc_set_fast_step(dmcmc_ctx *ctx, int32_t on) {
     return 0;
 }
 
+extern "C" int32_t dmcmc_conjugate_dim(const dmcmc_ctx *ctx, int32_t *theta_idx) {
+    return ctx ? conjugate_dim(ctx->cfg.model, theta_idx) : -1;
+}
+
+// mu [C][nc] and W [C][nc][nc] of the conjugate Gaussian update over the accepted path under the
+// current law (compute_mu_and_W, src/updates.jl:241-262); nc = dmcmc_conjugate_dim
+extern "C" int dmcmc_conjugate_sums(dmcmc_ctx *ctx, double *mu, double *W) {
+    REQUIRE(ctx && mu && W, "dmcmc_conjugate_sums: bad argument");
+    REQUIRE(ctx->have_grid && ctx->have_start, "dmcmc_conjugate_sums: context not initialised");
+    const int nc = conjugate_dim(ctx->cfg.model, nullptr);
+    REQUIRE(nc > 0, "dmcmc_conjugate_sums: this law has no conjugate parameters implemented");
+    CK(cudaSetDevice(ctx->cfg.device));
+    const int nout = nc + nc * nc;
+    DevBuf<double> partial, out;
+    CK(partial.ensure((size_t)ctx->J * ctx->C * nout));
+    CK(out.ensure((size_t)ctx->C * nout));
+    ConjParams c{};
+    c.C = ctx->C; c.J = ctx->J;
+    c.iv_N = ctx->d_N.p; c.iv_first = ctx->d_first.p; c.iv_rec = ctx->d_rec.p; c.iv_xs = ctx->d_xs.p;
+    c.iv_pt_off = ctx->d_pt_off.p; c.iv_xoff = ctx->d_xoff.p; c.t = ctx->d_t.p;
+    c.X[0] = ctx->d_X[0].p; c.X[1] = ctx->d_X[1].p;
+    c.selX = ctx->d_selX[ctx->sel_cur].p;
+    c.x0 = ctx->d_x0.p; c.partial = partial.p;
+    for (int i = 0; i < DMCMC_MAX_THETA; ++i) c.th.v[i] = ctx->law[ctx->law_cur].theta[i];
+    CK(launch_conjugate(ctx->cfg.model, c, out.p, ctx->stream));
+    std::vector<double> h((size_t)ctx->C * nout);
+    CK(cudaMemcpyAsync(h.data(), out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    for (int ch = 0; ch < ctx->C; ++ch) {
+        std::copy(h.begin() + (size_t)ch * nout, h.begin() + (size_t)ch * nout + nc, mu + (size_t)ch * nc);
+        std::copy(h.begin() + (size_t)ch * nout + nc, h.begin() + (size_t)(ch + 1) * nout, W + (size_t)ch * nc * nc);
+    }
+    partial.release();
+    out.release();
+    return 0;
+}
+
 extern "C" int dmcmc_set_timing(dmcmc_ctx *ctx, int32_t every) {
     REQUIRE(ctx && every >= 0, "dmcmc_set_timing: bad argument");
     ctx->time_every = every;

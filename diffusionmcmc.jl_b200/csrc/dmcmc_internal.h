@@ -107,6 +107,21 @@ cudaError_t launch_set_start(double *x0, const double *src, int64_t chain_stride
 
 // noise transposition [C][S][M] -> [M][TT][C][8] is done on the host in the C-ABI layer.
 
+// conjugate Gaussian update path integrals (dmcmc_conjugate.cu)
+struct ConjParams {
+    int32_t C, J;
+    const int32_t *iv_N, *iv_first, *iv_rec, *iv_xs, *iv_pt_off;
+    const int64_t *iv_xoff;
+    const double *t;       // [P] grid times
+    const double *X[2];
+    const uint8_t *selX;
+    const double *x0;
+    double *partial;       // [J][C][nc + nc*nc]
+    Theta th;
+};
+int conjugate_dim(int model, int32_t *idx);  // number of conjugate parameters of the law (0: none) and their theta indices
+cudaError_t launch_conjugate(int model, const ConjParams &c, double *out /* device [C][nc + nc*nc] */, cudaStream_t s);
+
 // backward filter (dmcmc_bf.cu)
 struct BFParams {
     int32_t D, J, nblk;

@@ -238,6 +238,19 @@ class Engine:
     def param_commit(self, accepted):
         self._ck(self.lib.dmcmc_param_commit(self.h, int(bool(accepted))))
 
+    def conjugate_coords(self):
+        """theta indices of the law's conjugate parameters (dmcmc_conjugate_dim)."""
+        idx = np.zeros(8, np.int32)
+        n = int(self.lib.dmcmc_conjugate_dim(self.h, _ip(idx)))
+        return idx[:max(n, 0)].copy()
+
+    def conjugate_sums(self):
+        """(mu [C][nc], W [C][nc][nc]) of compute_mu_and_W over the accepted path, reduced on the device."""
+        nc = len(self.conjugate_coords())
+        mu, W = np.empty((self.C, nc)), np.empty((self.C, nc, nc))
+        self._ck(self.lib.dmcmc_conjugate_sums(self.h, _dp(mu), _dp(W)))
+        return mu, W
+
     # -- read-outs --------------------------------------------------------------------------
     def download_state(self, which=0):
         X = np.empty((self.C, self.P, self.d))

@@ -170,6 +170,16 @@ int dmcmc_set_ll(dmcmc_ctx *ctx, const double *ll);
 /* Device-side accept counters per block since the last call (src/adaptation.jl:100-103). */
 int dmcmc_accept_counts(dmcmc_ctx *ctx, int64_t *accepted /* [nblk] */, int64_t *proposed);
 
+/* -- conjugate Gaussian parameter update (src/updates.jl:83-105, :225-262) ----------------------------
+ * For a drift whose rough coordinates are linear in some parameters, b = phi(x) theta_c + phi_c(x), the
+ * path integrals  mu = sum phi' Gamma^-1 (dy - phi_c dt),  W = sum phi' Gamma^-1 phi dt  over the accepted
+ * path (compute_mu_and_W, :241-262) are reduced on the device; the posterior draw stays on the host.
+ * dmcmc_conjugate_dim: number nc of such parameters of the context's law and their theta indices
+ * (FHN: gamma, beta; Lotka-Volterra: alpha..delta; Lorenz-63: theta1..theta3; 0 = none).
+ * Parameters of that set that are held fixed enter as  mu_S - W[S,F] theta_F  on the host. */
+int32_t dmcmc_conjugate_dim(const dmcmc_ctx *ctx, int32_t *theta_idx /* [nc] or NULL */);
+int dmcmc_conjugate_sums(dmcmc_ctx *ctx, double *mu /* [C][nc] */, double *W /* [C][nc][nc] */);
+
 /* -- device-side exchange for a block-sharded recording ------------------------------
  * The halo / end-point messages between neighbouring GPUs never have to touch the host: the caller
  * (NCCL send/recv, or a peer copy) works on DEVICE buffers, ordered on the context's stream.

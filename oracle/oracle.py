@@ -153,6 +153,46 @@ def philox_exponential(seed, it, first_interval, chain):
                                         C.c_uint32(first_interval), C.c_uint32(chain))
 
 
+def conjugate_structure(model, th, x):
+    """(theta indices, rough-coordinate rows, phi [NR][NC], phi_c [NR], Gamma^-1 diagonal [NR]) of a law
+    whose rough coordinates are linear in the parameters, b_rough = phi theta + phi_c
+    (phi / phi_c of /root/reference src/updates.jl:296-330 written out per law)."""
+    if model == MODEL_FHN:      # dX2 = (gamma X1 - X2 + beta) dt + sigma dW
+        return [2, 3], [1], np.array([[x[0], 1.0]]), np.array([-x[1]]), np.array([1.0 / th[4] ** 2])
+    if model in (MODEL_LV, MODEL_LVM):
+        P = np.array([[x[0], -x[0] * x[1], 0.0, 0.0], [0.0, 0.0, -x[1], x[0] * x[1]]])
+        s = np.array([th[4] * x[0], th[5] * x[1]]) if model == MODEL_LVM else np.array([th[4], th[5]])
+        return [0, 1, 2, 3], [0, 1], P, np.zeros(2), 1.0 / s ** 2
+    if model == MODEL_L63:
+        P = np.diag([x[1] - x[0], x[0], -x[2]])
+        return [0, 1, 2], [0, 1, 2], P, np.array([0.0, -x[1] - x[0] * x[2], x[0] * x[1]]), np.full(3, 1.0 / th[3] ** 2)
+    raise ValueError("no conjugate structure for this law")
+
+
+def conjugate_sums(model, th, X, N, t):
+    """compute_mu_and_W (/root/reference src/updates.jl:241-262) over per-interval containers
+    X [C][P][d] (N_j + 1 points each, as Oracle.accepted_X returns them) with grid times t [P]:
+        mu += phi' Gamma^-1 dy - phi' Gamma^-1 phi_c dt ;  W += phi' Gamma^-1 phi dt   per Euler step.
+    Pure-Python loops: small cases only."""
+    C_ = X.shape[0]
+    idx = conjugate_structure(model, th, X[0, 0])[0]
+    nc = len(idx)
+    mu, W = np.zeros((C_, nc)), np.zeros((C_, nc, nc))
+    off = 0
+    for n in N:
+        for c in range(C_):
+            for i in range(int(n)):
+                x, xn = X[c, off + i], X[c, off + i + 1]
+                dt = t[off + i + 1] - t[off + i]
+                _, rows, P, pc, g = conjugate_structure(model, th, x)
+                dy = xn[rows] - x[rows]
+                G = np.diag(g)
+                mu[c] += P.T @ G @ dy - P.T @ G @ pc * dt
+                W[c] += P.T @ G @ P * dt
+        off += int(n) + 1
+    return idx, mu, W
+
+
 def chequerboard_layout(rec_nobs, half_len, pattern):
     rec_nobs = i32(rec_nobs)
     J = int(rec_nobs.sum())
