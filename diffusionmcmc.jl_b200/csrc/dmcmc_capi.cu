@@ -739,12 +739,12 @@ int dmcmc_set_block_mask(dmcmc_ctx *ctx, const int32_t *active) {
     return 0;  // stream-ordered: no host synchronisation
 }
 
-static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool up) {
+static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool up, int c0 = 0, int nc = 0) {
     REQUIRE(ctx && X && j0 >= 0 && j1 > j0 && j1 <= ctx->J, "segment: bad interval range");
     REQUIRE(ctx->have_grid, "segment: call dmcmc_set_grid first");
     CK(cudaSetDevice(ctx->cfg.device));
     const int steps = ctx->st_off[j1] - ctx->st_off[j0];
-    const size_t n = (size_t)ctx->C * steps * ctx->d;
+    const size_t n = (size_t)(nc > 0 ? nc : ctx->C) * steps * ctx->d;
     DevBuf<double> pk;
     CK(pk.ensure(n));
     if (up) CK(cudaMemcpyAsync(pk.p, X, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -754,7 +754,7 @@ static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool 
     g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
     g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
     g.selX = ctx->d_selX[ctx->sel_cur].p;
-    g.packed = pk.p; g.upload = up; g.pk_stride = (int64_t)steps * ctx->d;
+    g.packed = pk.p; g.upload = up; g.pk_stride = (int64_t)steps * ctx->d; g.c0 = c0; g.nc = nc;
     CK(launch_segment(g, ctx->stream));
     if (!up) CK(cudaMemcpyAsync(X, pk.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (sync(ctx)) return -1;
@@ -1328,10 +1328,12 @@ int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_ou
     for (int r = 0; r < rec; ++r) j0 += ctx->rec_nobs[r];
     const int j1 = j0 + ctx->rec_nobs[rec], d = ctx->d;
     const int steps = ctx->st_off[j1] - ctx->st_off[j0];
-    std::vector<double> seg((size_t)ctx->C * steps * d);
-    if (segment_copy(ctx, j0, j1, seg.data(), false)) return -1;
-    for (int i = 0; i < d; ++i) x_out[i] = ctx->x0[((size_t)chain * ctx->R + rec) * d + i];
-    std::copy(seg.begin() + (size_t)chain * steps * d, seg.begin() + (size_t)(chain + 1) * steps * d, x_out + d);
+    // only this chain's records leave the device (a chain's interval record is contiguous in HBM)
+    if (segment_copy(ctx, j0, j1, x_out + d, false, chain, 1)) return -1;
+    // starting point from the device copy (dmcmc_set_start_device may have replaced it): x0[(rec * d + i) * C + chain]
+    CK(cudaMemcpy2D(x_out, sizeof(double), ctx->d_x0.p + (size_t)rec * d * ctx->C + chain, (size_t)ctx->C * sizeof(double),
+                    sizeof(double), d, cudaMemcpyDeviceToHost));
+    (void)steps;
     return 0;
 }
 

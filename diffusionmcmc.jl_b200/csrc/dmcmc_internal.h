@@ -92,6 +92,7 @@ cudaError_t launch_gather(const GatherParams &g, cudaStream_t s);
 // halo exchange of a block-sharded recording: accepted X of intervals [j0, j1), packed [C][steps][D]
 struct SegmentParams {
     int32_t C, D, j0, j1, steps;
+    int32_t c0, nc;   // chains [c0, c0 + nc) are packed (nc = 0: all)
     int64_t TT;
     const int32_t *iv_N, *iv_tile_off, *iv_st_off;
     const int64_t *iv_xoff;

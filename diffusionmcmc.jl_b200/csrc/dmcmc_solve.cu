@@ -861,14 +861,14 @@ __global__ void gather_kernel(const GatherParams g) {
 
 __global__ void segment_kernel(const SegmentParams g) {
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int nj = g.j1 - g.j0;
-    if (u >= (long long)nj * g.C) return;
-    const int j = g.j0 + (int)(u / g.C), chain = (int)(u % g.C);
+    const int nj = g.j1 - g.j0, nc = g.nc > 0 ? g.nc : g.C;
+    if (u >= (long long)nj * nc) return;
+    const int j = g.j0 + (int)(u / nc), ci = (int)(u % nc), chain = g.c0 + ci;
     double *X = g.X[g.selX[(size_t)j * g.C + chain]] + g.iv_xoff[j] + (size_t)chain * g.iv_xs[j];
     const int off = g.iv_st_off[j] - g.iv_st_off[g.j0];
     for (int k = 0; k < g.iv_N[j]; ++k)
         for (int c = 0; c < g.D; ++c) {
-            double *pk = g.packed + (size_t)chain * g.pk_stride + (size_t)(off + k) * g.D + c;
+            double *pk = g.packed + (size_t)ci * g.pk_stride + (size_t)(off + k) * g.D + c;
             if (g.upload) X[(size_t)k * g.D + c] = *pk;
             else *pk = X[(size_t)k * g.D + c];
         }
@@ -890,7 +890,7 @@ cudaError_t launch_set_start(double *x0, const double *src, int64_t chain_stride
 }
 
 cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s) {
-    const long long n = (long long)(g.j1 - g.j0) * g.C;
+    const long long n = (long long)(g.j1 - g.j0) * (g.nc > 0 ? g.nc : g.C);
     if (n <= 0) return cudaSuccess;
     segment_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g);
     return cudaGetLastError();
