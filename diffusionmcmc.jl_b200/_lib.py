@@ -69,6 +69,7 @@ SYMBOLS = {
     "dmcmc_timer_start": (C.c_int, [C.c_void_p]),
     "dmcmc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "dmcmc_set_fast_step": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dmcmc_set_cooperative": (C.c_int, [C.c_void_p, C.c_int32]),
 }
 
 _lib = None

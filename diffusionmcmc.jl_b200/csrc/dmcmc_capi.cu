@@ -121,7 +121,8 @@ struct dmcmc_ctx {
     bool param_pending = false;
     bool w_valid = false;  // stored accepted W is consistent with the accepted X under the current law/layout
     int threads = 64;
-    int fast_step = 1;  // 0: generic step; 1: model-specific fused step; 2: and the experimental warp-specialised kernel (dmcmc_set_fast_step)
+    bool fast_step = true;  // allow model-specific fused steps (dmcmc_set_fast_step)
+    int coop = -1;          // warp-per-unit imputation kernel: -1 auto, 0 never, 1 always (dmcmc_set_cooperative)
     SweepIO io;
 };
 
@@ -349,7 +350,8 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     sp.out_stride = lay.nblk;
     sp.reinvert = 0;
     sp.store_w = 1;
-    sp.fast_ok = (!law.custom_aux && ctx->fast_step) ? ctx->fast_step : 0;
+    sp.fast_ok = (!law.custom_aux && ctx->fast_step) ? 1 : 0;
+    sp.coop = ctx->coop;
     if (ctx->cfg.model == DMCMC_MODEL_FHN && sp.fast_ok) {  // fused step streams the derived coefficient table
         if (!tb.fvalid) {
             Theta th{};
@@ -1407,7 +1409,13 @@ int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx) {
 
 extern "C" int dmcmc_set_fast_step(dmcmc_ctx *ctx, int32_t on) {
     REQUIRE(ctx, "dmcmc_set_fast_step: null context");
-    ctx->fast_step = on < 0 ? 0 : (on > 2 ? 2 : on);
+    ctx->fast_step = on != 0;
+    return 0;
+}
+
+extern "C" int dmcmc_set_cooperative(dmcmc_ctx *ctx, int32_t mode) {
+    REQUIRE(ctx && mode >= -1 && mode <= 1, "dmcmc_set_cooperative: -1 (auto), 0 (never) or 1 (always)");
+    ctx->coop = mode;
     return 0;
 }
 

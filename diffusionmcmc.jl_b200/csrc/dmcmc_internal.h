@@ -55,8 +55,8 @@ struct SolveParams {
     int32_t force_accept;
     int32_t reinvert;   // 1: accepted noise is recovered from the accepted X (stored W is stale)
     int32_t store_w;    // 1: write the proposal noise W deg (0 when the next update re-inverts anyway)
-    int32_t fast_ok;    // >= 1: the law uses the model's built-in aux law (fused model-specific step allowed);
-                        // 2: and the warp-specialised kernel where one exists (dmcmc_solve_ws.cu)
+    int32_t fast_ok;    // 1: the law uses the model's built-in aux law (fused model-specific step allowed)
+    int32_t coop;       // warp-per-unit kernel for launches with few units: -1 auto (by unit count), 0 never, 1 always
     int32_t depth;      // tiles in flight of the table / input pipelines (2, 4 or 8; set by the launcher)
     int32_t out_stride; // row stride (per chain) of out_llprop / out_ll / out_acc
     const uint8_t *unit_mask;  // [C][nblk] or nullptr
@@ -70,7 +70,7 @@ struct SolveParams {
 // launchers (dmcmc_solve.cu); return the CUDA error of the launch
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s);
 cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_big.cu
-cudaError_t launch_solve_fhn_ws(const SolveParams &p, int threads, cudaStream_t s);   // dmcmc_solve_ws.cu
+cudaError_t launch_solve_coop(int model, const SolveParams &p, cudaStream_t s);        // dmcmc_solve_coop.cu (MODE_IMPUTE)
 cudaError_t launch_fhn_derive(const double *raw, double *out, long long nrec, int has_psi, const Theta &th, cudaStream_t s);
 
 // state gather for read-outs (dmcmc_solve.cu)

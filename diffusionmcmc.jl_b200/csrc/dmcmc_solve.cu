@@ -342,11 +342,7 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? 3 : 2) solve_kernel(const So
                             }
                             if constexpr (MODE == MODE_IMPUTE) dw[0] = fma(lam * rec[FD_SQ], (double)z[0][s], rho * dw[0]);  // pCN
                             if constexpr (SOLVE) {
-                                double g;
-                                fhn_dll(fk, rec, R0c, x[0], x[1], g, lsum);
-                                const double ynew = fma(rec[FD_KIE], g + (fk.s - x[1]), x[0]);
-                                x[1] = fma(rec[FD_A1], x[1], fma(rec[FD_B1], x[0], fma(fk.sig, dw[0], Cf)));
-                                x[0] = ynew;
+                                fhn_step(fk, rec, R0c, fma(fk.sig, dw[0], Cf), x[0], x[1], lsum);
                             }
                         } else {
                             double rec[RS], F[D];
@@ -354,10 +350,10 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? 3 : 2) solve_kernel(const So
                             guiding_F<D, PSI>(rec, xb, F);
                             const double dt = rec[0];
                             if constexpr (NEED_XA) {
-                                double xn[D], dr[D], res[D], dll;
+                                double xn[D], dr[D], res[D], gg;
                                 IS::state(hst, ks, xn);
-                                guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, xa, dt, dr, dll);
-                                lsum_a += dll;
+                                guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, xa, dt, dr, gg);
+                                lsum_a = fma(gg, dt, lsum_a);
 #pragma unroll
                                 for (int c = 0; c < D; ++c) res[c] = xn[c] - xa[c] - dr[c];
                                 MD::sigma_solve(p.th, xa, res, dw);
@@ -371,9 +367,9 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? 3 : 2) solve_kernel(const So
                                 for (int w = 0; w < M; ++w) dw[w] = lam * (rec[1] * (double)z[w][s]) + rho * dw[w];
                             }
                             if constexpr (SOLVE) {
-                                double dr[D], sdw[D], dll;
-                                guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, dt, dr, dll);
-                                lsum += dll;
+                                double dr[D], sdw[D], gg;
+                                guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, dt, dr, gg);
+                                lsum = fma(gg, dt, lsum);
                                 MD::sigma_mul(p.th, x, dw, sdw);
 #pragma unroll
                                 for (int c = 0; c < D; ++c) x[c] = x[c] + dr[c] + sdw[c];
@@ -576,11 +572,18 @@ static cudaError_t launch_psi(int mode, const SolveParams &p, int threads, cudaS
                      : launch_model<MD, false, FAST>(mode, p, threads, s);
 }
 
+// launches with at most this many (chain, block) units go to the warp-per-unit kernel: below it the
+// thread-per-unit kernel leaves most of the machine idle and one lane's instruction stream is the
+// critical path; above it the cooperative kernel's 32 x redundant recursion costs more than it hides
+constexpr long long COOP_MAX_UNITS = 2048;  // measured crossover on B200: ~3000 units (FitzHugh-Nagumo fused step), ~4000 (Lorenz-63)
+
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s) {
+    if (mode == MODE_IMPUTE && model != 3) {
+        const long long units = (long long)p.C * p.nblk;
+        if (p.coop > 0 || (p.coop < 0 && units <= COOP_MAX_UNITS)) return launch_solve_coop(model, p, s);
+    }
     switch (model) {
-    case 0:
-        if (p.fast_ok >= 2 && mode == MODE_IMPUTE && p.Z == nullptr && p.reinvert) return launch_solve_fhn_ws(p, threads, s);
-        return p.fast_ok ? launch_psi<ModelFHN, true>(mode, p, threads, s)
+    case 0: return p.fast_ok ? launch_psi<ModelFHN, true>(mode, p, threads, s)
                              : launch_psi<ModelFHN, false>(mode, p, threads, s);
     case 1: return launch_psi<ModelLV>(mode, p, threads, s);
     case 2: return launch_psi<ModelL63>(mode, p, threads, s);

@@ -1,4 +1,4 @@
-// dmcmc_solve_common.cuh -- pieces shared by the small-d solve kernels (dmcmc_solve.cu, dmcmc_solve_ws.cu):
+// dmcmc_solve_common.cuh -- building blocks of the small-d solve kernel (dmcmc_solve.cu):
 // guided step, FitzHugh-Nagumo fused step, TMA / mbarrier plumbing, the LDGSTS input stage.
 #pragma once
 #include <algorithm>
@@ -27,13 +27,14 @@ __device__ __forceinline__ void guiding_F(const double *rec, const double *xb, d
     }
 }
 
-// ---- one guided step: Girsanov integrand G*dt and the drift part (b + a r) dt -----------------
+// ---- one guided step: Girsanov integrand G and the drift part (b + a r) dt -------------------
+// (callers accumulate ll = fma(G, dt, ll) explicitly, so that every kernel rounds the sum the same way)
 template <class MD, bool PSI>
 __device__ __forceinline__ void guided_terms(const Theta &th, const double *__restrict__ rec,
                                              const double *F, const double *aB,
                                              const double *abeta, const double *aatil,
                                              const double *x, double dt, double *drift_dt,
-                                             double &dll) {
+                                             double &gout) {
     constexpr int D = MD::D;
     using R = Rec<D, PSI>;
     double r[D], b[D], ar[D];
@@ -64,7 +65,7 @@ __device__ __forceinline__ void guided_terms(const Theta &th, const double *__re
                 tr += (a[i * D + k] - aatil[i * D + k]) * (r[k] * r[i] - rec[R::OFF_H + hidx(D, k, i)]);
         g += 0.5 * tr;
     }
-    dll = g * dt;
+    gout = g;
     MD::a_mul(th, x, r, ar);
 #pragma unroll
     for (int i = 0; i < D; ++i) drift_dt[i] = (b[i] + ar[i]) * dt;
@@ -94,7 +95,7 @@ struct FhnK {
 };
 
 // derived record: [A1, B1, dt H11, dt H12, dt/eps, sqrt(dt) | C1, dt F0_1 | dt s2 Psi21, dt s2 Psi22, dt Psi11, dt Psi12]
-// (the first six are all the recursion itself reads: the solver warps of dmcmc_solve_ws.cu load only those)
+// (the first six are all the recursion itself reads)
 enum { FD_A1 = 0, FD_B1, FD_G00, FD_G01, FD_KIE, FD_SQ, FD_C1, FD_R0, FD_Q10, FD_Q11, FD_T00, FD_T01 };
 
 template <bool PSI>
@@ -120,13 +121,32 @@ __device__ __forceinline__ void fhn_derive(const double *raw, double *r, const F
     }
 }
 
-// adds the Girsanov increment G dt at state (y, x) to ll; g = y - y^3 is returned for the drift
-__device__ __forceinline__ void fhn_dll(const FhnK &fk, const double *rec, double R0c, double y, double x, double &g, double &ll) {
-    const double y2 = y * y;
-    g = fma(-y2, y, y);
-    const double d1 = fma(fk.ie, g, fma(-fk.aB0, y, -fk.c2));
-    const double r1dt = fma(-rec[FD_G00], y, fma(-rec[FD_G01], x, R0c));
+// the two factors of the Girsanov increment G dt = d1 * r1dt at state (y, x); p = 1 - y^2 is returned for the drift
+__device__ __forceinline__ void fhn_dll_terms(const FhnK &fk, const double *rec, double R0c, double y, double x, double &p,
+                                              double &d1, double &r1dt) {
+    p = fma(-y, y, 1.0);
+    const double g = y * p;  // y - y^3
+    d1 = fma(fk.ie, g, fma(-fk.aB0, y, -fk.c2));
+    r1dt = fma(-rec[FD_G00], y, fma(-rec[FD_G01], x, R0c));
+}
+// adds the Girsanov increment G dt at state (y, x) to ll
+__device__ __forceinline__ void fhn_dll(const FhnK &fk, const double *rec, double R0c, double y, double x, double &p, double &ll) {
+    double d1, r1dt;
+    fhn_dll_terms(fk, rec, R0c, y, x, p, d1, r1dt);
     ll = fma(d1, r1dt, ll);
+}
+// one fused step from (y, x): ll += G dt, then
+//     y' = y + (dt/eps) (y - y^3 + s - x) = [y + (dt/eps)(s - x)] + ((dt/eps) y)(1 - y^2)
+//     x' = A1 x + B1 y + ev ,   ev = sigma dW + C
+// written so that the recurrence y -> y' is two dependent FMAs deep (1 - y^2, then the sum): this chain is the
+// critical path of every latency-bound launch (few units; the warp-per-unit kernel)
+__device__ __forceinline__ void fhn_step(const FhnK &fk, const double *rec, double R0c, double ev, double &y, double &x, double &ll) {
+    double p;
+    fhn_dll(fk, rec, R0c, y, x, p, ll);
+    const double a = fma(rec[FD_KIE], fk.s - x, y);
+    const double ynew = fma(rec[FD_KIE] * y, p, a);
+    x = fma(rec[FD_A1], x, fma(rec[FD_B1], y, ev));
+    y = ynew;
 }
 
 // ---- TMA bulk copy + mbarrier plumbing (sm_90+/sm_100a PTX) -------------------------------------

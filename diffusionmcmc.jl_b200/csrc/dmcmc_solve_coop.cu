@@ -1,0 +1,403 @@
+// dmcmc_solve_coop.cu -- the imputation update for FEW, LONG units: one WARP per (chain, block) unit.
+//
+// solve_kernel (dmcmc_solve.cu) gives every unit one thread; that fills the machine when there are tens
+// of thousands of units (1024 chains under chequerboard blocking), but the reference's own shapes -- one
+// chain without blocking (BASELINE config 1), one chain with 8 blocks (config 2), 1024 unblocked chains
+// (config 3 as the reference would run it), one long recording cut into ~10^3 blocks (config 4) -- have
+// 1 .. 10^3 units of 10^2 .. 10^4 serial Euler steps, and then a single lane's ~110-instruction step is the
+// whole critical path.  Of that step only the recursion x_{k+1} = f(x_k) is serial.  Here the 32 lanes of a
+// warp share one unit, 32 Euler steps per tile:
+//   phase P (lane = step): Philox normals, accepted noise in (stored W, or -- fused layout switch -- recovered
+//            from the accepted path together with the accepted path's Girsanov terms), pCN mix, W deg out, and
+//            the mixed increments left in shared memory;
+//   phase S (all lanes redundantly, so no divergence and no broadcast): the recursion and its Girsanov sum,
+//            reading one broadcast table record and one increment per step; lane k keeps the state after step k
+//            and the tile's 32 states go out as one coalesced store.
+// The arithmetic per step is the single-thread kernel's, operation for operation (shared inline functions),
+// so the two kernels give bit-identical results and the choice between them (launch_solve: by unit count)
+// never changes a sample.  Reference rows: a1-a7 of SURVEY.md section 8a (src/run!_alterations.jl:5-47, :81-91).
+#include "dmcmc_solve_common.cuh"
+
+namespace dmcmc {
+
+constexpr int CT = 32;  // Euler steps per tile = lanes
+
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
+__global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
+    constexpr int D = MD::D, M = MD::M;
+    using R = Rec<D, PSI>;
+    constexpr int RS = R::SIZE;
+    constexpr bool STORE_W = !REINV;
+    using ZT = typename std::conditional<PHILOX, float, double>::type;
+    static_assert(!FAST || (D == 2 && M == 1), "the fused step is FitzHugh-Nagumo's");
+
+    extern __shared__ __align__(256) double dsm[];
+    __shared__ alignas(8) uint64_t full[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = (int)blockDim.x >> 5;
+    double *stab = dsm;                                              // [2][CT][RS]  table records of a tile
+    constexpr int SW = FAST ? 4 : M + 2;  // per step: mixed increments (FAST: e_k, R_k), two factors of the accepted G dt
+    double *sdw = dsm + 2 * CT * RS + (size_t)warp * CT * (SW + D);  // [CT][SW]
+    double *sxk = sdw + CT * SW;                                      // [CT][D]   the tile's proposal states
+
+    const int groups = (p.C + wpc - 1) / wpc;
+    const int blk = (int)(blockIdx.x / groups);
+    const int chain_raw = (int)(blockIdx.x % groups) * wpc + warp;
+    const bool in_range = chain_raw < p.C;
+    const int chain = in_range ? chain_raw : p.C - 1;  // surplus warps shadow the last chain, stores off
+    const size_t uo = (size_t)chain * p.nblk + blk;
+    const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
+    const bool masked = (p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]);
+    const bool active = in_range && !masked;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // ---- table pipeline (thread 0): one bulk copy per 32-step tile, one tile ahead ----
+    int tj = i1, ttl = 0, tq = 0, tN = p.iv_N[i1], ttoff = p.iv_tile_off[i1];
+    auto issue_table = [&]() {
+        if (tj > i2) return;
+        const int npad = ((tN + TILE - 1) >> 3) * TILE;  // records the table holds for this interval
+        const int nrec = min(CT, npad - ttl * CT);
+        const uint32_t bytes = (uint32_t)(nrec * RS * sizeof(double));
+        uint64_t *bar = &full[tq & 1];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stab + (size_t)(tq & 1) * CT * RS, p.table + ((size_t)ttoff * TILE + (size_t)ttl * CT) * RS, bytes, bar);
+        ++tq;
+        if (++ttl * CT >= tN) {
+            ttl = 0;
+            if (++tj <= i2) { tN = p.iv_N[tj]; ttoff = p.iv_tile_off[tj]; }
+        }
+    };
+    if (threadIdx.x == 0) issue_table();
+
+    const bool pinned = PSI && p.blk_pinned[blk];
+    double x[D], xb[D];
+    load_start<D>(p, chain, i1, x);
+#pragma unroll
+    for (int c = 0; c < D; ++c) xb[c] = 0.0;
+    if (pinned) load_end<D>(p, chain, i2, xb);
+    [[maybe_unused]] double xa_prev[D];  // REINV: accepted state before the tile's first step
+#pragma unroll
+    for (int c = 0; c < D; ++c) xa_prev[c] = x[c];
+
+    FhnK fk;
+    if constexpr (FAST) fk.set_law(p.th);
+
+    double llp;
+    {
+        // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
+        double rec[RS], F[D];
+        const double *r0 = p.table_raw + (size_t)p.iv_tile_off[i1] * TILE * RS;
+#pragma unroll
+        for (int i = 0; i < RS; ++i) rec[i] = __ldg(r0 + i);
+        guiding_F<D, PSI>(rec, xb, F);
+        double c = p.blk_c0[blk];
+        if (pinned) {
+            double gx = 0.0, qq = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                gx += p.blk_g[(size_t)blk * D + i] * xb[i];
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) s += p.blk_Qc[(size_t)blk * D * D + i * D + k] * xb[k];
+                qq += xb[i] * s;
+            }
+            c += gx + 0.5 * qq;
+        }
+        double xHx = 0.0, Fx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) s += rec[R::OFF_H + hidx(D, i, k)] * x[k];
+            xHx += x[i] * s;
+            Fx += F[i] * x[i];
+        }
+        llp = -c - 0.5 * xHx + Fx;
+    }
+    double lla = llp, lsum = 0.0, lsum_a = 0.0;
+    bool ok = true;
+    const uint32_t gchain = (uint32_t)(chain + p.chain_offset);
+    PhiloxKeys pkeys;
+    pkeys.set(p.seed);
+
+    int q = 0;
+    double *xp_end = nullptr;
+    for (int j = i1; j <= i2; ++j) {
+        const int N = p.iv_N[j], nt = (N + CT - 1) / CT;
+        const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
+        double aB[FAST ? 1 : D * D], abeta[FAST ? 1 : D], aatil[MD::CONST_SIGMA ? 1 : D * D];
+        if constexpr (FAST) {
+            fk.set_interval(p.auxB + (size_t)j * D * D, p.auxbeta + (size_t)j * D);
+        } else {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) aB[i] = p.auxB[(size_t)j * D * D + i];
+#pragma unroll
+            for (int i = 0; i < D; ++i) abeta[i] = p.auxbeta[(size_t)j * D + i];
+        }
+        if constexpr (!MD::CONST_SIGMA) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
+        }
+        const double rho = p.rho[j], lam = sqrt(1.0 - rho * rho);
+        const double *Xa = p.X[sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];      // accepted record
+        double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];        // proposal record
+        const double *Wa = p.W[sw];
+        double *Wp = p.W[1 - sw];
+        xp_end = Xp + (size_t)(N - 1) * D;
+        const size_t wtile0 = (size_t)p.iv_tile_off[j];
+
+        for (int tl = 0; tl < nt; ++tl, ++q) {
+            __syncthreads();  // every warp is done with tile q-1: its table stage and (per warp) its increments are free
+            if (threadIdx.x == 0) issue_table();
+            mbar_wait(&full[q & 1], (uint32_t)((q >> 1) & 1));
+            const double *srec = stab + (size_t)(q & 1) * CT * RS;
+            const int k = tl * CT + lane;  // this lane's Euler step in phase P
+            const int nlive = min(CT, N - tl * CT);
+            const bool live = lane < nlive;
+
+            // ================= phase P: lane = step =================
+            {
+                const double *rp = srec + lane * RS;
+                double dw[M];
+#pragma unroll
+                for (int w = 0; w < M; ++w) dw[w] = 0.0;
+                double ga = 0.0, gb = 0.0;  // accepted-path Girsanov increment = ga * gb
+                [[maybe_unused]] double xn[D];
+                if constexpr (REINV) {
+                    // accepted state before and after this lane's step; recover the accepted increment and G dt
+                    double xa[D];
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) xn[c] = Xa[(size_t)k * D + c];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) xn[c] = 0.0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const double up = __shfl_up_sync(0xffffffffu, xn[c], 1);
+                        xa[c] = lane == 0 ? xa_prev[c] : up;
+                    }
+                    if (live) {
+                        if constexpr (FAST) {
+                            double rec[RS];
+                            load_rec_smem<RS>(rp, rec);
+                            double Cf = rec[FD_C1], R0c = rec[FD_R0];
+                            if constexpr (PSI) {
+                                Cf = fma(rec[FD_Q10], xb[0], fma(rec[FD_Q11], xb[1], Cf));
+                                R0c = fma(rec[FD_T00], xb[0], fma(rec[FD_T01], xb[1], R0c));
+                            }
+                            double g;
+                            fhn_dll_terms(fk, rec, R0c, xa[0], xa[1], g, ga, gb);
+                            const double pred = fma(rec[FD_A1], xa[1], fma(rec[FD_B1], xa[0], Cf));
+                            dw[0] = (xn[1] - pred) * fk.isig;
+                        } else {
+                            double rec[RS], F[D], dr[D], res[D];
+                            load_rec_smem<RS>(rp, rec);
+                            guiding_F<D, PSI>(rec, xb, F);
+                            guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, xa, rec[0], dr, ga);
+                            gb = rec[0];
+#pragma unroll
+                            for (int c = 0; c < D; ++c) res[c] = xn[c] - xa[c] - dr[c];
+                            MD::sigma_solve(p.th, xa, res, dw);
+                        }
+                    }
+                    // the next tile's first step starts from this tile's last accepted state
+                    const int last = nlive - 1;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) xa_prev[c] = __shfl_sync(0xffffffffu, xn[c], last);
+                } else {
+                    if (live) {
+#pragma unroll
+                        for (int w = 0; w < M; ++w) dw[w] = Wa[w_off(wtile0 + (size_t)(k >> 3), chain, w, p.C, M) + (k & 7)];
+                    }
+                }
+                // pCN: W deg = sqrt(1 - rho^2) W_fresh + rho W   (a2)
+                ZT z[M];
+#pragma unroll
+                for (int w = 0; w < M; ++w) {
+                    if constexpr (PHILOX) {
+                        float z4[4];
+                        philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w, (uint32_t)(k >> 2), z4);
+                        const int e = k & 3;
+                        z[w] = e == 0 ? z4[0] : (e == 1 ? z4[1] : (e == 2 ? z4[2] : z4[3]));
+                    } else {
+                        z[w] = live ? p.Z[w_off(wtile0 + (size_t)(k >> 3), chain, w, p.C, M) + (k & 7)] : 0.0;
+                    }
+                }
+                if (live) {
+                    if constexpr (FAST) {
+                        dw[0] = fma(lam * rp[FD_SQ], (double)z[0], rho * dw[0]);
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < M; ++w) dw[w] = lam * (rp[1] * (double)z[w]) + rho * dw[w];
+                    }
+                    if (STORE_W && active) {
+#pragma unroll
+                        for (int w = 0; w < M; ++w) Wp[w_off(wtile0 + (size_t)(k >> 3), chain, w, p.C, M) + (k & 7)] = dw[w];
+                    }
+                }
+                if constexpr (FAST) {
+                    // everything of the step that does not depend on the proposal state: e_k = sigma dW deg_k + C_k, R_k
+                    double Cf = rp[FD_C1], R0c = rp[FD_R0];
+                    if constexpr (PSI) {
+                        Cf = fma(rp[FD_Q10], xb[0], fma(rp[FD_Q11], xb[1], Cf));
+                        R0c = fma(rp[FD_T00], xb[0], fma(rp[FD_T01], xb[1], R0c));
+                    }
+                    sdw[lane * SW] = fma(fk.sig, dw[0], Cf);
+                    sdw[lane * SW + 1] = R0c;
+                    if constexpr (REINV) { sdw[lane * SW + 2] = ga; sdw[lane * SW + 3] = gb; }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < M; ++w) sdw[lane * SW + w] = dw[w];
+                    if constexpr (REINV) { sdw[lane * SW + M] = ga; sdw[lane * SW + M + 1] = gb; }
+                }
+            }
+            __syncwarp();
+
+            // ================= phase S: the recursion, all lanes in step =================
+            const uint32_t sxk_a = smem_u32(sxk);
+#pragma unroll 4
+            for (int s = 0; s < nlive; ++s) {
+                const double *rp = srec + s * RS;
+                if constexpr (FAST) {
+                    double rec[6];
+                    load_rec_smem<6>(rp, rec);  // A1, B1, dt H11, dt H12, dt/eps, (sqrt dt)
+                    const double2 er = *reinterpret_cast<const double2 *>(sdw + s * SW);  // e_k, R_k
+                    if constexpr (REINV) {
+                        const double2 gg = *reinterpret_cast<const double2 *>(sdw + s * SW + 2);
+                        lsum_a = fma(gg.x, gg.y, lsum_a);
+                    }
+                    fhn_step(fk, rec, er.y, er.x, x[0], x[1], lsum);
+                } else {
+                    double dw[M];
+#pragma unroll
+                    for (int w = 0; w < M; ++w) dw[w] = sdw[s * SW + w];
+                    if constexpr (REINV) lsum_a = fma(sdw[s * SW + M], sdw[s * SW + M + 1], lsum_a);
+                    double rec[RS], F[D], dr[D], sdwv[D], gg;
+                    load_rec_smem<RS>(rp, rec);
+                    guiding_F<D, PSI>(rec, xb, F);
+                    guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, rec[0], dr, gg);
+                    lsum = fma(gg, rec[0], lsum);
+                    MD::sigma_mul(p.th, x, dw, sdwv);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) x[c] = x[c] + dr[c] + sdwv[c];
+                    ok = ok && MD::bound_ok(x);
+                }
+                // every lane holds the same state: one (same-address) shared store per step.  No "memory" clobber: the
+                // stage is read only after the loop (behind __syncwarp), and the loop's table / increment loads must stay
+                // free to move ahead of these stores
+                if constexpr (D == 2) {
+                    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(sxk_a + (uint32_t)s * 16u), "d"(x[0]), "d"(x[1]));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c)
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(sxk_a + (uint32_t)(s * D + c) * 8u), "d"(x[c]));
+                }
+            }
+            __syncwarp();
+            if (live && active) {  // the tile's states: one coalesced store
+                double *dst = Xp + (size_t)k * D;
+                if constexpr (D == 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(sxk + lane * D);
+                    st_v2(dst, v.x, v.y);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) dst[c] = sxk[lane * D + c];
+                }
+            }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    llp += lsum;
+    lla += lsum_a;
+    if (!ok) llp = -INFINITY;
+    if (pinned && active && lane == 0) {  // pin the proposal's last point to x_b (glued paths stay continuous)
+#pragma unroll
+        for (int c = 0; c < D; ++c) xp_end[c] = xb[c];
+    }
+
+    double llcur = REINV ? lla : p.ll[uo];
+    const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain) : p.E[uo];
+    // accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!)
+    const bool acc = active && (p.force_accept ? ok : (e > -(llp - llcur)));
+    if (in_range) {
+        for (int j = i1 + lane; j <= i2; j += 32) {  // swap_paths!: flip the accepted-container selectors
+            const size_t o = (size_t)j * p.C + chain;
+            p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
+            p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && STORE_W);
+        }
+    }
+    if (lane == 0) {
+        if (p.acc_count && acc) atomicAdd(p.acc_count + blk, 1ull);
+        if (p.prop_count && active) atomicAdd(p.prop_count + blk, 1ull);
+        if (active) {
+            if (acc) llcur = llp;
+            p.ll[uo] = llcur;
+            if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = llp;
+            if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = llcur;
+            if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = (uint8_t)acc;
+        } else if (in_range && p.blk_active && !p.blk_active[blk]) {  // block owned by a neighbouring shard
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            if (p.out_llprop) p.out_llprop[(size_t)chain * p.out_stride + blk] = nan;
+            if (p.out_ll) p.out_ll[(size_t)chain * p.out_stride + blk] = nan;
+            if (p.out_acc) p.out_acc[(size_t)chain * p.out_stride + blk] = 0;
+        }
+    }
+}
+
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
+static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
+    constexpr int RS = Rec<MD::D, PSI>::SIZE;
+    const int wpc = std::min(4, (int)p.C);  // units of one block (consecutive chains) share the table stage
+    const unsigned groups = (unsigned)((p.C + wpc - 1) / wpc);
+    const unsigned grid = groups * (unsigned)p.nblk;
+    const size_t smem = sizeof(double) * ((size_t)2 * CT * RS + (size_t)wpc * CT * ((FAST ? 4 : MD::M + 2) + MD::D));
+    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)(32 * wpc));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <class MD, bool FAST>
+static cudaError_t launch_coop_model(const SolveParams &p, cudaStream_t s) {
+    const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
+#define DMCMC_COOP(PSI_)                                                                              \
+    if (philox) return reinv ? launch_coop_one<MD, PSI_, true, true, FAST>(p, s)                       \
+                             : launch_coop_one<MD, PSI_, true, false, FAST>(p, s);                     \
+    return reinv ? launch_coop_one<MD, PSI_, false, true, FAST>(p, s)                                  \
+                 : launch_coop_one<MD, PSI_, false, false, FAST>(p, s);
+    if (p.has_psi) { DMCMC_COOP(true) }
+    DMCMC_COOP(false)
+#undef DMCMC_COOP
+}
+
+// MODE_IMPUTE only; the caller (launch_solve) has decided that the launch has few units
+cudaError_t launch_solve_coop(int model, const SolveParams &p, cudaStream_t s) {
+    if ((long long)p.nblk * p.C == 0) return cudaSuccess;
+    switch (model) {
+    case 0: return p.fast_ok ? launch_coop_model<ModelFHN, true>(p, s) : launch_coop_model<ModelFHN, false>(p, s);
+    case 1: return launch_coop_model<ModelLV, false>(p, s);
+    case 2: return launch_coop_model<ModelL63, false>(p, s);
+    case 4: return launch_coop_model<ModelLIN2, false>(p, s);
+    case 5: return launch_coop_model<ModelLVM, false>(p, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace dmcmc

@@ -8,6 +8,8 @@ Everything numerical happens in libdmcmc_b200.so on the GPU; this class only mar
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -55,6 +57,8 @@ class Engine:
         if self.lib.dmcmc_create(C.byref(cfg), C.byref(h)) != 0:
             raise DmcmcError(self.lib.dmcmc_last_error(None).decode())
         self.h = h
+        if os.environ.get("DMCMC_COOP"):  # test hook: pin the imputation kernel (0 thread-per-unit, 1 warp-per-unit)
+            self.set_cooperative(int(os.environ["DMCMC_COOP"]))
         self.N = _i32(spec["N"])
         self.J = len(self.N)
         self.pt_off = np.concatenate([[0], np.cumsum(self.N + 1)]).astype(np.int64)
@@ -286,6 +290,10 @@ class Engine:
         a, p = np.zeros(self.nblk, np.int64), np.zeros(self.nblk, np.int64)
         self._ck(self.lib.dmcmc_accept_counts(self.h, a.ctypes.data_as(_lib._lp), p.ctypes.data_as(_lib._lp)))
         return a, p
+
+    def set_cooperative(self, mode):
+        """-1: imputation kernel chosen by unit count (default); 0: thread per (chain, block) unit; 1: warp per unit."""
+        self._ck(self.lib.dmcmc_set_cooperative(self.h, int(mode)))
 
     def kernel_times(self):
         """(ms[4], launches[4]) per kernel mode since the last call: impute, param, relayout, ll."""

@@ -215,6 +215,11 @@ int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
 /* Model-specific fused step kernels (FitzHugh-Nagumo with its built-in aux law); on by default.
  * Off = the generic step for every model (same mathematics, different rounding). */
 int dmcmc_set_fast_step(dmcmc_ctx *ctx, int32_t on);
+/* Which imputation kernel serves dmcmc_impute / dmcmc_run_sweeps: one thread per (chain, block) unit, or --
+ * for launches with few, long units (the reference's own shapes: one chain, no or few blocks,
+ * src/run!_alterations.jl:15-16 loops over them serially) -- one warp per unit.  -1: chosen by unit count
+ * (default), 0: never, 1: always.  The two kernels give bit-identical results. */
+int dmcmc_set_cooperative(dmcmc_ctx *ctx, int32_t mode);
 
 #ifdef __cplusplus
 }

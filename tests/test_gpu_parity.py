@@ -9,6 +9,14 @@ from helpers import RTOL, accept_mismatch_is_tie, close, interior_mask, maxrel
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["thread_per_unit", "warp_per_unit"])
+def imputation_kernel(request, monkeypatch):
+    """Every parity test runs against both imputation kernels (dmcmc_set_cooperative): the problems here are
+    small enough that the automatic choice would always be the warp-per-unit kernel."""
+    monkeypatch.setenv("DMCMC_COOP", "0" if request.param == "thread_per_unit" else "1")
+    return request.param
+
+
 def _mk(pkg, name, **kw):
     P = pkg.problems
     return {"fhn": P.fhn_spec, "lv": P.lv_spec, "l63": P.l63_spec, "lin2": P.lin2_spec,
@@ -392,3 +400,24 @@ def test_block_ll_additivity_full_size(pkg):
     ll1 = e.get_ll().copy()
     e.init_ll()
     assert np.array_equal(ll1, e.get_ll())
+
+
+@pytest.mark.parametrize("name,kw,half", [("fhn", dict(n_obs=9, C=70, dt=0.004), 0), ("fhn", dict(n_obs=9, C=70, dt=0.004), 1),
+                                          ("lv", dict(n_obs=12, C=5, dt=0.01), 2), ("l63", dict(n_obs=40, C=3, dt=1e-3), 3),
+                                          ("l63", dict(n_obs=10, C=2, dt=2e-4), 0), ("lvm", dict(n_obs=6, C=4, dt=0.005), 1)])
+def test_warp_per_unit_kernel_is_bit_identical(pkg, monkeypatch, name, kw, half):
+    """The kernel choice (by unit count) must never change a sample: stored-noise sweeps (half = 0) and fused
+    layout-switch sweeps, Philox noise, ragged tiles (N = 25, 50, 10, 5 steps per interval)."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = _mk(pkg, name, **kw)
+    out = []
+    for mode in (0, 1):
+        monkeypatch.setenv("DMCMC_COOP", str(mode))
+        e = Engine(spec, seed=11)
+        e.init_paths()
+        e.run_sweeps(0, 5, half)
+        X, W = e.download_state(0)
+        out.append((X, W, e.get_ll().copy(), e.accept_counts()[0].copy()))
+        e.close()
+    for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "accept counts")):
+        assert np.array_equal(a, b), f"{what} differs between the two imputation kernels"
