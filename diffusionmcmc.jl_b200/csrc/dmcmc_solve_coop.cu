@@ -16,14 +16,18 @@
 // The arithmetic per step is the single-thread kernel's, operation for operation (shared inline functions),
 // so the two kernels give bit-identical results and the choice between them (launch_solve: by unit count)
 // never changes a sample.  Reference rows: a1-a7 of SURVEY.md section 8a (src/run!_alterations.jl:5-47, :81-91).
+#include <cstdlib>
+
 #include "dmcmc_solve_common.cuh"
 
 namespace dmcmc {
 
 constexpr int CT = 32;  // Euler steps per tile = lanes
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
-__global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
+// SPLIT: every unit gets TWO warps -- a producer that runs phase P one tile ahead and a solver that runs phase S --
+// so that phase P (global loads, Philox, Box-Muller) leaves the critical path altogether.
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT>
+__global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     constexpr int D = MD::D, M = MD::M;
     using R = Rec<D, PSI>;
     constexpr int RS = R::SIZE;
@@ -31,13 +35,23 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
     using ZT = typename std::conditional<PHILOX, float, double>::type;
     static_assert(!FAST || (D == 2 && M == 1), "the fused step is FitzHugh-Nagumo's");
 
+    constexpr int TD = SPLIT ? 4 : 2;   // table ring: SPLIT: tile q-1 (solver), q (producer), q+1 and q+2 in flight
+    constexpr int NB = SPLIT ? 2 : 1;   // staging buffers per unit
     extern __shared__ __align__(256) double dsm[];
-    __shared__ alignas(8) uint64_t full[2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = (int)blockDim.x >> 5;
-    double *stab = dsm;                                              // [2][CT][RS]  table records of a tile
+    __shared__ alignas(8) uint64_t full[TD];
+    const int lane = threadIdx.x & 31, nthr = (int)blockDim.x;
+    const int wpc = SPLIT ? nthr >> 6 : nthr >> 5;                   // units per CTA
+    const int warp_raw = threadIdx.x >> 5;
+    const bool do_P = !SPLIT || warp_raw >= wpc, do_S = !SPLIT || warp_raw < wpc;  // producer / solver role of this warp
+    const int warp = SPLIT && warp_raw >= wpc ? warp_raw - wpc : warp_raw;          // unit of the CTA
+    double *stab = dsm;                                              // [TD][CT][RS]  table records of a tile
     constexpr int SW = FAST ? 4 : M + 2;  // per step: mixed increments (FAST: e_k, R_k), two factors of the accepted G dt
-    double *sdw = dsm + 2 * CT * RS + (size_t)warp * CT * (SW + D);  // [CT][SW]
-    double *sxk = sdw + CT * SW;                                      // [CT][D]   the tile's proposal states
+    double *sdw0 = dsm + TD * CT * RS + (size_t)warp * CT * (NB * SW + D);  // [NB][CT][SW]
+    double *sxk = sdw0 + NB * CT * SW;                                       // [CT][D]   the tile's proposal states
+    auto cta_sync = [&]() {
+        if constexpr (SPLIT) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");  // called from both roles' code paths
+        else __syncthreads();
+    };
 
     const int groups = (p.C + wpc - 1) / wpc;
     const int blk = (int)(blockIdx.x / groups);
@@ -50,8 +64,7 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
     const bool active = in_range && !masked;
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < TD; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -64,17 +77,20 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
         const int npad = ((tN + TILE - 1) >> 3) * TILE;  // records the table holds for this interval
         const int nrec = min(CT, npad - ttl * CT);
         const uint32_t bytes = (uint32_t)(nrec * RS * sizeof(double));
-        uint64_t *bar = &full[tq & 1];
+        uint64_t *bar = &full[tq & (TD - 1)];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(stab + (size_t)(tq & 1) * CT * RS, p.table + ((size_t)ttoff * TILE + (size_t)ttl * CT) * RS, bytes, bar);
+        bulk_g2s(stab + (size_t)(tq & (TD - 1)) * CT * RS, p.table + ((size_t)ttoff * TILE + (size_t)ttl * CT) * RS, bytes, bar);
         ++tq;
         if (++ttl * CT >= tN) {
             ttl = 0;
             if (++tj <= i2) { tN = p.iv_N[tj]; ttoff = p.iv_tile_off[tj]; }
         }
     };
-    if (threadIdx.x == 0) issue_table();
+    if (threadIdx.x == 0) {
+        issue_table();
+        if constexpr (SPLIT) issue_table();
+    }
 
     const bool pinned = PSI && p.blk_pinned[blk];
     double x[D], xb[D];
@@ -129,6 +145,12 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
 
     int q = 0;
     double *xp_end = nullptr;
+    if constexpr (SPLIT) {
+        if (do_S) {  // the solver runs one tile behind the producer
+            cta_sync();
+            if (threadIdx.x == 0) issue_table();
+        }
+    }
     for (int j = i1; j <= i2; ++j) {
         const int N = p.iv_N[j], nt = (N + CT - 1) / CT;
         const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
@@ -154,16 +176,17 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
         const size_t wtile0 = (size_t)p.iv_tile_off[j];
 
         for (int tl = 0; tl < nt; ++tl, ++q) {
-            __syncthreads();  // every warp is done with tile q-1: its table stage and (per warp) its increments are free
+            cta_sync();  // every warp is done with its previous tile: that table stage and staging buffer are free
             if (threadIdx.x == 0) issue_table();
-            mbar_wait(&full[q & 1], (uint32_t)((q >> 1) & 1));
-            const double *srec = stab + (size_t)(q & 1) * CT * RS;
+            mbar_wait(&full[q & (TD - 1)], (uint32_t)((q / TD) & 1));
+            const double *srec = stab + (size_t)(q & (TD - 1)) * CT * RS;
+            double *sdw = sdw0 + (SPLIT ? (q & 1) * CT * SW : 0);
             const int k = tl * CT + lane;  // this lane's Euler step in phase P
             const int nlive = min(CT, N - tl * CT);
             const bool live = lane < nlive;
 
             // ================= phase P: lane = step =================
-            {
+            if (do_P) {
                 const double *rp = srec + lane * RS;
                 double dw[M];
 #pragma unroll
@@ -260,7 +283,8 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
                     if constexpr (REINV) { sdw[lane * SW + M] = ga; sdw[lane * SW + M + 1] = gb; }
                 }
             }
-            __syncwarp();
+            if constexpr (!SPLIT) __syncwarp();
+            if (!do_S) continue;
 
             // ================= phase S: the recursion, all lanes in step =================
             const uint32_t sxk_a = smem_u32(sxk);
@@ -316,6 +340,12 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
         }
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if constexpr (SPLIT) {
+        if (!do_S) {  // producer: the solver's last tile is still to come
+            cta_sync();
+            return;
+        }
+    }
     llp += lsum;
     lla += lsum_a;
     if (!ok) llp = -INFINITY;
@@ -353,17 +383,24 @@ __global__ void __launch_bounds__(128) solve_coop_kernel(const SolveParams p) {
     }
 }
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
-static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT>
+static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     constexpr int RS = Rec<MD::D, PSI>::SIZE;
+    constexpr int TD = SPLIT ? 4 : 2, NB = SPLIT ? 2 : 1, SW = FAST ? 4 : MD::M + 2;
     const int wpc = std::min(4, (int)p.C);  // units of one block (consecutive chains) share the table stage
     const unsigned groups = (unsigned)((p.C + wpc - 1) / wpc);
     const unsigned grid = groups * (unsigned)p.nblk;
-    const size_t smem = sizeof(double) * ((size_t)2 * CT * RS + (size_t)wpc * CT * ((FAST ? 4 : MD::M + 2) + MD::D));
-    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST>;
+    const size_t smem = sizeof(double) * ((size_t)TD * CT * RS + (size_t)wpc * CT * (NB * SW + MD::D));
+    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3((unsigned)(32 * wpc));
+    cfg.blockDim = dim3((unsigned)((SPLIT ? 64 : 32) * wpc));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -372,6 +409,13 @@ static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
+static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
+    static const int env_split = getenv("DMCMC_COOP_SPLIT") ? atoi(getenv("DMCMC_COOP_SPLIT")) : 1;  // A/B override
+    return env_split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true>(p, s)
+                     : launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false>(p, s);
 }
 
 template <class MD, bool FAST>
