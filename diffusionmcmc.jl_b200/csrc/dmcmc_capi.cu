@@ -352,6 +352,7 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     sp.store_w = 1;
     sp.fast_ok = (!law.custom_aux && ctx->fast_step) ? 1 : 0;
     sp.coop = ctx->coop;
+    sp.mean_N = ctx->J > 0 ? (int32_t)(ctx->st_off[ctx->J] / ctx->J) : 0;
     if (ctx->cfg.model == DMCMC_MODEL_FHN && sp.fast_ok) {  // fused step streams the derived coefficient table
         if (!tb.fvalid) {
             Theta th{};

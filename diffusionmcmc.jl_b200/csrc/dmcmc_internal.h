@@ -57,6 +57,7 @@ struct SolveParams {
     int32_t store_w;    // 1: write the proposal noise W deg (0 when the next update re-inverts anyway)
     int32_t fast_ok;    // 1: the law uses the model's built-in aux law (fused model-specific step allowed)
     int32_t coop;       // warp-per-unit kernel for launches with few units: -1 auto (by unit count), 0 never, 1 always
+    int32_t mean_N;     // mean Euler steps per interval (host-side hint for kernel variants)
     int32_t depth;      // tiles in flight of the table / input pipelines (2, 4 or 8; set by the launcher)
     int32_t out_stride; // row stride (per chain) of out_llprop / out_ll / out_acc
     const uint8_t *unit_mask;  // [C][nblk] or nullptr

@@ -287,34 +287,48 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             if (!do_S) continue;
 
             // ================= phase S: the recursion, all lanes in step =================
+            // The operands of step s+1 (table record, staged increments) are loaded BEFORE step s's state is stored:
+            // shared-memory loads are never moved above a shared store whose address they might alias, so in source
+            // order their ~30-cycle latency would sit in the recurrence of every step.
             const uint32_t sxk_a = smem_u32(sxk);
+            constexpr int NREC = FAST ? 6 : RS;  // FAST: A1, B1, dt H11, dt H12, dt/eps, (sqrt dt) is all the recursion reads
+            double rec[NREC], sv[SW];
+            auto load_ops = [&](int s, double *r, double *v) {
+                load_rec_smem<NREC>(srec + s * RS, r);
+                if constexpr (SW % 2 == 0) {
+#pragma unroll
+                    for (int i = 0; i < SW / 2; ++i) {
+                        const double2 t = *reinterpret_cast<const double2 *>(sdw + s * SW + 2 * i);
+                        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SW; ++i) v[i] = sdw[s * SW + i];
+                }
+            };
+            load_ops(0, rec, sv);
 #pragma unroll 4
             for (int s = 0; s < nlive; ++s) {
-                const double *rp = srec + s * RS;
+                double recn[NREC], svn[SW];
+                load_ops(min(s + 1, CT - 1), recn, svn);
                 if constexpr (FAST) {
-                    double rec[6];
-                    load_rec_smem<6>(rp, rec);  // A1, B1, dt H11, dt H12, dt/eps, (sqrt dt)
-                    const double2 er = *reinterpret_cast<const double2 *>(sdw + s * SW);  // e_k, R_k
-                    if constexpr (REINV) {
-                        const double2 gg = *reinterpret_cast<const double2 *>(sdw + s * SW + 2);
-                        lsum_a = fma(gg.x, gg.y, lsum_a);
-                    }
-                    fhn_step(fk, rec, er.y, er.x, x[0], x[1], lsum);
+                    if constexpr (REINV) lsum_a = fma(sv[2], sv[3], lsum_a);
+                    fhn_step(fk, rec, sv[1], sv[0], x[0], x[1], lsum);  // sv = e_k, R_k, (two factors of the accepted G dt)
                 } else {
-                    double dw[M];
-#pragma unroll
-                    for (int w = 0; w < M; ++w) dw[w] = sdw[s * SW + w];
-                    if constexpr (REINV) lsum_a = fma(sdw[s * SW + M], sdw[s * SW + M + 1], lsum_a);
-                    double rec[RS], F[D], dr[D], sdwv[D], gg;
-                    load_rec_smem<RS>(rp, rec);
+                    if constexpr (REINV) lsum_a = fma(sv[M], sv[M + 1], lsum_a);
+                    double F[D], dr[D], sdwv[D], gg;
                     guiding_F<D, PSI>(rec, xb, F);
                     guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, rec[0], dr, gg);
                     lsum = fma(gg, rec[0], lsum);
-                    MD::sigma_mul(p.th, x, dw, sdwv);
+                    MD::sigma_mul(p.th, x, sv, sdwv);
 #pragma unroll
                     for (int c = 0; c < D; ++c) x[c] = x[c] + dr[c] + sdwv[c];
                     ok = ok && MD::bound_ok(x);
                 }
+#pragma unroll
+                for (int i = 0; i < NREC; ++i) rec[i] = recn[i];
+#pragma unroll
+                for (int i = 0; i < SW; ++i) sv[i] = svn[i];
                 // every lane holds the same state: one (same-address) shared store per step.  No "memory" clobber: the
                 // stage is read only after the loop (behind __syncwarp), and the loop's table / increment loads must stay
                 // free to move ahead of these stores
@@ -413,8 +427,12 @@ static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
 
 template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
 static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
-    static const int env_split = getenv("DMCMC_COOP_SPLIT") ? atoi(getenv("DMCMC_COOP_SPLIT")) : 1;  // A/B override
-    return env_split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true>(p, s)
+    // a producer warp per unit pays off when tiles are reasonably full (intervals of >= 24 Euler steps) or when there
+    // are so few units that nothing else hides phase P; with ~10^3 units of short intervals (Lorenz-63 at 10 steps per
+    // interval) the other warps already hide it and the extra hand-over per tile costs more than it saves
+    static const int env_split = getenv("DMCMC_COOP_SPLIT") ? atoi(getenv("DMCMC_COOP_SPLIT")) : -1;  // A/B override
+    const bool split = env_split >= 0 ? env_split != 0 : (p.mean_N >= 24 || (long long)p.C * p.nblk <= 2 * 148);
+    return split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true>(p, s)
                      : launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false>(p, s);
 }
 
