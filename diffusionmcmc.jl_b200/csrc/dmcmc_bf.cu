@@ -70,8 +70,11 @@ struct SmallMat {
                 A[j * D + i] = s;
             }
     }
-    __device__ static void lu(double *A, int *piv, double &lad) {
-        lad = 0.0;
+    // LU with partial pivoting in place.  invd = reciprocals of the pivots (each division is done once and shared by
+    // every solve against this factorisation); lad = log|det| taken from the product of the pivots (one log per
+    // factorisation instead of D: the recursion is serial per block, so its latency is the kernel's run time)
+    __device__ static void lu(double *A, int *piv, double *invd, double &lad) {
+        double prod = 1.0;
         for (int k = 0; k < D; ++k) {
             int p = k;
             double best = fabs(A[k * D + k]);
@@ -82,17 +85,19 @@ struct SmallMat {
                 for (int j = 0; j < D; ++j) {
                     const double t = A[k * D + j]; A[k * D + j] = A[p * D + j]; A[p * D + j] = t;
                 }
-            lad += log(fabs(A[k * D + k]));
+            prod *= fabs(A[k * D + k]);
             const double inv = 1.0 / A[k * D + k];
+            invd[k] = inv;
             for (int i = k + 1; i < D; ++i) {
                 const double l = A[i * D + k] * inv;
                 A[i * D + k] = l;
                 for (int j = k + 1; j < D; ++j) A[i * D + j] -= l * A[k * D + j];
             }
         }
+        lad = log(prod);
     }
     template <int NR>
-    __device__ static void solve(const double *LU, const int *piv, double *Bm) {
+    __device__ static void solve(const double *LU, const int *piv, const double *invd, double *Bm) {
         for (int k = 0; k < D; ++k) {
             const int p = piv[k];
             if (p != k)
@@ -105,7 +110,7 @@ struct SmallMat {
             }
         }
         for (int k = D - 1; k >= 0; --k) {
-            const double inv = 1.0 / LU[k * D + k];
+            const double inv = invd[k];
             for (int j = 0; j < NR; ++j) {
                 double s = Bm[k * NR + j];
                 for (int i = k + 1; i < D; ++i) s -= LU[k * D + i] * Bm[i * NR + j];
@@ -176,21 +181,21 @@ __device__ void bf_step(bool pinned, const double *Phi, const double *Q, const d
     using S = SmallMat<D>;
     double A[D * D], Hs[D * D], T1[D * D], Psis[D * D], Fs[D], tv[D], tv2[D];
     int piv[D];
-    double lad;
+    double lad, invd[D];
     S::mm(s.H, Q, A);
     for (int i = 0; i < D; ++i) A[i * D + i] += 1.0;
-    S::lu(A, piv, lad);
+    S::lu(A, piv, invd, lad);
     for (int i = 0; i < D * D; ++i) Hs[i] = s.H[i];
-    S::template solve<D>(A, piv, Hs);
+    S::template solve<D>(A, piv, invd, Hs);
     S::sym(Hs);
     for (int i = 0; i < D; ++i) Fs[i] = s.F0[i];
-    S::template solve<1>(A, piv, Fs);
+    S::template solve<1>(A, piv, invd, Fs);
     S::mv(Hs, mvec, tv);
     S::mv(Q, Fs, tv2);
     s.c0 = s.c0 + 0.5 * lad + 0.5 * S::dot(mvec, tv) - S::dot(mvec, Fs) - 0.5 * S::dot(s.F0, tv2);
     if (pinned) {
         for (int i = 0; i < D * D; ++i) Psis[i] = s.Psi[i];
-        S::template solve<D>(A, piv, Psis);
+        S::template solve<D>(A, piv, invd, Psis);
         double a1[D], a2[D];
         S::mTv(Psis, mvec, a1);
         S::mTv(s.Psi, tv2, a2);

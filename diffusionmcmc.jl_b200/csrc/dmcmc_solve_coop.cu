@@ -26,12 +26,15 @@ constexpr int CT = 32;  // Euler steps per tile = lanes
 
 // SPLIT: every unit gets TWO warps -- a producer that runs phase P one tile ahead and a solver that runs phase S --
 // so that phase P (global loads, Philox, Box-Muller) leaves the critical path altogether.
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT>
+// PARAM: the parameter-step solve (a9, set_proposal! / compute_ll!, src/run!_alterations.jl:177-211, :258-265): fixed
+// accepted noise under the proposal law, no mix, no accept -- per-unit ll deg and success flag out.
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, bool PARAM>
 __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     constexpr int D = MD::D, M = MD::M;
     using R = Rec<D, PSI>;
     constexpr int RS = R::SIZE;
-    constexpr bool STORE_W = !REINV;
+    constexpr bool STORE_W = !REINV && !PARAM;
+    static_assert(!PARAM || (!PHILOX && !REINV), "the parameter step reads the stored accepted noise");
     using ZT = typename std::conditional<PHILOX, float, double>::type;
     static_assert(!FAST || (D == 2 && M == 1), "the fused step is FitzHugh-Nagumo's");
 
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     const int chain = in_range ? chain_raw : p.C - 1;  // surplus warps shadow the last chain, stores off
     const size_t uo = (size_t)chain * p.nblk + blk;
     const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
-    const bool masked = (p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]);
+    const bool masked = !PARAM && ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
     const bool active = in_range && !masked;
 
     if (threadIdx.x == 0) {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
         }
-        const double rho = p.rho[j], lam = sqrt(1.0 - rho * rho);
+        const double rho = PARAM ? 1.0 : p.rho[j], lam = PARAM ? 0.0 : sqrt(1.0 - rho * rho);
         const double *Xa = p.X[sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];      // accepted record
         double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];        // proposal record
         const double *Wa = p.W[sw];
@@ -243,10 +246,12 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     }
                 }
                 // pCN: W deg = sqrt(1 - rho^2) W_fresh + rho W   (a2)
-                ZT z[M];
+                [[maybe_unused]] ZT z[M];
 #pragma unroll
                 for (int w = 0; w < M; ++w) {
-                    if constexpr (PHILOX) {
+                    if constexpr (PARAM) {
+                        z[w] = 0.0;
+                    } else if constexpr (PHILOX) {
                         float z4[4];
                         philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w, (uint32_t)(k >> 2), z4);
                         const int e = k & 3;
@@ -256,7 +261,9 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     }
                 }
                 if (live) {
-                    if constexpr (FAST) {
+                    if constexpr (PARAM) {
+                        // the accepted increments as they are
+                    } else if constexpr (FAST) {
                         dw[0] = fma(lam * rp[FD_SQ], (double)z[0], rho * dw[0]);
                     } else {
 #pragma unroll
@@ -368,6 +375,13 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
         for (int c = 0; c < D; ++c) xp_end[c] = xb[c];
     }
 
+    if constexpr (PARAM) {
+        if (in_range && lane == 0) {
+            if (p.out_llprop) p.out_llprop[uo] = llp;
+            if (p.out_acc) p.out_acc[uo] = (uint8_t)ok;
+        }
+        return;
+    }
     double llcur = REINV ? lla : p.ll[uo];
     const double e = PHILOX ? philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain) : p.E[uo];
     // accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!)
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     }
 }
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT>
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, bool PARAM>
 static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     constexpr int RS = Rec<MD::D, PSI>::SIZE;
     constexpr int TD = SPLIT ? 4 : 2, NB = SPLIT ? 2 : 1, SW = FAST ? 4 : MD::M + 2;
@@ -405,7 +419,7 @@ static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     const unsigned groups = (unsigned)((p.C + wpc - 1) / wpc);
     const unsigned grid = groups * (unsigned)p.nblk;
     const size_t smem = sizeof(double) * ((size_t)TD * CT * RS + (size_t)wpc * CT * (NB * SW + MD::D));
-    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT>;
+    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT, PARAM>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -425,19 +439,22 @@ static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST>
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool PARAM = false>
 static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
     // a producer warp per unit pays off when tiles are reasonably full (intervals of >= 24 Euler steps) or when there
     // are so few units that nothing else hides phase P; with ~10^3 units of short intervals (Lorenz-63 at 10 steps per
     // interval) the other warps already hide it and the extra hand-over per tile costs more than it saves
     static const int env_split = getenv("DMCMC_COOP_SPLIT") ? atoi(getenv("DMCMC_COOP_SPLIT")) : -1;  // A/B override
     const bool split = env_split >= 0 ? env_split != 0 : (p.mean_N >= 24 || (long long)p.C * p.nblk <= 2 * 148);
-    return split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true>(p, s)
-                     : launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false>(p, s);
+    return split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true, PARAM>(p, s)
+                 : launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false, PARAM>(p, s);
 }
 
 template <class MD, bool FAST>
-static cudaError_t launch_coop_model(const SolveParams &p, cudaStream_t s) {
+static cudaError_t launch_coop_model(int mode, const SolveParams &p, cudaStream_t s) {
+    if (mode == MODE_PARAM)
+        return p.has_psi ? launch_coop_one<MD, true, false, false, FAST, true>(p, s)
+                         : launch_coop_one<MD, false, false, false, FAST, true>(p, s);
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
 #define DMCMC_COOP(PSI_)                                                                              \
     if (philox) return reinv ? launch_coop_one<MD, PSI_, true, true, FAST>(p, s)                       \
@@ -449,15 +466,15 @@ static cudaError_t launch_coop_model(const SolveParams &p, cudaStream_t s) {
 #undef DMCMC_COOP
 }
 
-// MODE_IMPUTE only; the caller (launch_solve) has decided that the launch has few units
-cudaError_t launch_solve_coop(int model, const SolveParams &p, cudaStream_t s) {
+// MODE_IMPUTE and MODE_PARAM; the caller (launch_solve) has decided that the launch has few units
+cudaError_t launch_solve_coop(int model, int mode, const SolveParams &p, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
     switch (model) {
-    case 0: return p.fast_ok ? launch_coop_model<ModelFHN, true>(p, s) : launch_coop_model<ModelFHN, false>(p, s);
-    case 1: return launch_coop_model<ModelLV, false>(p, s);
-    case 2: return launch_coop_model<ModelL63, false>(p, s);
-    case 4: return launch_coop_model<ModelLIN2, false>(p, s);
-    case 5: return launch_coop_model<ModelLVM, false>(p, s);
+    case 0: return p.fast_ok ? launch_coop_model<ModelFHN, true>(mode, p, s) : launch_coop_model<ModelFHN, false>(mode, p, s);
+    case 1: return launch_coop_model<ModelLV, false>(mode, p, s);
+    case 2: return launch_coop_model<ModelL63, false>(mode, p, s);
+    case 4: return launch_coop_model<ModelLIN2, false>(mode, p, s);
+    case 5: return launch_coop_model<ModelLVM, false>(mode, p, s);
     }
     return cudaErrorInvalidValue;
 }
