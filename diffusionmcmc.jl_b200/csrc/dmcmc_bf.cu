@@ -17,102 +17,138 @@
 
 namespace dmcmc {
 
+// Every loop below has compile-time bounds and is unrolled, and the row exchanges of the pivoted LU are written as
+// predicated swaps over compile-time indices: with a run-time row index the matrices would live in local memory,
+// and this recursion is serial per layout block -- its latency IS the run time of a critical parameter step.
 template <int D>
 struct SmallMat {
-    __device__ static void mm(const double *A, const double *B, double *C) {
+    __device__ static __forceinline__ void mm(const double *A, const double *B, double *C) {
+#pragma unroll
         for (int i = 0; i < D; ++i)
+#pragma unroll
             for (int j = 0; j < D; ++j) {
                 double s = 0.0;
+#pragma unroll
                 for (int k = 0; k < D; ++k) s += A[i * D + k] * B[k * D + j];
                 C[i * D + j] = s;
             }
     }
-    __device__ static void mmT(const double *A, const double *B, double *C) {
+    __device__ static __forceinline__ void mmT(const double *A, const double *B, double *C) {
+#pragma unroll
         for (int i = 0; i < D; ++i)
+#pragma unroll
             for (int j = 0; j < D; ++j) {
                 double s = 0.0;
+#pragma unroll
                 for (int k = 0; k < D; ++k) s += A[i * D + k] * B[j * D + k];
                 C[i * D + j] = s;
             }
     }
-    __device__ static void mTm(const double *A, const double *B, double *C) {
+    __device__ static __forceinline__ void mTm(const double *A, const double *B, double *C) {
+#pragma unroll
         for (int i = 0; i < D; ++i)
+#pragma unroll
             for (int j = 0; j < D; ++j) {
                 double s = 0.0;
+#pragma unroll
                 for (int k = 0; k < D; ++k) s += A[k * D + i] * B[k * D + j];
                 C[i * D + j] = s;
             }
     }
-    __device__ static void mv(const double *A, const double *x, double *y) {
+    __device__ static __forceinline__ void mv(const double *A, const double *x, double *y) {
+#pragma unroll
         for (int i = 0; i < D; ++i) {
             double s = 0.0;
+#pragma unroll
             for (int k = 0; k < D; ++k) s += A[i * D + k] * x[k];
             y[i] = s;
         }
     }
-    __device__ static void mTv(const double *A, const double *x, double *y) {
+    __device__ static __forceinline__ void mTv(const double *A, const double *x, double *y) {
+#pragma unroll
         for (int i = 0; i < D; ++i) {
             double s = 0.0;
+#pragma unroll
             for (int k = 0; k < D; ++k) s += A[k * D + i] * x[k];
             y[i] = s;
         }
     }
-    __device__ static double dot(const double *a, const double *b) {
+    __device__ static __forceinline__ double dot(const double *a, const double *b) {
         double s = 0.0;
+#pragma unroll
         for (int i = 0; i < D; ++i) s += a[i] * b[i];
         return s;
     }
-    __device__ static void sym(double *A) {
+    __device__ static __forceinline__ void sym(double *A) {
+#pragma unroll
         for (int i = 0; i < D; ++i)
+#pragma unroll
             for (int j = i + 1; j < D; ++j) {
                 const double s = 0.5 * (A[i * D + j] + A[j * D + i]);
                 A[i * D + j] = s;
                 A[j * D + i] = s;
             }
     }
-    // LU with partial pivoting in place.  invd = reciprocals of the pivots (each division is done once and shared by
-    // every solve against this factorisation); lad = log|det| taken from the product of the pivots (one log per
-    // factorisation instead of D: the recursion is serial per block, so its latency is the kernel's run time)
-    __device__ static void lu(double *A, int *piv, double *invd, double &lad) {
+    // LU with partial pivoting in place (pivot = first row of maximal modulus, as in the oracle).  invd = reciprocals
+    // of the pivots (each division is done once and shared by every solve against this factorisation); lad = log|det|
+    // taken from the product of the pivots (one log per factorisation instead of D)
+    __device__ static __forceinline__ void lu(double *A, int *piv, double *invd, double &lad) {
         double prod = 1.0;
+#pragma unroll
         for (int k = 0; k < D; ++k) {
             int p = k;
             double best = fabs(A[k * D + k]);
+#pragma unroll
             for (int i = k + 1; i < D; ++i)
                 if (fabs(A[i * D + k]) > best) { best = fabs(A[i * D + k]); p = i; }
             piv[k] = p;
-            if (p != k)
-                for (int j = 0; j < D; ++j) {
-                    const double t = A[k * D + j]; A[k * D + j] = A[p * D + j]; A[p * D + j] = t;
+#pragma unroll
+            for (int i = k + 1; i < D; ++i)
+                if (p == i) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        const double t = A[k * D + j]; A[k * D + j] = A[i * D + j]; A[i * D + j] = t;
+                    }
                 }
             prod *= fabs(A[k * D + k]);
             const double inv = 1.0 / A[k * D + k];
             invd[k] = inv;
+#pragma unroll
             for (int i = k + 1; i < D; ++i) {
                 const double l = A[i * D + k] * inv;
                 A[i * D + k] = l;
+#pragma unroll
                 for (int j = k + 1; j < D; ++j) A[i * D + j] -= l * A[k * D + j];
             }
         }
         lad = log(prod);
     }
     template <int NR>
-    __device__ static void solve(const double *LU, const int *piv, const double *invd, double *Bm) {
+    __device__ static __forceinline__ void solve(const double *LU, const int *piv, const double *invd, double *Bm) {
+#pragma unroll
         for (int k = 0; k < D; ++k) {
-            const int p = piv[k];
-            if (p != k)
-                for (int j = 0; j < NR; ++j) {
-                    const double t = Bm[k * NR + j]; Bm[k * NR + j] = Bm[p * NR + j]; Bm[p * NR + j] = t;
+#pragma unroll
+            for (int i = k + 1; i < D; ++i)
+                if (piv[k] == i) {
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) {
+                        const double t = Bm[k * NR + j]; Bm[k * NR + j] = Bm[i * NR + j]; Bm[i * NR + j] = t;
+                    }
                 }
+#pragma unroll
             for (int i = k + 1; i < D; ++i) {
                 const double l = LU[i * D + k];
+#pragma unroll
                 for (int j = 0; j < NR; ++j) Bm[i * NR + j] -= l * Bm[k * NR + j];
             }
         }
+#pragma unroll
         for (int k = D - 1; k >= 0; --k) {
             const double inv = invd[k];
+#pragma unroll
             for (int j = 0; j < NR; ++j) {
                 double s = Bm[k * NR + j];
+#pragma unroll
                 for (int i = k + 1; i < D; ++i) s -= LU[k * D + i] * Bm[i * NR + j];
                 Bm[k * NR + j] = s * inv;
             }
@@ -265,7 +301,7 @@ __global__ void bf_kernel(const BFParams b) {
         double dt_cached = -1.0;
         for (int k = N - 1; k >= 0; --k) {
             const double dt = b.t[base + k + 1] - b.t[base + k];
-            if (!(fabs(dt - dt_cached) <= 1e-12 * fabs(dt_cached))) {
+            if (!(fabs(dt - dt_cached) <= 1e-9 * fabs(dt_cached))) {
                 transition<D>(b.auxB + (size_t)j * D * D, b.auxbeta + (size_t)j * D,
                               b.auxatil + (size_t)j * D * D, dt, Phi, Q, mvec);
                 dt_cached = dt;
@@ -466,7 +502,7 @@ __global__ void __launch_bounds__(256) bf_big_kernel(const BFParams b) {
         double dt_cached = -1.0;
         for (int k = N - 1; k >= 0; --k) {
             const double dt = b.t[base + k + 1] - b.t[base + k];
-            if (!(fabs(dt - dt_cached) <= 1e-12 * fabs(dt_cached))) {
+            if (!(fabs(dt - dt_cached) <= 1e-9 * fabs(dt_cached))) {
                 // transition (Phi, Q, mvec): Taylor series with scaling-and-doubling (mirrors transition<D>)
                 double nrm = 0.0;
                 for (int i = 0; i < D; ++i) {
