@@ -11,6 +11,7 @@
 // dependence on the pinned end point x_b is carried as F = F0 + Psi x_b, c = c0 + g'x_b + x_b'Qc x_b/2
 // so that one table serves every chain.  Same operation order as oracle/dmcmc_oracle.c.
 #include <cmath>
+#include <cstdlib>
 
 #include "dmcmc_device.cuh"
 #include "dmcmc_internal.h"
@@ -322,6 +323,72 @@ __global__ void bf_kernel(const BFParams b) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same filter, parallel in time inside an interval.  On an interval the aux law (B, beta, a~) is constant,
+// so the Gaussian transition from grid point k to the interval's right end is the one-step flow over
+// tau_k = t_N - t_k, and the value at EVERY grid point follows from the right-end value by one application of
+// bf_step with that transition: the N grid points of an interval are independent, only the chain over intervals is
+// serial (J links per block instead of J N).  One CTA per layout block, one thread per grid point of the current
+// interval.  Mathematically identical to the step-by-step recursion (both are exact flows of the H, F, c ODEs);
+// rounding differs at the 1e-13 level.  A critical parameter update on an unblocked recording -- one block, where
+// bf_kernel runs 10^4 steps on one thread -- drops from milliseconds to the latency of J transitions.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) bf_par_kernel(const BFParams b) {
+    const int blk = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ BFState<D> send[2];  // right-end state of the current interval / of the next one to the left
+    const bool pinned = b.blk_pinned[blk] != 0;
+    const int i1 = b.blk_i1[blk], i2 = b.blk_i2[blk];
+    if (tid == 0) {
+        BFState<D> &s = send[0];
+        for (int i = 0; i < D * D; ++i) { s.H[i] = 0.0; s.Psi[i] = 0.0; s.Qc[i] = 0.0; }
+        for (int i = 0; i < D; ++i) { s.F0[i] = 0.0; s.g[i] = 0.0; }
+        s.c0 = 0.0;
+    }
+    int cur = 0;
+    for (int j = i2; j >= i1; --j) {
+        const int N = b.iv_N[j];
+        const size_t base = (size_t)b.iv_pt_off[j];
+        const size_t sbase = (size_t)b.iv_tile_off[j] * TILE;
+        if (tid == 0) {  // observation at the interval's right end (or the pin of the block's last point)
+            BFState<D> &s = send[cur];
+            if (j == i2 && pinned) {
+                const double ie = 1.0 / b.pin_eps;
+                for (int i = 0; i < D; ++i) { s.H[i * D + i] = ie; s.Psi[i * D + i] = ie; s.Qc[i * D + i] = ie; }
+                s.c0 = 0.5 * D * log(2.0 * M_PI * b.pin_eps);
+            } else {
+                for (int i = 0; i < D * D; ++i) s.H[i] += b.Hobs[(size_t)j * D * D + i];
+                for (int i = 0; i < D; ++i) s.F0[i] += b.Fobs[(size_t)j * D + i];
+                s.c0 += b.cobs[j];
+            }
+            store_point<D>(b, s, base + N);
+        }
+        __syncthreads();
+        const double tN = b.t[base + N];
+        for (int k = tid; k < N; k += nt) {
+            double Phi[D * D], Q[D * D], mvec[D];
+            transition<D>(b.auxB + (size_t)j * D * D, b.auxbeta + (size_t)j * D, b.auxatil + (size_t)j * D * D,
+                          tN - b.t[base + k], Phi, Q, mvec);
+            BFState<D> s = send[cur];
+            bf_step<D>(pinned, Phi, Q, mvec, s);
+            store_point<D>(b, s, base + k);
+            store_rec<D>(b, s, sbase + k, b.t[base + k + 1] - b.t[base + k]);
+            if (k == 0) send[cur ^ 1] = s;
+        }
+        // pad slots of the interval's last tile: benign record (dt = 0)
+        const int npad = ((N + TILE - 1) / TILE) * TILE;
+        for (int e = N * b.rec + tid; e < npad * b.rec; e += nt) b.table[sbase * b.rec + e] = 0.0;
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (tid == 0) {
+        const BFState<D> &s = send[cur];
+        b.blk_c0[blk] = s.c0;
+        for (int i = 0; i < D; ++i) b.blk_g[(size_t)blk * D + i] = s.g[i];
+        for (int i = 0; i < D * D; ++i) b.blk_Qc[(size_t)blk * D * D + i] = s.Qc[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Large state dimension (Lorenz-96, D = 40): one CTA per layout block, matrices in shared memory,
 // every matrix operation of the small-D recursion spread over the CTA's threads.  Each output
 // element is still produced by ONE thread that sums in the same order as the scalar code (and the
@@ -609,11 +676,22 @@ cudaError_t launch_backward_filter(const BFParams &b, cudaStream_t s) {
         bf_big_kernel<D><<<b.nblk, 256, smem, s>>>(b);
         return cudaGetLastError();
     }
-    const int threads = 32;
-    const unsigned grid = (unsigned)((b.nblk + threads - 1) / threads);
+    static const int env_serial = getenv("DMCMC_BF_SERIAL") ? atoi(getenv("DMCMC_BF_SERIAL")) : 0;  // A/B: step-by-step recursion
+    if (env_serial) {
+        const int threads = 32;
+        const unsigned grid = (unsigned)((b.nblk + threads - 1) / threads);
+        switch (b.D) {
+        case 2: bf_kernel<2><<<grid, threads, 0, s>>>(b); break;
+        case 3: bf_kernel<3><<<grid, threads, 0, s>>>(b); break;
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
+    // one thread per grid point of an interval: 32 .. 128 threads by the mean interval length
+    const int threads = b.mean_N <= 32 ? 32 : (b.mean_N <= 64 ? 64 : 128);
     switch (b.D) {
-    case 2: bf_kernel<2><<<grid, threads, 0, s>>>(b); break;
-    case 3: bf_kernel<3><<<grid, threads, 0, s>>>(b); break;
+    case 2: bf_par_kernel<2><<<(unsigned)b.nblk, threads, 0, s>>>(b); break;
+    case 3: bf_par_kernel<3><<<(unsigned)b.nblk, threads, 0, s>>>(b); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

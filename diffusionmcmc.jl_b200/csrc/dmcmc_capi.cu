@@ -316,6 +316,7 @@ int run_backward_filter(dmcmc_ctx *ctx, int slot) {
     b.has_psi = lay.has_psi; b.rec = rec_size(ctx->d, lay.has_psi);
     b.table = tb.table.p;
     b.ptH = tb.ptH.p; b.ptF0 = tb.ptF0.p; b.ptPsi = tb.ptPsi.p; b.ptc0 = tb.ptc0.p;
+    b.mean_N = ctx->J > 0 ? (int32_t)(ctx->st_off[ctx->J] / ctx->J) : 0;
     b.blk_c0 = tb.blk_c0.p; b.blk_g = tb.blk_g.p; b.blk_Qc = tb.blk_Qc.p;
     CK(launch_backward_filter(b, ctx->stream));
     tb.valid = true;

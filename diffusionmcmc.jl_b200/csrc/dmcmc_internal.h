@@ -138,6 +138,7 @@ struct BFParams {
     const double *cobs;     // [J]
     double pin_eps;
     int32_t has_psi, rec;
+    int32_t mean_N;         // mean Euler steps per interval (launch-shape hint)
     double *table;          // [TT*8][rec]
     double *ptH, *ptF0, *ptPsi, *ptc0;  // per-grid-point copies (download / parity), may be null
     double *blk_c0, *blk_g, *blk_Qc;

@@ -417,7 +417,12 @@ def test_warp_per_unit_kernel_is_bit_identical(pkg, monkeypatch, name, kw, half)
         e.init_paths()
         e.run_sweeps(0, 5, half)
         X, W = e.download_state(0)
-        out.append((X, W, e.get_ll().copy(), e.accept_counts()[0].copy()))
+        th = np.array(spec["theta"], float)
+        llp, ok = e.param_loglik(th * (1 + 1e-3), critical=True)   # a9 under a perturbed law, fixed noise
+        Xp, _ = e.download_state(1)
+        e.param_commit(False)
+        out.append((X, W, e.get_ll().copy(), e.accept_counts()[0].copy(), llp, ok, Xp))
         e.close()
-    for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "accept counts")):
+    for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "accept counts", "parameter-step ll", "parameter-step success",
+                                           "parameter-step X")):
         assert np.array_equal(a, b), f"{what} differs between the two imputation kernels"
