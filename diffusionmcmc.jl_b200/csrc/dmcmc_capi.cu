@@ -1107,12 +1107,14 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
     // histories arrive at (879 KB per 80 us sweep), and every hand-over costs two wake-ups (the sleep below and
     // the blocking event wait: 50-100 us each on a loaded host, where eight ranks share the cores).  Four threads
     // take every fourth sweep, so a thread has ~300 us per sweep; they sleep, they do not spin.
-    constexpr int NDRAIN = 4;
+    constexpr int MAXDRAIN = 8;
+    static const int env_drain = getenv("DMCMC_DRAIN_THREADS") ? atoi(getenv("DMCMC_DRAIN_THREADS")) : 0;  // tuning override: 1, 2, 4, 8
+    const int NDRAIN = (env_drain == 1 || env_drain == 2 || env_drain == 4 || env_drain == 8) ? env_drain : 4;
     std::atomic<int> recorded{0};
-    std::atomic<int> drained[NDRAIN];  // per thread: sweeps it = t, t + NDRAIN, ... finished so far
+    std::atomic<int> drained[MAXDRAIN];  // per thread: sweeps it = t, t + NDRAIN, ... finished so far
     for (auto &d : drained) d.store(0);
     std::atomic<bool> failed{false};
-    std::thread drainer[NDRAIN];
+    std::thread drainer[MAXDRAIN];
     if (want_hist && n_sweeps > 0) {
         for (int t = 0; t < NDRAIN; ++t)
             drainer[t] = std::thread([&, t]() {
@@ -1139,7 +1141,7 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             const int pat = (first_pattern + it) & 1;
             const int slot = it % R;
             if (want_hist) {  // the slot's previous rows have left the pinned ring (and hence the device ring)
-                static_assert(R % NDRAIN == 0, "a ring slot is always drained by the same thread");
+                static_assert(R % MAXDRAIN == 0, "a ring slot is always drained by the same thread");
                 const int prev = it - R;  // the sweep that used this slot before
                 while (prev >= 0 && drained[prev % NDRAIN].load(std::memory_order_acquire) < prev / NDRAIN + 1) {
                     if (failed.load(std::memory_order_relaxed)) return fail(ctx, "dmcmc_run_sweeps: history copy failed");

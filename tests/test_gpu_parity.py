@@ -134,6 +134,27 @@ def test_device_backward_filter_vs_oracle(pkg, orc):
         assert np.abs(t["c0"] - o.c0).max() <= 1e-11 * max(1.0, np.abs(o.c0).max())
 
 
+def test_device_backward_filter_pinned_layout_vs_oracle(pkg, orc):
+    """a8 under chequerboard blocking: the device filter (parallel in time inside an interval: every grid point from
+    the interval's right-end value and the transition over tau_k) against the oracle's step-by-step recursion,
+    including the pinned blocks' Psi, g, Qc.  The pinned tables carry 1/pin_eps conditioning: 1e-9."""
+    P = pkg.problems
+    for name, kw, half in [("fhn", dict(n_obs=9, C=2, dt=0.004), 1), ("l63", dict(n_obs=12, C=1, dt=1e-3), 2),
+                           ("lv", dict(n_obs=10, C=1, dt=0.01), 3)]:
+        spec = _mk(pkg, name, **kw)
+        o, e = _pair(pkg, orc, spec, upload=False)
+        for pat in (0, 1):
+            lay = P.chequerboard_layout(o.rec_nobs, half, pat)
+            o.set_layout(*lay) if hasattr(o, "set_layout") else o.relayout(*lay)
+            e.set_layout(*lay)
+            e.backward_filter(0)
+            t = e.download_tables()
+            for key, ref in (("H", o.H), ("F0", o.F0), ("Psi", o.Psi), ("c0", o.c0), ("blk_g", o.blk_g), ("blk_Qc", o.blk_Qc)):
+                sc = max(1.0, float(np.abs(ref).max()))
+                err = float(np.abs(t[key] - ref).max())
+                assert err <= 1e-9 * sc, f"{name} pattern {pat} {key}: {err:.3e} vs scale {sc:.3e}"
+
+
 def test_blocked_sweeps_parity(pkg, orc):
     """Chequerboard blocking: relayout (W re-inversion + ll recompute) then imputation, both
     patterns, pinned end points."""
