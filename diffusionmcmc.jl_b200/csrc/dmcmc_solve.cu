@@ -578,7 +578,7 @@ static cudaError_t launch_psi(int mode, const SolveParams &p, int threads, cudaS
 constexpr long long COOP_MAX_UNITS = 2048;  // measured crossover on B200: ~3000 units (FitzHugh-Nagumo fused step), ~4000 (Lorenz-63)
 
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s) {
-    if ((mode == MODE_IMPUTE || mode == MODE_PARAM) && model != 3) {
+    if (model != 3) {
         const long long units = (long long)p.C * p.nblk;
         if (p.coop > 0 || (p.coop < 0 && units <= COOP_MAX_UNITS)) return launch_solve_coop(model, mode, p, s);
     }

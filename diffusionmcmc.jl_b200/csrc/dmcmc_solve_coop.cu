@@ -28,12 +28,17 @@ constexpr int CT = 32;  // Euler steps per tile = lanes
 // so that phase P (global loads, Philox, Box-Muller) leaves the critical path altogether.
 // PARAM: the parameter-step solve (a9, set_proposal! / compute_ll!, src/run!_alterations.jl:177-211, :258-265): fixed
 // accepted noise under the proposal law, no mix, no accept -- per-unit ll deg and success flag out.
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, bool PARAM>
+// MODE_RELAYOUT / MODE_LOGLIK: the accepted path only -- recover its noise (RELAYOUT: store it) and its ll under the
+// current layout (update_workspaces!, src/workspaces.jl:467-471; init_ll!, :425-431): phase P alone, plus the serial sum.
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE>
 __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
+    constexpr bool PARAM = MODE == MODE_PARAM;
+    constexpr bool ACC_ONLY = MODE == MODE_RELAYOUT || MODE == MODE_LOGLIK;
+    static_assert(!ACC_ONLY || (REINV && !PHILOX && !SPLIT), "accepted-path passes walk X, draw nothing, have no recursion");
     constexpr int D = MD::D, M = MD::M;
     using R = Rec<D, PSI>;
     constexpr int RS = R::SIZE;
-    constexpr bool STORE_W = !REINV && !PARAM;
+    constexpr bool STORE_W = MODE == MODE_IMPUTE && !REINV;
     static_assert(!PARAM || (!PHILOX && !REINV), "the parameter step reads the stored accepted noise");
     using ZT = typename std::conditional<PHILOX, float, double>::type;
     static_assert(!FAST || (D == 2 && M == 1), "the fused step is FitzHugh-Nagumo's");
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     const int chain = in_range ? chain_raw : p.C - 1;  // surplus warps shadow the last chain, stores off
     const size_t uo = (size_t)chain * p.nblk + blk;
     const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
-    const bool masked = !PARAM && ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
+    const bool masked = MODE == MODE_IMPUTE && ((p.unit_mask && !p.unit_mask[uo]) || (p.blk_active && !p.blk_active[blk]));
     const bool active = in_range && !masked;
 
     if (threadIdx.x == 0) {
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
 #pragma unroll
             for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
         }
-        const double rho = PARAM ? 1.0 : p.rho[j], lam = PARAM ? 0.0 : sqrt(1.0 - rho * rho);
+        const double rho = MODE != MODE_IMPUTE ? 1.0 : p.rho[j], lam = MODE != MODE_IMPUTE ? 0.0 : sqrt(1.0 - rho * rho);
         const double *Xa = p.X[sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];      // accepted record
         double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];        // proposal record
         const double *Wa = p.W[sw];
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                 [[maybe_unused]] ZT z[M];
 #pragma unroll
                 for (int w = 0; w < M; ++w) {
-                    if constexpr (PARAM) {
+                    if constexpr (MODE != MODE_IMPUTE) {
                         z[w] = 0.0;
                     } else if constexpr (PHILOX) {
                         float z4[4];
@@ -261,8 +266,12 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     }
                 }
                 if (live) {
-                    if constexpr (PARAM) {
+                    if constexpr (MODE != MODE_IMPUTE) {
                         // the accepted increments as they are
+                        if (MODE == MODE_RELAYOUT && in_range) {  // materialise them in the accepted noise container
+#pragma unroll
+                            for (int w = 0; w < M; ++w) p.W[sw][w_off(wtile0 + (size_t)(k >> 3), chain, w, p.C, M) + (k & 7)] = dw[w];
+                        }
                     } else if constexpr (FAST) {
                         dw[0] = fma(lam * rp[FD_SQ], (double)z[0], rho * dw[0]);
                     } else {
@@ -293,6 +302,11 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             if constexpr (!SPLIT) __syncwarp();
             if (!do_S) continue;
 
+            if constexpr (ACC_ONLY) {  // no proposal: only the accepted path's Girsanov sum, in serial order
+                for (int s = 0; s < nlive; ++s) lsum_a = fma(sdw[s * SW + (FAST ? 2 : M)], sdw[s * SW + (FAST ? 3 : M + 1)], lsum_a);
+                __syncwarp();
+                continue;
+            }
             // ================= phase S: the recursion, all lanes in step =================
             // The operands of step s+1 (table record, staged increments) are loaded BEFORE step s's state is stored:
             // shared-memory loads are never moved above a shared store whose address they might alias, so in source
@@ -370,6 +384,10 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     llp += lsum;
     lla += lsum_a;
     if (!ok) llp = -INFINITY;
+    if constexpr (ACC_ONLY) {
+        if (in_range && lane == 0) p.ll[uo] = lla;
+        return;
+    }
     if (pinned && active && lane == 0) {  // pin the proposal's last point to x_b (glued paths stay continuous)
 #pragma unroll
         for (int c = 0; c < D; ++c) xp_end[c] = xb[c];
@@ -411,7 +429,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     }
 }
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, bool PARAM>
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE>
 static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     constexpr int RS = Rec<MD::D, PSI>::SIZE;
     constexpr int TD = SPLIT ? 4 : 2, NB = SPLIT ? 2 : 1, SW = FAST ? 4 : MD::M + 2;
@@ -419,7 +437,7 @@ static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     const unsigned groups = (unsigned)((p.C + wpc - 1) / wpc);
     const unsigned grid = groups * (unsigned)p.nblk;
     const size_t smem = sizeof(double) * ((size_t)TD * CT * RS + (size_t)wpc * CT * (NB * SW + MD::D));
-    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT, PARAM>;
+    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -439,22 +457,32 @@ static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool PARAM = false>
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, int MODE = MODE_IMPUTE>
 static cudaError_t launch_coop_one(const SolveParams &p, cudaStream_t s) {
     // a producer warp per unit pays off when tiles are reasonably full (intervals of >= 24 Euler steps) or when there
     // are so few units that nothing else hides phase P; with ~10^3 units of short intervals (Lorenz-63 at 10 steps per
     // interval) the other warps already hide it and the extra hand-over per tile costs more than it saves
     static const int env_split = getenv("DMCMC_COOP_SPLIT") ? atoi(getenv("DMCMC_COOP_SPLIT")) : -1;  // A/B override
     const bool split = env_split >= 0 ? env_split != 0 : (p.mean_N >= 24 || (long long)p.C * p.nblk <= 2 * 148);
-    return split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true, PARAM>(p, s)
-                 : launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false, PARAM>(p, s);
+    if constexpr (MODE == MODE_RELAYOUT || MODE == MODE_LOGLIK) {
+        return launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false, MODE>(p, s);
+    } else {
+        return split ? launch_coop_split<MD, PSI, PHILOX, REINV, FAST, true, MODE>(p, s)
+                     : launch_coop_split<MD, PSI, PHILOX, REINV, FAST, false, MODE>(p, s);
+    }
 }
 
 template <class MD, bool FAST>
 static cudaError_t launch_coop_model(int mode, const SolveParams &p, cudaStream_t s) {
     if (mode == MODE_PARAM)
-        return p.has_psi ? launch_coop_one<MD, true, false, false, FAST, true>(p, s)
-                         : launch_coop_one<MD, false, false, false, FAST, true>(p, s);
+        return p.has_psi ? launch_coop_one<MD, true, false, false, FAST, MODE_PARAM>(p, s)
+                         : launch_coop_one<MD, false, false, false, FAST, MODE_PARAM>(p, s);
+    if (mode == MODE_RELAYOUT)
+        return p.has_psi ? launch_coop_one<MD, true, false, true, FAST, MODE_RELAYOUT>(p, s)
+                         : launch_coop_one<MD, false, false, true, FAST, MODE_RELAYOUT>(p, s);
+    if (mode == MODE_LOGLIK)
+        return p.has_psi ? launch_coop_one<MD, true, false, true, FAST, MODE_LOGLIK>(p, s)
+                         : launch_coop_one<MD, false, false, true, FAST, MODE_LOGLIK>(p, s);
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
 #define DMCMC_COOP(PSI_)                                                                              \
     if (philox) return reinv ? launch_coop_one<MD, PSI_, true, true, FAST>(p, s)                       \
@@ -466,7 +494,7 @@ static cudaError_t launch_coop_model(int mode, const SolveParams &p, cudaStream_
 #undef DMCMC_COOP
 }
 
-// MODE_IMPUTE and MODE_PARAM; the caller (launch_solve) has decided that the launch has few units
+// every solve mode; the caller (launch_solve) has decided that the launch has few units
 cudaError_t launch_solve_coop(int model, int mode, const SolveParams &p, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
     switch (model) {

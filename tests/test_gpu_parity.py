@@ -442,8 +442,10 @@ def test_warp_per_unit_kernel_is_bit_identical(pkg, monkeypatch, name, kw, half)
         llp, ok = e.param_loglik(th * (1 + 1e-3), critical=True)   # a9 under a perturbed law, fixed noise
         Xp, _ = e.download_state(1)
         e.param_commit(False)
-        out.append((X, W, e.get_ll().copy(), e.accept_counts()[0].copy(), llp, ok, Xp))
+        e.relayout(*pkg.problems.chequerboard_layout(e.rec_nobs, max(half, 1), 1))   # layout switch: W re-inversion + ll
+        _, Wr = e.download_state(0)
+        out.append((X, W, e.get_ll().copy(), e.accept_counts()[0].copy(), llp, ok, Xp, Wr))
         e.close()
     for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "accept counts", "parameter-step ll", "parameter-step success",
-                                           "parameter-step X")):
+                                           "parameter-step X", "W after a layout switch")):
         assert np.array_equal(a, b), f"{what} differs between the two imputation kernels"
