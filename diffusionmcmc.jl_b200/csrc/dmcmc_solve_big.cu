@@ -13,6 +13,7 @@
 // of the first mapping (one chain per warp, 11 wavefronts per chain and column; now 3.3).
 //
 // Same rows of SURVEY.md section 8a as dmcmc_solve.cu (a1-a7, a9, layout switch, init_ll).
+#include <algorithm>
 #include <cmath>
 
 #include "dmcmc_device.cuh"
@@ -334,11 +335,20 @@ __global__ void __launch_bounds__(256, 2) solve_big_kernel(const SolveParams p) 
 template <int D, bool PSI>
 static cudaError_t launch_big_model(int mode, const SolveParams &p, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
-    // warps per CTA: as many chains per CTA as possible (the per-step table record is staged once per
-    // CTA) while the grid still fills the machine twice over
+    // warps per CTA (all on one block: the per-step table record is staged once per CTA).  Every CTA of a launch runs
+    // for about the same time (same number of Euler steps in lockstep), so a grid of 1.19 waves costs two full rounds
+    // (measured: 528 CTAs on 444 slots).  Score = warps resident per SM averaged over the rounds the grid needs; ties
+    // go to the smaller CTA while the grid does not yet cover every SM, to the larger one otherwise.
     int warps = 1;
-    for (int w = 8; w >= 1; w >>= 1)
-        if ((long long)p.nblk * ((p.C + w * CH - 1) / (w * CH)) >= 2 * 148) { warps = w; break; }
+    double best = -1.0;
+    for (int w = 1; w <= 8; w <<= 1) {
+        const long long g = (long long)p.nblk * ((p.C + w * CH - 1) / (w * CH));
+        const size_t sm = (size_t)(2 * rec_size_big(D, PSI) + w * CH * 3 * D) * sizeof(double) + 1024;
+        const int cps = (int)std::max<size_t>(1, std::min<size_t>((size_t)227 * 1024 / sm, (size_t)(512 / (32 * w))));  // 128 registers
+        const double slots = 148.0 * cps, waves = (double)g / slots;
+        const double score = waves <= 1.0 ? (double)g * w / 148.0 : waves / std::ceil(waves) * cps * w;
+        if (score > best * 1.05 || (score >= best * 0.95 && g >= 148)) { best = std::max(best, score); warps = w; }
+    }
     const unsigned groups = (unsigned)((p.C + warps * CH - 1) / (warps * CH));
     const unsigned grid = groups * (unsigned)p.nblk;
     const unsigned threads = warps * 32;
