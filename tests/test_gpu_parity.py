@@ -140,7 +140,8 @@ def test_device_backward_filter_pinned_layout_vs_oracle(pkg, orc):
     including the pinned blocks' Psi, g, Qc.  The pinned tables carry 1/pin_eps conditioning: 1e-9."""
     P = pkg.problems
     for name, kw, half in [("fhn", dict(n_obs=9, C=2, dt=0.004), 1), ("l63", dict(n_obs=12, C=1, dt=1e-3), 2),
-                           ("lv", dict(n_obs=10, C=1, dt=0.01), 3)]:
+                           ("lv", dict(n_obs=10, C=1, dt=0.01), 3),
+                           ("fhn", dict(n_obs=3, C=1, dt=4e-4), 1)]:   # 250 grid points per interval: more than one per thread
         spec = _mk(pkg, name, **kw)
         o, e = _pair(pkg, orc, spec, upload=False)
         for pat in (0, 1):
