@@ -327,11 +327,16 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     for (int i = 0; i < SW; ++i) v[i] = sdw[s * SW + i];
                 }
             };
+            // FAST: two steps ahead -- one step of the fused recursion is ~30 issue cycles, about one shared-load latency;
+            // the generic step is long enough for one step ahead (and its 20-double records would not fit twice)
+            constexpr int AHEAD = FAST ? 2 : 1;
+            [[maybe_unused]] double rec1[AHEAD == 2 ? NREC : 1], sv1[AHEAD == 2 ? SW : 1];
             load_ops(0, rec, sv);
+            if constexpr (AHEAD == 2) load_ops(1, rec1, sv1);
 #pragma unroll 4
             for (int s = 0; s < nlive; ++s) {
                 double recn[NREC], svn[SW];
-                load_ops(min(s + 1, CT - 1), recn, svn);
+                load_ops(min(s + AHEAD, CT - 1), recn, svn);
                 if constexpr (FAST) {
                     if constexpr (REINV) lsum_a = fma(sv[2], sv[3], lsum_a);
                     fhn_step(fk, rec, sv[1], sv[0], x[0], x[1], lsum);  // sv = e_k, R_k, (two factors of the accepted G dt)
@@ -346,10 +351,17 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     for (int c = 0; c < D; ++c) x[c] = x[c] + dr[c] + sdwv[c];
                     ok = ok && MD::bound_ok(x);
                 }
+                if constexpr (AHEAD == 2) {
 #pragma unroll
-                for (int i = 0; i < NREC; ++i) rec[i] = recn[i];
+                    for (int i = 0; i < NREC; ++i) { rec[i] = rec1[i]; rec1[i] = recn[i]; }
 #pragma unroll
-                for (int i = 0; i < SW; ++i) sv[i] = svn[i];
+                    for (int i = 0; i < SW; ++i) { sv[i] = sv1[i]; sv1[i] = svn[i]; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NREC; ++i) rec[i] = recn[i];
+#pragma unroll
+                    for (int i = 0; i < SW; ++i) sv[i] = svn[i];
+                }
                 // every lane holds the same state: one (same-address) shared store per step.  No "memory" clobber: the
                 // stage is read only after the loop (behind __syncwarp), and the loop's table / increment loads must stay
                 // free to move ahead of these stores
