@@ -256,7 +256,15 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
             u.rho_s[b] = [new] * len(u.rho_s[b])
         return True
 
-    if all_imputation and len(updates) in (1, 2):
+    lst = mcmc.updates_and_decorators
+    has_switch = any(isinstance(u, BlockingChequerboardSwitch) for u in lst)
+    # the device loop alternates the pattern with every sweep: that is the schedule only when a switch decorator stands
+    # directly before every update (or there is no blocking at all)
+    switch_before_each = (len(lst) == 2 * len(updates) and
+                          all(isinstance(lst[2 * i], BlockingChequerboardSwitch) and lst[2 * i + 1] is updates[i]
+                              for i in range(len(updates))) and
+                          len({u.block_half_len for u in lst if isinstance(u, BlockingChequerboardSwitch)}) <= 1)
+    if all_imputation and len(updates) in (1, 2) and (not has_switch or switch_before_each):
         # Smoothing fast path: the whole schedule is PathImputation sweeps, so the device loops
         # (dmcmc_run_sweeps) between the points where the host must look: adaptation and saving.
         half_len = 0
@@ -265,6 +273,16 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
                 half_len = u.block_half_len
         nu = len(updates)
         stride = max(len(l[0]) for l in layouts)
+        n_switch = sum(isinstance(u, BlockingChequerboardSwitch) for u in mcmc.updates_and_decorators)
+        if half_len > 0 and n_switch % 2 == 1:
+            # every switch decorator moves to the other pattern; with an odd number of switches per pass of the update
+            # list the pattern an update sees alternates from one MCMC iteration to the next, so its histories must hold
+            # the larger of the two patterns' block counts (the shifted pattern has one block more)
+            stride = max(stride, max(len(chequerboard_layout(eng.rec_nobs, half_len, p)[0]) for p in (0, 1)))
+            for w in lws:
+                if w._acc.shape[2] < stride:
+                    shape = (num_mcmc_steps, C, stride)
+                    w._acc, w._ll, w._llp = np.zeros(shape, bool), np.full(shape, np.nan), np.full(shape, np.nan)
         k_adapt = min([u.adpt.v[0].adapt_every_k_steps for u in updates
                        if isinstance(u.adpt, AdaptationMultiPathImputation)] or [save_every])
         max_sw = max(1, min(k_adapt, save_every, num_mcmc_steps)) * nu

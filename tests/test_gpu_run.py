@@ -74,3 +74,16 @@ def test_parameter_inference_recovers_gamma(pkg):
     assert lws[1].acceptance_history.mean() > 0.02
     assert abs(th[-500:, 2].mean() - 1.5) < 0.35, th[-500:, 2].mean()
     assert np.all(th[:, [0, 1, 3, 4]] == th0[[0, 1, 3, 4]])
+
+
+def test_single_update_with_switch_alternates_patterns(pkg):
+    """[BlockingChequerboardSwitch, PathImputation]: the pattern alternates from one MCMC iteration to the next, and the
+    shifted pattern has one block more -- the histories must hold both (regression: the row stride was that of the
+    first pattern only)."""
+    data = pkg.problems.fhn_spec(n_obs=10, C=3, dt=0.01, rho=0.9)
+    mcmc = pkg.MCMC([pkg.BlockingChequerboardSwitch(1), pkg.PathImputation(0.9, "FitzHughNagumoAux")])
+    gws, lws = pkg.run_(mcmc, 7, data, seed=3)
+    acc, ll = lws[0].acceptance_history, lws[0].ll_history
+    assert acc.shape == (7, 3, 6) and ll.shape == (7, 3, 6)      # 5 blocks (pattern 0) / 6 blocks (pattern 1)
+    assert np.isfinite(ll[:, :, :5]).all()
+    assert np.isfinite(ll[1::2, :, 5]).all()                     # the sixth block exists in every other iteration
