@@ -18,7 +18,7 @@ class Config(C.Structure):
                 ("seed", C.c_uint64), ("pin_eps", C.c_double), ("store_noise", C.c_int32)]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # name -> (restype, argtypes); every symbol include/dmcmc.h declares
 SYMBOLS = {
@@ -43,6 +43,10 @@ SYMBOLS = {
                                    C.c_int32, _dp, _dp, _bp]),
     "dmcmc_host_alloc": (C.c_void_p, [C.c_size_t]),
     "dmcmc_host_free": (None, [C.c_void_p]),
+    "dmcmc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "dmcmc_host_unregister": (C.c_int, [C.c_void_p]),
+    "dmcmc_save_path_async": (C.c_int, [C.c_void_p, C.c_int32, _ip, C.c_int32, _ip]),
+    "dmcmc_save_path_wait": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "dmcmc_relayout": (C.c_int, [C.c_void_p, C.c_int32, _ip, _ip, _ip]),
     "dmcmc_param_loglik": (C.c_int, [C.c_void_p, _dp, C.c_int32, C.c_int32, _dp, _bp]),
     "dmcmc_param_commit": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -63,6 +67,7 @@ SYMBOLS = {
     "dmcmc_accept_counts": (C.c_int, [C.c_void_p, _lp, _lp]),
     "dmcmc_kernel_times": (C.c_int, [C.c_void_p, _dp, _lp]),
     "dmcmc_device_bytes": (C.c_int64, [C.c_void_p]),
+    "dmcmc_fp64_peak": (C.c_double, [C.c_int32]),
     "dmcmc_set_threads": (C.c_int, [C.c_void_p, C.c_int32]),
     "dmcmc_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "dmcmc_launch_count": (C.c_int64, [C.c_void_p]),

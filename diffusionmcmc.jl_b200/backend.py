@@ -13,6 +13,8 @@ Differences from the reference that are deliberate:
   * save_path! fires once per iteration, not once per block (src/run!_alterations.jl:45 quirk);
   * blocking is implemented (the reference has only the decorator and TODOs).
 """
+import copy
+
 import numpy as np
 
 from .adaptation import (AdaptationMultiPathImputation, AdaptationPathImputation, NoAdaptation)
@@ -140,10 +142,11 @@ class DiffusionLocalWorkspace:
     `ll_history[it][block]`, `ll_prop_history[it][block]` (with a chain axis in between when
     n_chains > 1)."""
 
-    def __init__(self, update, layout, num_mcmc_steps, n_chains, kind):
+    def __init__(self, update, layout, num_mcmc_steps, n_chains, kind, nblk=None):
         self.update, self.layout, self.kind = update, layout, kind
-        nblk = len(layout[0]) if kind == "imputation" else 1
-        shape = (num_mcmc_steps, n_chains, nblk)
+        if nblk is None:
+            nblk = len(layout[0]) if kind == "imputation" else 1
+        shape = (num_mcmc_steps, n_chains, nblk)   # nblk: the most blocks any pattern of this update has
         self._acc = np.zeros(shape, bool)
         self._ll = np.zeros(shape)
         self._llp = np.zeros(shape)
@@ -174,32 +177,102 @@ class DiffusionGlobalWorkspace:
         self.state_history = []
 
 
-def _layouts_for_updates(rec_nobs, updates_and_decorators):
-    """extra_schedule_params (src/schedule.jl:15-75) with update_layout / update_layout_type!
-    defined: each BlockingChequerboardSwitch moves to the next chequerboard pattern."""
-    layouts, types = [], []
-    cur = chequerboard_layout(rec_nobs, 0, 0)
-    cur_type, n_switch = 1, 0
-    for u in updates_and_decorators:
-        if isinstance(u, BlockingChequerboardSwitch):
-            cur = chequerboard_layout(rec_nobs, u.block_half_len, n_switch % 2)
-            n_switch += 1
-            cur_type = 1 + (n_switch % 2) + 1
-        else:
-            layouts.append(cur)
-            types.append(tuple(cur_type for _ in rec_nobs))
-    return layouts, tuple(types)
+class _BlockingPlan:
+    """extra_schedule_params (src/schedule.jl:15-75) with `update_layout` / `update_layout_type!` defined (the
+    reference calls them but defines neither): every BlockingChequerboardSwitch in the update list moves to the other
+    chequerboard pattern, the first one to pattern 0.  The reference asserts an even number of switches per pass
+    (src/schedule.jl:89), so that an update always sees the same layout; here an odd number is allowed as well, and
+    then the switch count -- hence the pattern an update runs under -- carries over from one MCMC iteration to the
+    next (`[Switch, PathImputation]` alternates the two patterns, which is what makes the sampler move the block
+    end points)."""
+
+    def __init__(self, rec_nobs, updates_and_decorators):
+        self.rec_nobs = rec_nobs
+        self.half_len, self.k_before = [], []   # per update: block_half_len in force (0: none), switches passed so far
+        h, k = 0, 0
+        for u in updates_and_decorators:
+            if isinstance(u, BlockingChequerboardSwitch):
+                h, k = int(u.block_half_len), k + 1
+            else:
+                self.half_len.append(h)
+                self.k_before.append(k)
+        self.n_switch = k
+        self._cache = {}
+
+    def pattern(self, ui, mcmciter):
+        """chequerboard pattern (0 / 1) of update `ui` (0-based) in MCMC iteration `mcmciter` (1-based); None = no blocking"""
+        if self.half_len[ui] <= 0 or self.k_before[ui] == 0:
+            return None
+        return ((mcmciter - 1) * self.n_switch + self.k_before[ui] - 1) % 2
+
+    def patterns_seen(self, ui):
+        if self.pattern(ui, 1) is None:
+            return [None]
+        return sorted({self.pattern(ui, 1), self.pattern(ui, 2)})
+
+    def layout(self, ui, pat):
+        key = (self.half_len[ui], pat)
+        if key not in self._cache:
+            self._cache[key] = chequerboard_layout(self.rec_nobs, 0, 0) if pat is None else \
+                chequerboard_layout(self.rec_nobs, self.half_len[ui], pat)
+        return self._cache[key]
+
+    def layout_types(self):
+        """layout type per update and recording in the first pass (src/schedule.jl:62-64), for MCMCSchedule.same_layout"""
+        return tuple(tuple(1 if self.pattern(ui, 1) is None else 2 + self.pattern(ui, 1) for _ in self.rec_nobs)
+                     for ui in range(len(self.half_len)))
+
+
+class _ImputationState:
+    """pCN memory and its adaptation for ONE (update, chequerboard pattern): rho_s[block][interval] and one
+    AdaptationPathImputation per block (src/updates.jl:53-74, src/adaptation.jl:122-167).  An update that alternates
+    between the two patterns keeps two of these: block b of pattern 0 and block b of pattern 1 are different blocks."""
+
+    def __init__(self, update, layout):
+        self.layout = layout
+        n_iv = [int(e - a + 1) for a, e in zip(layout[0], layout[1])]
+        first = update.rho_s[0][0]
+        self.rho_s = [list(r) for r in update.rho_s[:len(n_iv)]]
+        while len(self.rho_s) < len(n_iv):
+            self.rho_s.append([first])
+        for r, n in zip(self.rho_s, n_iv):
+            while len(r) < n:
+                r.append(r[0])
+            del r[n:]
+        self.adpt = copy.deepcopy(update.adpt)
+        if isinstance(self.adpt, AdaptationMultiPathImputation):
+            self.adpt.resize(len(n_iv))
+
+    def rho_per_interval(self, J):
+        rho = np.zeros(J)
+        for r, a, e in zip(self.rho_s, self.layout[0], self.layout[1]):
+            rho[a:e + 1] = r[:e - a + 1]
+        return rho
+
+    def register_and_adapt(self, acc_counts, proposed, mcmciter):
+        """register! + time_to_update + readjust! (src/adaptation.jl:82-90, :100-113, :143-149)."""
+        if not isinstance(self.adpt, AdaptationMultiPathImputation):
+            return False
+        self.adpt.register(acc_counts, proposed)
+        if not self.adpt.time_to_update():
+            return False
+        for b, a in enumerate(self.adpt.v[:len(self.rho_s)]):
+            new = a.readjust(self.rho_s[b][0], mcmciter)
+            self.rho_s[b] = [new] * len(self.rho_s[b])
+        return True
 
 
 def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, path_buffer_size=1,
          n_chains=None, device=0, seed=0, chain_offset=0, save_every=100, rng=None,
-         exclude_updates=()):
+         exclude_updates=(), save_chains=(0,)):
     """`run!(mcmc, num_mcmc_steps, data, θinit, callbacks; dt, path_buffer_size, ...)`.
 
     `data` is a spec dict from problems.make_spec (the `AllObservations` stand-in).  When `dt`
     is given the imputation grids are rebuilt from the observation times
     (OBS.setup_time_grids, src/workspaces.jl:164-170; default there is 0.01).
-    Returns (global_ws, local_wss)."""
+    `save_every` replaces the reference's hard-coded 100 (src/run!_alterations.jl:52); `save_chains` are the chains
+    whose glued accepted paths go into `XX_buffer` (one: `x` is [points][d] like the reference's; several:
+    [chain][points][d]).  Returns (global_ws, local_wss)."""
     spec = dict(data)
     if dt is not None:
         N, t = setup_time_grids(spec.get("t0", 0.0), spec["obs_times"], dt)
@@ -208,16 +281,24 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
         spec["theta"] = np.asarray(theta_init, float)
     if n_chains is not None and spec["x0"].shape[0] != n_chains:
         spec["x0"] = np.broadcast_to(spec["x0"][:1], (n_chains,) + spec["x0"].shape[1:]).copy()
+    updates = mcmc.updates
+    if spec["x0"].shape[0] > 1 and any(not isinstance(u, PathImputation) for u in updates):
+        # every chain of a context shares ONE theta (the tables are shared): a joint Metropolis step over C chains
+        # would target prior x likelihood^C.  Chains are for smoothing; for inference run one chain per context.
+        raise ValueError("parameter updates need n_chains == 1: the chains of one context share the parameter, "
+                         "so a joint accept/reject over them would count the recording n_chains times")
     rng = rng or np.random.default_rng(seed)
     eng = Engine(spec, device=device, seed=seed, chain_offset=chain_offset)
     eng.init_paths()  # init_paths! + init_ll! (src/workspaces.jl:80-92, :425-431)
     C, J = eng.C, eng.J
+    nu = len(updates)
 
-    layouts, layout_types = _layouts_for_updates(eng.rec_nobs, mcmc.updates_and_decorators)
-    updates = mcmc.updates
-    for u, lay in zip(updates, layouts):
+    plan = _BlockingPlan(eng.rec_nobs, mcmc.updates_and_decorators)
+    states = {}   # (update index, pattern) -> _ImputationState
+    for ui, u in enumerate(updates):
         if isinstance(u, PathImputation):
-            u.init_update([int(e - a + 1) for a, e in zip(lay[0], lay[1])])
+            for pat in plan.patterns_seen(ui):
+                states[(ui, pat)] = _ImputationState(u, plan.layout(ui, pat))
 
     # glued time axis per recording (PathSavingBuffer ctor, src/path_saving_buffer.jl:33-44)
     times, j0 = [], 0
@@ -225,14 +306,18 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
         segs = [spec["t"][eng.pt_off[j]:eng.pt_off[j + 1]] for j in range(j0, j0 + int(n))]
         times.append(np.concatenate([s[:-1] for s in segs] + [segs[-1][-1:]]))
         j0 += int(n)
-    buf = PathSavingBuffer(times, eng.d, path_buffer_size)
+    save_chains = [int(c) for c in save_chains]
+    buf = PathSavingBuffer(times, eng.d, path_buffer_size, n_chains=len(save_chains))
     gws = DiffusionGlobalWorkspace(eng, spec, buf, list(range(len(spec["theta"]))))
-    lws = [DiffusionLocalWorkspace(u, lay, num_mcmc_steps, C,
-                                   "imputation" if isinstance(u, PathImputation) else "param")
-           for u, lay in zip(updates, layouts)]
+    lws = []
+    for ui, u in enumerate(updates):
+        if isinstance(u, PathImputation):
+            nb = max(len(plan.layout(ui, pat)[0]) for pat in plan.patterns_seen(ui))
+            lws.append(DiffusionLocalWorkspace(u, plan.layout(ui, plan.pattern(ui, 1)), num_mcmc_steps, C, "imputation", nb))
+        else:
+            lws.append(DiffusionLocalWorkspace(u, plan.layout(ui, plan.pattern(ui, 1)), num_mcmc_steps, C, "param", 1))
 
-    schedule = MCMCSchedule(num_mcmc_steps, len(updates), exclude_updates,
-                            extra_info=dict(layout_types=layout_types))
+    schedule = MCMCSchedule(num_mcmc_steps, nu, exclude_updates, extra_info=dict(layout_types=plan.layout_types()))
     cur_layout = chequerboard_layout(eng.rec_nobs, 0, 0)
     theta = np.array(spec["theta"], float)
     all_imputation = all(isinstance(u, PathImputation) for u in updates) and not exclude_updates \
@@ -241,95 +326,96 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
     def same(l1, l2):
         return all(np.array_equal(a, b) for a, b in zip(l1, l2))
 
-    def save_paths():
-        buf.save([eng.download_path(0, r) for r in range(eng.R)])
+    pending_save = []
 
-    def adapt(u, lay, mcmciter):
-        if not isinstance(u.adpt, AdaptationMultiPathImputation):
-            return False
-        acc, prop = eng.accept_counts()
-        u.adpt.register(acc, prop)
-        if not u.adpt.time_to_update():
-            return False
-        for b, a in enumerate(u.adpt.v[:len(u.rho_s)]):   # readjust!, src/adaptation.jl:143-149
-            new = a.readjust(u.rho_s[b][0], mcmciter)
-            u.rho_s[b] = [new] * len(u.rho_s[b])
-        return True
+    def save_paths():
+        """save! (src/path_saving_buffer.jl:52): the snapshot is taken on the device now, the copy to the host overlaps
+        the sweeps that follow and is collected at the next save (or at the end)."""
+        collect_saves()
+        pending_save.append([eng.save_path_async(save_chains, r) for r in range(eng.R)])
+
+    def collect_saves():
+        while pending_save:
+            glued = [eng.save_path_wait(tk) for tk in pending_save.pop(0)]
+            buf.save([g[0] if len(save_chains) == 1 else g for g in glued])
+
+    def finish():
+        collect_saves()
+        for (ui, pat), st in states.items():      # report the adapted rho back on the update object
+            if pat == plan.pattern(ui, max(1, num_mcmc_steps)):
+                updates[ui].rho_s = [list(r) for r in st.rho_s]
+                updates[ui].adpt = st.adpt
+        return gws, lws
 
     lst = mcmc.updates_and_decorators
-    has_switch = any(isinstance(u, BlockingChequerboardSwitch) for u in lst)
+    has_switch = plan.n_switch > 0
     # the device loop alternates the pattern with every sweep: that is the schedule only when a switch decorator stands
     # directly before every update (or there is no blocking at all)
-    switch_before_each = (len(lst) == 2 * len(updates) and
+    switch_before_each = (len(lst) == 2 * nu and
                           all(isinstance(lst[2 * i], BlockingChequerboardSwitch) and lst[2 * i + 1] is updates[i]
-                              for i in range(len(updates))) and
+                              for i in range(nu)) and
                           len({u.block_half_len for u in lst if isinstance(u, BlockingChequerboardSwitch)}) <= 1)
-    if all_imputation and len(updates) in (1, 2) and (not has_switch or switch_before_each):
+    if all_imputation and nu in (1, 2) and (not has_switch or switch_before_each):
         # Smoothing fast path: the whole schedule is PathImputation sweeps, so the device loops
         # (dmcmc_run_sweeps) between the points where the host must look: adaptation and saving.
-        half_len = 0
-        for u in mcmc.updates_and_decorators:
-            if isinstance(u, BlockingChequerboardSwitch):
-                half_len = u.block_half_len
-        nu = len(updates)
-        stride = max(len(l[0]) for l in layouts)
-        n_switch = sum(isinstance(u, BlockingChequerboardSwitch) for u in mcmc.updates_and_decorators)
-        if half_len > 0 and n_switch % 2 == 1:
-            # every switch decorator moves to the other pattern; with an odd number of switches per pass of the update
-            # list the pattern an update sees alternates from one MCMC iteration to the next, so its histories must hold
-            # the larger of the two patterns' block counts (the shifted pattern has one block more)
-            stride = max(stride, max(len(chequerboard_layout(eng.rec_nobs, half_len, p)[0]) for p in (0, 1)))
-            for w in lws:
-                if w._acc.shape[2] < stride:
-                    shape = (num_mcmc_steps, C, stride)
-                    w._acc, w._ll, w._llp = np.zeros(shape, bool), np.full(shape, np.nan), np.full(shape, np.nan)
-        k_adapt = min([u.adpt.v[0].adapt_every_k_steps for u in updates
-                       if isinstance(u.adpt, AdaptationMultiPathImputation)] or [save_every])
+        half_len = plan.half_len[0] if has_switch else 0
+        stride = max(w._acc.shape[2] for w in lws)
+        k_adapt = min([st.adpt.v[0].adapt_every_k_steps for st in states.values()
+                       if isinstance(st.adpt, AdaptationMultiPathImputation)] or [save_every])
         max_sw = max(1, min(k_adapt, save_every, num_mcmc_steps)) * nu
-        # ordinary host arrays: the library stages through its own pinned rings (dmcmc_run_sweeps)
-        rho_buf = np.empty((max_sw, J), np.float64)
-        hist_buf = (np.empty((max_sw, C, stride), np.float64), np.empty((max_sw, C, stride), np.float64),
-                    np.empty((max_sw, C, stride), np.uint8))
+        # pinned host arrays (dmcmc_host_alloc): the history rows land in them by DMA, no staging copy
+        rho_buf = eng.pinned((max_sw, J), np.float64)
+        hist_buf = (eng.pinned((max_sw, C, stride), np.float64), eng.pinned((max_sw, C, stride), np.float64),
+                    eng.pinned((max_sw, C, stride), np.uint8))
         it = 0
         while it < num_mcmc_steps:
             chunk = min(num_mcmc_steps - it, max(1, min(k_adapt, save_every - (it % save_every))))
             nsw = chunk * nu
-            rho_sched = rho_buf[:nsw]
+            sweep_state = []
             for s in range(nsw):
-                u, lay = updates[s % nu], layouts[s % nu]
-                rho_sched[s] = u.rho_per_interval(lay[0], lay[1], J)
+                ui, mcmciter = s % nu, it + s // nu + 1
+                sweep_state.append(states[(ui, plan.pattern(ui, mcmciter))])
+                rho_buf[s] = sweep_state[-1].rho_per_interval(J)
             hist = tuple(h[:nsw] for h in hist_buf)
-            if half_len == 0 and not same(cur_layout, layouts[0]):
-                eng.relayout(*layouts[0])
-            eng.run_sweeps(it * nu, nsw, half_len, 0, rho_sched, hist)
-            cur_layout = layouts[(nsw - 1) % nu]
+            if half_len == 0 and not same(cur_layout, sweep_state[0].layout):
+                eng.relayout(*sweep_state[0].layout)
+            first_pattern = plan.pattern(0, it + 1) or 0
+            eng.run_sweeps(it * nu, nsw, half_len, first_pattern, rho_buf[:nsw], hist)
+            cur_layout = sweep_state[-1].layout
             eng.nblk = len(cur_layout[0])
-            for s in range(nsw):
-                w = lws[s % nu]
-                nb = w._acc.shape[2]
-                w._llp[it + s // nu] = hist[0][s][:, :nb]
-                w._ll[it + s // nu] = hist[1][s][:, :nb]
-                w._acc[it + s // nu] = hist[2][s][:, :nb].astype(bool)
+            for s, st in enumerate(sweep_state):
+                w, row = lws[s % nu], it + s // nu
+                nb = len(st.layout[0])
+                w._llp[row, :, :nb] = hist[0][s][:, :nb]
+                w._ll[row, :, :nb] = hist[1][s][:, :nb]
+                w._acc[row, :, :nb] = hist[2][s][:, :nb].astype(bool)
+                w._llp[row, :, nb:] = np.nan     # blocks this sweep's pattern does not have
+                w._ll[row, :, nb:] = np.nan
+                st.register_and_adapt(hist[2][s][:, :nb].sum(axis=0, dtype=np.int64), np.full(nb, C), row + 1)
             it += chunk
-            for u, lay in zip(updates, layouts):
-                adapt(u, lay, it)
             if it % save_every == 0:
                 save_paths()
         gws.state_history = [theta.copy() for _ in range(num_mcmc_steps)]
-        return gws, lws
+        return finish()
 
     # General path: the schedule is walked update by update (src/run!_alterations.jl:5-26, :357-369)
     for step in schedule:
         pidx, mcmciter = step.pidx - 1, step.mcmciter
-        u, lay, w = updates[pidx], layouts[pidx], lws[pidx]
+        u, w = updates[pidx], lws[pidx]
+        pat = plan.pattern(pidx, mcmciter)
+        lay = plan.layout(pidx, pat)
         if not same(cur_layout, lay):   # update_workspaces!: layout changed (src/workspaces.jl:467-471)
             eng.relayout(*lay)
             cur_layout = lay
         if isinstance(u, PathImputation):
-            eng.set_rho(u.rho_per_interval(lay[0], lay[1], J))
-            llp, ll, acc = eng.impute(mcmciter * len(updates) + pidx)
-            w._llp[mcmciter - 1], w._ll[mcmciter - 1], w._acc[mcmciter - 1] = llp, ll, acc
-            adapt(u, lay, mcmciter)
+            st = states[(pidx, pat)]
+            nb = len(lay[0])
+            eng.set_rho(st.rho_per_interval(J))
+            llp, ll, acc = eng.impute(mcmciter * nu + pidx)
+            w._llp[mcmciter - 1, :, :nb], w._ll[mcmciter - 1, :, :nb], w._acc[mcmciter - 1, :, :nb] = llp, ll, acc
+            w._llp[mcmciter - 1, :, nb:] = np.nan
+            w._ll[mcmciter - 1, :, nb:] = np.nan
+            st.register_and_adapt(acc.sum(axis=0, dtype=np.int64), np.full(nb, C), mcmciter)
             if mcmciter % save_every == 0 and step.pidx == 1:   # save_path!, src/run!_alterations.jl:51-54
                 save_paths()
         elif isinstance(u, DiffusionConjugGsnUpdate):
@@ -346,7 +432,7 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
             th_prop = u.proposal(theta, rng)                                   # proposal!
             llp, ok = eng.param_loglik(th_prop, critical=u.critical)           # set_proposal!
             ll = eng.get_ll()
-            # one decision for all blocks and chains (src/run!_alterations.jl:367): E > -(Delta)
+            # one decision for all blocks (src/run!_alterations.jl:367): E > -(Delta)
             delta = (llp.sum() - ll.sum() + u.log_prior(th_prop) - u.log_prior(theta)
                      + u.log_transition_ratio(theta, th_prop))
             accepted = bool(ok.all()) and (rng.exponential() > -delta)
@@ -356,14 +442,13 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
             w._llp[mcmciter - 1, :, 0] = llp.sum(axis=1)
             w._ll[mcmciter - 1, :, 0] = (llp if accepted else ll).sum(axis=1)
             w._acc[mcmciter - 1, :, 0] = accepted
-        if step.pidx == len(updates) or True:
-            if len(gws.state_history) < mcmciter:
-                gws.state_history.append(theta.copy())
-            else:
-                gws.state_history[mcmciter - 1] = theta.copy()
+        if len(gws.state_history) < mcmciter:
+            gws.state_history.append(theta.copy())
+        else:
+            gws.state_history[mcmciter - 1] = theta.copy()
         for cb in callbacks:
             cb(gws, lws, step)
-    return gws, lws
+    return finish()
 
 
 class ImputationRunner:
@@ -383,13 +468,13 @@ class ImputationRunner:
         self.sweeps += n
 
     def reserve_host(self, n):
-        """Host buffers (ordinary NumPy arrays, as a Julia caller would pass) for n sweeps of rho
-        schedule and history rows, allocated and touched once."""
+        """Pinned host buffers (dmcmc_host_alloc; a Julia caller would wrap them as Arrays, or register its own with
+        dmcmc_host_register) for n sweeps of rho schedule and history rows, allocated and touched once."""
         e = self.e
         if self._host is None or self._host[0].shape[0] < n:
-            self._host = (np.empty((n, e.J), np.float64), np.empty((n, e.C, self.stride), np.float64),
-                          np.empty((n, e.C, self.stride), np.float64),
-                          np.empty((n, e.C, self.stride), np.uint8))
+            self._host = (e.pinned((n, e.J), np.float64), e.pinned((n, e.C, self.stride), np.float64),
+                          e.pinned((n, e.C, self.stride), np.float64),
+                          e.pinned((n, e.C, self.stride), np.uint8))
             for a in self._host:
                 a[...] = 0  # touch the pages
 

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -75,15 +77,44 @@ struct Law {
 }  // namespace
 
 // staging rings and streams of dmcmc_run_sweeps (allocated on first use, kept for the context's lifetime)
+constexpr int SWEEP_RING = 16;   // ring slots: sweeps whose history rows may be in flight
+constexpr int NDRAIN = 4;        // drainer threads (pageable caller buffers only)
+
+// what the drainer threads of one dmcmc_run_sweeps call copy: pinned ring -> the caller's pageable arrays
+struct DrainJob {
+    int n_sweeps = 0;
+    size_t row = 0, slot_bytes = 0;
+    double *llp = nullptr, *ll = nullptr;
+    uint8_t *acc = nullptr;
+};
+
 struct SweepIO {
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t kernel_done[8] = {}, rho_ready[8] = {}, copied[8] = {};
+    cudaEvent_t kernel_done[SWEEP_RING] = {}, copied[SWEEP_RING] = {};
     DevBuf<uint8_t> d_hist;   // [R][ll deg row | ll row | accepted row]
-    DevBuf<double> d_rho;     // [R][J]
-    uint8_t *h_hist = nullptr;  // pinned mirror of d_hist
+    DevBuf<double> d_rho;     // [chunk][J]
+    uint8_t *h_hist = nullptr;  // pinned mirror of d_hist (pageable caller buffers only)
     size_t h_hist_bytes = 0;
-    double *h_rho = nullptr;    // pinned [R][J]
-    size_t h_rho_n = 0;
+    // persistent drainer pool: started by the first call that needs it, parked on cv_job between calls
+    std::thread drainer[NDRAIN];
+    bool pool_started = false, stop = false;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    uint64_t gen = 0;
+    int done = 0;
+    DrainJob job;
+    std::atomic<int> recorded{0};
+    std::atomic<bool> failed{false};
+    std::atomic<int> drained[NDRAIN];
+};
+
+// device snapshots of glued accepted paths on their way to the host (dmcmc_save_path_async / _wait)
+struct PathSave {
+    DevBuf<double> d_buf;
+    double *h_buf = nullptr;   // pinned
+    size_t h_n = 0, n = 0;
+    cudaEvent_t snap = nullptr, landed = nullptr;
+    bool busy = false;
 };
 
 struct dmcmc_ctx {
@@ -125,6 +156,8 @@ struct dmcmc_ctx {
     bool fast_step = true;  // allow model-specific fused steps (dmcmc_set_fast_step)
     int coop = -1;          // warp-per-unit imputation kernel: -1 auto, 0 never, 1 always (dmcmc_set_cooperative)
     SweepIO io;
+    PathSave saves[4];
+    cudaStream_t save_stream = nullptr;
 };
 
 namespace {
@@ -545,14 +578,28 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     if (ctx->sw0) { cudaEventDestroy(ctx->sw0); cudaEventDestroy(ctx->sw1); }
     {
         SweepIO &io = ctx->io;
+        if (io.pool_started) {
+            {
+                std::lock_guard<std::mutex> lk(io.m);
+                io.stop = true;
+            }
+            io.cv_job.notify_all();
+            for (auto &t : io.drainer)
+                if (t.joinable()) t.join();
+        }
         if (io.s_in) {
             cudaStreamSynchronize(io.s_in); cudaStreamSynchronize(io.s_out);
-            for (int i = 0; i < 8; ++i) { cudaEventDestroy(io.kernel_done[i]); cudaEventDestroy(io.rho_ready[i]); cudaEventDestroy(io.copied[i]); }
+            for (int i = 0; i < SWEEP_RING; ++i) { cudaEventDestroy(io.kernel_done[i]); cudaEventDestroy(io.copied[i]); }
             cudaStreamDestroy(io.s_in); cudaStreamDestroy(io.s_out);
         }
         io.d_hist.release(); io.d_rho.release();
         if (io.h_hist) cudaFreeHost(io.h_hist);
-        if (io.h_rho) cudaFreeHost(io.h_rho);
+        if (ctx->save_stream) { cudaStreamSynchronize(ctx->save_stream); cudaStreamDestroy(ctx->save_stream); }
+        for (auto &sv : ctx->saves) {
+            sv.d_buf.release();
+            if (sv.h_buf) cudaFreeHost(sv.h_buf);
+            if (sv.snap) { cudaEventDestroy(sv.snap); cudaEventDestroy(sv.landed); }
+        }
     }
     auto rel_law = [](Law &l) { l.d_auxB.release(); l.d_auxbeta.release(); l.d_auxatil.release(); };
     rel_law(ctx->law[0]);
@@ -1043,13 +1090,58 @@ static int relayout_async(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const
     return materialize_async(ctx);
 }
 
-// Host side of the sweep loop.  The caller's buffers are ordinary host memory (Julia arrays); the
-// library stages through its own small pinned rings, which stay hot in the IOMMU/TLB (DMA into a
-// fresh multi-hundred-MB pinned history buffer was measured 3-6x slower than into a re-used ring):
-//   copy-in stream : rho row of sweep k   host ring -> device ring          (waits for kernel k-R)
-//   compute stream : kernel k                                               (waits for rho k, and for D2H k-R)
-//   copy-out stream: history rows of k    device ring -> pinned host ring   (waits for kernel k)
-//   drainer thread : pinned host ring -> caller's arrays, then frees the ring slot
+// is [p, p + bytes) page-locked host memory (cudaHostAlloc / cudaHostRegister)?  Then DMA can land in it directly.
+static bool is_pinned(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static void drainer_main(dmcmc_ctx *ctx, int t) {
+    SweepIO &io = ctx->io;
+    cudaSetDevice(ctx->cfg.device);
+    prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // 1 us instead of the default 50 us on this thread's sleeps
+    uint64_t seen = 0;
+    for (;;) {
+        DrainJob j;
+        {
+            std::unique_lock<std::mutex> lk(io.m);
+            io.cv_job.wait(lk, [&] { return io.stop || io.gen != seen; });
+            if (io.stop) return;
+            seen = io.gen;
+            j = io.job;
+        }
+        for (int it = t; it < j.n_sweeps; it += NDRAIN) {
+            bool bail = false;
+            while (io.recorded.load(std::memory_order_acquire) <= it) {  // sleep, do not spin: one process per GPU
+                if (io.failed.load(std::memory_order_relaxed)) { bail = true; break; }  // shares the host cores with 7 others
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+            if (bail) break;
+            const int slot = it % SWEEP_RING;
+            if (cudaEventSynchronize(io.copied[slot]) != cudaSuccess) { io.failed = true; break; }
+            const uint8_t *src = io.h_hist + j.slot_bytes * slot;
+            if (j.llp) std::memcpy(j.llp + j.row * it, src, j.row * sizeof(double));
+            if (j.ll) std::memcpy(j.ll + j.row * it, src + j.row * sizeof(double), j.row * sizeof(double));
+            if (j.acc) std::memcpy(j.acc + j.row * it, src + 2 * j.row * sizeof(double), j.row);
+            io.drained[t].fetch_add(1, std::memory_order_release);
+        }
+        {
+            std::lock_guard<std::mutex> lk(io.m);
+            ++io.done;
+        }
+        io.cv_done.notify_one();
+    }
+}
+
+// Host side of the sweep loop (what `run!` drives for a smoothing chain):
+//   compute stream : [rho schedule of the chunk, one H2D]  kernel 0, kernel 1, ...   (kernel k waits for D2H k-R)
+//   copy-out stream: history rows of sweep k: device ring -> host                   (waits for kernel k)
+// PINNED caller buffers (dmcmc_host_alloc / dmcmc_host_register): the rows are DMA'd straight into the caller's
+// arrays -- every byte crosses host memory once and no host thread touches it; the call only enqueues and then waits.
+// PAGEABLE caller buffers: the rows land in the library's small pinned ring (which stays hot in the IOMMU/TLB) and
+// a pool of drainer threads, kept parked between calls, moves them into the caller's arrays.
 int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
                      int32_t first_pattern, const double *rho_sched, int32_t nblk_stride,
                      double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted) {
@@ -1072,97 +1164,75 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
     const int nbmax = std::max(nb[0], nb[1]);
     REQUIRE(!want_hist || nblk_stride >= nbmax, "dmcmc_run_sweeps: nblk_stride smaller than the number of blocks");
     const size_t row = (size_t)ctx->C * (want_hist ? nblk_stride : nbmax);  // units per history row
-    constexpr int R = 8;                                                    // ring slots
+    constexpr int R = SWEEP_RING;
     const size_t slot_bytes = 2 * row * sizeof(double) + ((row + 15) & ~(size_t)15);  // [ll deg | ll | accepted], 16-byte aligned
     const size_t J = (size_t)ctx->J;
     SweepIO &io = ctx->io;
-    if (want_hist) {
-        CK(io.d_hist.ensure(slot_bytes * R));
-        if (io.h_hist_bytes < slot_bytes * R) {
-            if (io.h_hist) cudaFreeHost(io.h_hist);
-            io.h_hist = nullptr; io.h_hist_bytes = 0;
-            CK(cudaHostAlloc((void **)&io.h_hist, slot_bytes * R, cudaHostAllocDefault));
-            io.h_hist_bytes = slot_bytes * R;
-        }
-    }
-    if (rho_sched) {
-        CK(io.d_rho.ensure(J * R));
-        if (!io.h_rho || io.h_rho_n < J * R) {
-            if (io.h_rho) cudaFreeHost(io.h_rho);
-            io.h_rho = nullptr; io.h_rho_n = 0;
-            CK(cudaHostAlloc((void **)&io.h_rho, J * R * sizeof(double), cudaHostAllocDefault));
-            io.h_rho_n = J * R;
-        }
+    const bool direct = want_hist && is_pinned(hist_ll_prop) && is_pinned(hist_ll) && is_pinned(hist_accepted);
+    const bool drain = want_hist && !direct && n_sweeps > 0;
+    if (want_hist) CK(io.d_hist.ensure(slot_bytes * R));
+    if (drain && io.h_hist_bytes < slot_bytes * R) {
+        if (io.h_hist) cudaFreeHost(io.h_hist);
+        io.h_hist = nullptr; io.h_hist_bytes = 0;
+        CK(cudaHostAlloc((void **)&io.h_hist, slot_bytes * R, cudaHostAllocDefault));
+        io.h_hist_bytes = slot_bytes * R;
     }
     if (!io.s_in) {
         CK(cudaStreamCreateWithFlags(&io.s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&io.s_out, cudaStreamNonBlocking));
         for (int i = 0; i < R; ++i) {
             CK(cudaEventCreateWithFlags(&io.kernel_done[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&io.rho_ready[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&io.copied[i], cudaEventDisableTiming | cudaEventBlockingSync));
         }
     }
-    // drainers: pinned ring -> caller's arrays.  One core copies ~10 GB/s, which is just the rate the C3
-    // histories arrive at (879 KB per 80 us sweep), and every hand-over costs two wake-ups (the sleep below and
-    // the blocking event wait: 50-100 us each on a loaded host, where eight ranks share the cores).  Four threads
-    // take every fourth sweep, so a thread has ~300 us per sweep; they sleep, they do not spin.
-    constexpr int MAXDRAIN = 8;
-    static const int env_drain = getenv("DMCMC_DRAIN_THREADS") ? atoi(getenv("DMCMC_DRAIN_THREADS")) : 0;  // tuning override: 1, 2, 4, 8
-    const int NDRAIN = (env_drain == 1 || env_drain == 2 || env_drain == 4 || env_drain == 8) ? env_drain : 4;
-    std::atomic<int> recorded{0};
-    std::atomic<int> drained[MAXDRAIN];  // per thread: sweeps it = t, t + NDRAIN, ... finished so far
-    for (auto &d : drained) d.store(0);
-    std::atomic<bool> failed{false};
-    std::thread drainer[MAXDRAIN];
-    if (want_hist && n_sweeps > 0) {
-        for (int t = 0; t < NDRAIN; ++t)
-            drainer[t] = std::thread([&, t]() {
-                cudaSetDevice(ctx->cfg.device);
-                prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // 1 us instead of the default 50 us on this thread's sleeps
-                for (int it = t; it < n_sweeps; it += NDRAIN) {
-                    while (recorded.load(std::memory_order_acquire) <= it) {  // sleep, do not spin: one process per GPU
-                        if (failed.load(std::memory_order_relaxed)) return;  // shares the host cores with 7 others
-                        std::this_thread::sleep_for(std::chrono::microseconds(20));
-                    }
-                    const int slot = it % R;
-                    if (cudaEventSynchronize(io.copied[slot]) != cudaSuccess) { failed = true; return; }
-                    const uint8_t *src = io.h_hist + slot_bytes * slot;
-                    if (hist_ll_prop) std::memcpy(hist_ll_prop + row * it, src, row * sizeof(double));
-                    if (hist_ll) std::memcpy(hist_ll + row * it, src + row * sizeof(double), row * sizeof(double));
-                    if (hist_accepted) std::memcpy(hist_accepted + row * it, src + 2 * row * sizeof(double), row);
-                    drained[t].fetch_add(1, std::memory_order_release);
-                }
-            });
+    if (drain) {
+        // Drainers: pinned ring -> caller's arrays.  One core copies ~10 GB/s, which is just the rate the C3 histories
+        // arrive at (879 KB per 80 us sweep), and every hand-over costs two wake-ups: NDRAIN threads take every
+        // NDRAIN-th sweep; they sleep, they do not spin.  The pool outlives the call (run! with adaptation every k
+        // steps issues many short calls).
+        static_assert(SWEEP_RING % NDRAIN == 0, "a ring slot is always drained by the same thread");
+        if (!io.pool_started) {
+            for (auto &d : io.drained) d.store(0);
+            for (int t = 0; t < NDRAIN; ++t) io.drainer[t] = std::thread(drainer_main, ctx, t);
+            io.pool_started = true;
+        }
+        {
+            std::lock_guard<std::mutex> lk(io.m);
+            io.job.n_sweeps = n_sweeps; io.job.row = row; io.job.slot_bytes = slot_bytes;
+            io.job.llp = hist_ll_prop; io.job.ll = hist_ll; io.job.acc = hist_accepted;
+            io.recorded.store(0);
+            io.failed.store(false);
+            for (auto &d : io.drained) d.store(0);
+            io.done = 0;
+            ++io.gen;
+        }
+        io.cv_job.notify_all();
     }
+    // rho schedule: one H2D per chunk of sweeps, on the compute stream (ordered before the chunk's first kernel and
+    // after the previous chunk's last one)
+    const int CHUNK = (int)std::max<size_t>(1, std::min<size_t>((size_t)1 << 14, ((size_t)32 << 20) / (J * sizeof(double))));
+    if (rho_sched) CK(io.d_rho.ensure(J * (size_t)std::min(n_sweeps, CHUNK)));
     int rc = 0;
     auto body = [&]() -> int {
         for (int it = 0; it < n_sweeps; ++it) {
             const int pat = (first_pattern + it) & 1;
             const int slot = it % R;
-            if (want_hist) {  // the slot's previous rows have left the pinned ring (and hence the device ring)
-                static_assert(R % MAXDRAIN == 0, "a ring slot is always drained by the same thread");
+            if (drain) {  // the slot's previous rows have left the pinned ring (and hence the device ring)
                 const int prev = it - R;  // the sweep that used this slot before
-                while (prev >= 0 && drained[prev % NDRAIN].load(std::memory_order_acquire) < prev / NDRAIN + 1) {
-                    if (failed.load(std::memory_order_relaxed)) return fail(ctx, "dmcmc_run_sweeps: history copy failed");
+                while (prev >= 0 && io.drained[prev % NDRAIN].load(std::memory_order_acquire) < prev / NDRAIN + 1) {
+                    if (io.failed.load(std::memory_order_relaxed)) return fail(ctx, "dmcmc_run_sweeps: history copy failed");
                     std::this_thread::sleep_for(std::chrono::microseconds(20));
                 }
             }
-            if (rho_sched) {  // this sweep's pCN memory: caller -> pinned ring -> device ring, on the copy-in stream
-                if (it >= R) {
-                    CK(cudaEventSynchronize(io.rho_ready[slot]));                 // the ring row's last upload has left the host
-                    CK(cudaStreamWaitEvent(io.s_in, io.kernel_done[slot], 0));   // and its kernel no longer reads the device row
-                }
-                std::memcpy(io.h_rho + J * slot, rho_sched + J * it, J * sizeof(double));
-                CK(cudaMemcpyAsync(io.d_rho.p + J * slot, io.h_rho + J * slot, J * sizeof(double), cudaMemcpyHostToDevice, io.s_in));
-                CK(cudaEventRecord(io.rho_ready[slot], io.s_in));
-                CK(cudaStreamWaitEvent(ctx->stream, io.rho_ready[slot], 0));
+            if (rho_sched && it % CHUNK == 0) {
+                const size_t n = (size_t)std::min(CHUNK, n_sweeps - it);
+                CK(cudaMemcpyAsync(io.d_rho.p, rho_sched + J * it, n * J * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             }
             if (half_len > 0 && switch_layout_async(ctx, nb[pat], li1[pat].data(), li2[pat].data(), lpin[pat].data()))
                 return -1;
             SolveParams sp;
             if (fill_params(ctx, sp, ctx->law_cur)) return -1;
-            if (rho_sched) sp.rho = io.d_rho.p + J * slot;
+            if (rho_sched) sp.rho = io.d_rho.p + J * (size_t)(it % CHUNK);
             sp.iter = iter0 + (uint32_t)it;
             sp.reinvert = !ctx->w_valid;  // fused layout switch: noise and ll recovered from the accepted X
             sp.store_w = ctx->w_valid;
@@ -1178,27 +1248,35 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             }
             if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
             ctx->sel_cur ^= 1;
-            if (want_hist || rho_sched) CK(cudaEventRecord(io.kernel_done[slot], ctx->stream));
             if (want_hist) {
+                CK(cudaEventRecord(io.kernel_done[slot], ctx->stream));
                 CK(cudaStreamWaitEvent(io.s_out, io.kernel_done[slot], 0));
-                // the kernel wrote its rows with the caller's stride: one contiguous copy per sweep
-                CK(cudaMemcpyAsync(io.h_hist + slot_bytes * slot, io.d_hist.p + slot_bytes * slot, slot_bytes, cudaMemcpyDeviceToHost, io.s_out));
+                const uint8_t *d = io.d_hist.p + slot_bytes * slot;
+                if (direct) {  // straight into the caller's pinned arrays
+                    if (hist_ll_prop) CK(cudaMemcpyAsync(hist_ll_prop + row * it, d, row * sizeof(double), cudaMemcpyDeviceToHost, io.s_out));
+                    if (hist_ll) CK(cudaMemcpyAsync(hist_ll + row * it, d + row * sizeof(double), row * sizeof(double), cudaMemcpyDeviceToHost, io.s_out));
+                    if (hist_accepted) CK(cudaMemcpyAsync(hist_accepted + row * it, d + 2 * row * sizeof(double), row, cudaMemcpyDeviceToHost, io.s_out));
+                } else {       // the kernel wrote its rows with the caller's stride: one contiguous copy per sweep
+                    CK(cudaMemcpyAsync(io.h_hist + slot_bytes * slot, d, slot_bytes, cudaMemcpyDeviceToHost, io.s_out));
+                }
                 CK(cudaEventRecord(io.copied[slot], io.s_out));
-                recorded.store(it + 1, std::memory_order_release);
+                if (drain) io.recorded.store(it + 1, std::memory_order_release);
             }
         }
         return 0;
     };
     const int old_slack = prctl(PR_GET_TIMERSLACK, 0, 0, 0, 0);  // this thread's waits for a drained ring slot
-    prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);
+    if (drain) prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);
     rc = body();
-    if (old_slack > 0) prctl(PR_SET_TIMERSLACK, (unsigned long)old_slack, 0, 0, 0);
-    if (rc) failed = true;
-    for (auto &d : drainer)
-        if (d.joinable()) d.join();
+    if (drain && old_slack > 0) prctl(PR_SET_TIMERSLACK, (unsigned long)old_slack, 0, 0, 0);
+    if (drain) {
+        if (rc) io.failed = true;
+        std::unique_lock<std::mutex> lk(io.m);
+        io.cv_done.wait(lk, [&] { return io.done == NDRAIN; });
+    }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, "dmcmc_run_sweeps: stream synchronisation failed");
-    if (io.s_in) { cudaStreamSynchronize(io.s_in); cudaStreamSynchronize(io.s_out); }
-    if (!rc && failed) rc = fail(ctx, "dmcmc_run_sweeps: history copy failed");
+    if (io.s_out && cudaStreamSynchronize(io.s_out) != cudaSuccess && !rc) rc = fail(ctx, "dmcmc_run_sweeps: history copy failed");
+    if (!rc && drain && io.failed) rc = fail(ctx, "dmcmc_run_sweeps: history copy failed");
     return rc;
 }
 
@@ -1210,6 +1288,18 @@ void *dmcmc_host_alloc(size_t bytes) {
 
 void dmcmc_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+int dmcmc_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return -1;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+
+int dmcmc_host_unregister(void *p) {
+    if (!p) return -1;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
 }
 
 int dmcmc_relayout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_t *i2, const int32_t *pinned) {
@@ -1347,6 +1437,70 @@ int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_ou
     CK(cudaMemcpy2D(x_out, sizeof(double), ctx->d_x0.p + (size_t)rec * d * ctx->C + chain, (size_t)ctx->C * sizeof(double),
                     sizeof(double), d, cudaMemcpyDeviceToHost));
     (void)steps;
+    return 0;
+}
+
+// a12 without stalling the sampler (save!, src/path_saving_buffer.jl:52; trigger src/run!_alterations.jl:51-54):
+// the glued accepted paths of the chosen chains are snapshotted into a device buffer on the compute stream (so the
+// sweeps enqueued afterwards cannot touch what is saved) and copied to a pinned buffer on the copy-out stream while
+// those sweeps run; dmcmc_save_path_wait collects them.  Up to four saves may be in flight.
+int dmcmc_save_path_async(dmcmc_ctx *ctx, int32_t n_sel, const int32_t *chains, int32_t rec, int32_t *ticket) {
+    REQUIRE(ctx && chains && ticket && n_sel > 0, "dmcmc_save_path_async: bad argument");
+    REQUIRE(rec >= 0 && rec < ctx->R && ctx->have_start, "dmcmc_save_path_async: bad recording / context not initialised");
+    for (int i = 0; i < n_sel; ++i) REQUIRE(chains[i] >= 0 && chains[i] < ctx->C, "dmcmc_save_path_async: chain out of range");
+    CK(cudaSetDevice(ctx->cfg.device));
+    int tk = -1;
+    for (int i = 0; i < 4; ++i)
+        if (!ctx->saves[i].busy) { tk = i; break; }
+    REQUIRE(tk >= 0, "dmcmc_save_path_async: four saves already in flight (call dmcmc_save_path_wait)");
+    PathSave &sv = ctx->saves[tk];
+    int j0 = 0;
+    for (int r = 0; r < rec; ++r) j0 += ctx->rec_nobs[r];
+    const int j1 = j0 + ctx->rec_nobs[rec], d = ctx->d;
+    const int steps = ctx->st_off[j1] - ctx->st_off[j0];
+    const size_t per = (size_t)(steps + 1) * d;   // one glued path: start point + every step
+    sv.n = per * n_sel;
+    CK(sv.d_buf.ensure(sv.n));
+    if (sv.h_n < sv.n) {
+        if (sv.h_buf) cudaFreeHost(sv.h_buf);
+        sv.h_buf = nullptr; sv.h_n = 0;
+        CK(cudaHostAlloc((void **)&sv.h_buf, sv.n * sizeof(double), cudaHostAllocDefault));
+        sv.h_n = sv.n;
+    }
+    if (!sv.snap) {
+        CK(cudaEventCreateWithFlags(&sv.snap, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sv.landed, cudaEventDisableTiming | cudaEventBlockingSync));
+    }
+    if (!ctx->save_stream) CK(cudaStreamCreateWithFlags(&ctx->save_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < n_sel; ++i) {
+        SegmentParams g{};
+        g.C = ctx->C; g.D = d; g.j0 = j0; g.j1 = j1; g.steps = steps; g.TT = ctx->TT;
+        g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_st_off = ctx->d_st_off.p;
+        g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
+        g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
+        g.selX = ctx->d_selX[ctx->sel_cur].p;
+        g.packed = sv.d_buf.p + per * i + d; g.upload = 0; g.pk_stride = (int64_t)per; g.c0 = chains[i]; g.nc = 1;
+        CK(launch_segment(g, ctx->stream));
+        // starting point x0[(rec * d + c) * C + chain] -> first d doubles of the glued path
+        CK(cudaMemcpy2DAsync(sv.d_buf.p + per * i, sizeof(double), ctx->d_x0.p + (size_t)rec * d * ctx->C + chains[i],
+                             (size_t)ctx->C * sizeof(double), sizeof(double), d, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaEventRecord(sv.snap, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->save_stream, sv.snap, 0));
+    CK(cudaMemcpyAsync(sv.h_buf, sv.d_buf.p, sv.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->save_stream));
+    CK(cudaEventRecord(sv.landed, ctx->save_stream));
+    sv.busy = true;
+    *ticket = tk;
+    return 0;
+}
+
+int dmcmc_save_path_wait(dmcmc_ctx *ctx, int32_t ticket, double *x_out) {
+    REQUIRE(ctx && x_out && ticket >= 0 && ticket < 4 && ctx->saves[ticket].busy, "dmcmc_save_path_wait: no such save in flight");
+    CK(cudaSetDevice(ctx->cfg.device));
+    PathSave &sv = ctx->saves[ticket];
+    CK(cudaEventSynchronize(sv.landed));
+    std::memcpy(x_out, sv.h_buf, sv.n * sizeof(double));
+    sv.busy = false;
     return 0;
 }
 
@@ -1503,4 +1657,50 @@ extern "C" int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads) {
     REQUIRE(ctx && threads >= 32 && threads <= 128 && threads % 32 == 0, "dmcmc_set_threads: 32, 64, 96 or 128");
     ctx->threads = threads;
     return 0;
+}
+
+// ---- measurement helper: FP64 FMA throughput of this device (the denominator of the Lorenz-96 kernel's FP64 view) ----
+// Every thread runs eight independent DFMA chains (the dependent-issue latency of one chain is ~8 cycles, measured in
+// tools/micro/fp64lat.cu), 32 warps per SM resident: nothing but the FP64 pipe limits it.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double b, double c) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-9 * (double)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" double dmcmc_fp64_peak(int32_t device) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    if (cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {  // first pass warms the clocks
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
 }

@@ -269,6 +269,21 @@ class Engine:
         self._ck(self.lib.dmcmc_download_path(self.h, chain, rec, _dp(out)))
         return out
 
+    def save_path_async(self, chains, rec=0):
+        """dmcmc_save_path_async: snapshot of the glued accepted paths of `chains`; returns a ticket for save_path_wait."""
+        ch = _i32(chains)
+        tk = C.c_int32()
+        self._ck(self.lib.dmcmc_save_path_async(self.h, len(ch), _ip(ch), rec, C.byref(tk)))
+        j0 = int(self.rec_nobs[:rec].sum())
+        npts = int(self.N[j0:j0 + self.rec_nobs[rec]].sum()) + 1
+        return (tk.value, len(ch), npts)
+
+    def save_path_wait(self, ticket):
+        tk, n, npts = ticket
+        out = np.empty((n, npts, self.d))
+        self._ck(self.lib.dmcmc_save_path_wait(self.h, tk, _dp(out)))
+        return out
+
     def _sync_nblk(self):
         self.nblk = int(self.lib.dmcmc_n_blocks(self.h))
         return self.nblk

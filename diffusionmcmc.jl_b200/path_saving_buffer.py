@@ -29,8 +29,10 @@ class PathSavingBuffer:
     """`XX[k][rec]` = dict(t=glued times, x=glued states) as in
     docs/src/tutorials/simple_inference.md:110-117."""
 
-    def __init__(self, times_per_recording, d, N):
-        self.XX = [[dict(t=np.array(t, float), x=np.zeros((len(t), d))) for t in times_per_recording]
+    def __init__(self, times_per_recording, d, N, n_chains=1):
+        # one saved chain: x is [points][d] like the reference's glued trajectory; several: [chain][points][d]
+        shape = (lambda t: (len(t), d)) if n_chains == 1 else (lambda t: (n_chains, len(t), d))
+        self.XX = [[dict(t=np.array(t, float), x=np.zeros(shape(t))) for t in times_per_recording]
                    for _ in range(N)]
         self.iter = CyclicCounter(N)
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMCMC_ABI_VERSION 4
+#define DMCMC_ABI_VERSION 5
 
 /* Built-in diffusion laws (DiffusionDefinition.jl `@load_diffusion`, src/DiffusionMCMC.jl:4). */
 enum dmcmc_model {
@@ -129,15 +129,20 @@ int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E
  * PathImputation updates with Philox noise, iterations iter0, iter0+1, ...  half_len > 0
  * alternates the two chequerboard layouts (pattern first_pattern first), each sweep = layout
  * switch + imputation; half_len <= 0 keeps the current layout.  rho_sched [n_sweeps][J] (may be
- * NULL) is copied host->device before each sweep.  History rows (any may be NULL) are
- * [n_sweeps][n_chains][nblk_stride]; they stream back while later sweeps run, so host buffers
- * from dmcmc_host_alloc (pinned) overlap best.  Returns after everything has landed. */
+ * NULL) goes host->device inside the call.  History rows (any may be NULL) are
+ * [n_sweeps][n_chains][nblk_stride] -- the rows of src/run!_alterations.jl:65-74; they stream back
+ * while later sweeps run.  Page-locked history buffers (dmcmc_host_alloc, or the caller's own
+ * arrays after dmcmc_host_register) are filled by DMA directly; pageable ones are served through
+ * the library's pinned ring and a pool of copy threads.  Returns after everything has landed. */
 int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
                      int32_t first_pattern, const double *rho_sched, int32_t nblk_stride,
                      double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted);
-/* Pinned host memory for the streaming buffers above. */
+/* Pinned host memory for the streaming buffers above; or page-lock memory the caller already owns
+ * (a Julia Array: register once when the workspace is built, unregister before it is freed). */
 void *dmcmc_host_alloc(size_t bytes);
 void dmcmc_host_free(void *p);
+int dmcmc_host_register(void *p, size_t bytes);
+int dmcmc_host_unregister(void *p);
 
 /* -- layout switch (change_laws_for_blocking! + recompute_loglikhd!, called but undefined in the
  *    reference: src/workspaces.jl:469-470): new tables, Wiener re-inversion, ll recompute. ------ */
@@ -155,6 +160,14 @@ int dmcmc_param_commit(dmcmc_ctx *ctx, int32_t accepted);
 /* a12: accepted path of one chain/recording glued as _copy_path! does
  * (src/path_saving_buffer.jl:54-64): x_out [(sum_j N_j)+1][d]. */
 int dmcmc_download_path(dmcmc_ctx *ctx, int32_t chain, int32_t rec, double *x_out);
+/* The same without stalling the sampler (save!, src/path_saving_buffer.jl:52; the reference saves every
+ * 100th iteration, src/run!_alterations.jl:51-54): the glued accepted paths of n_sel chosen chains are
+ * snapshotted on the device in stream order and copied out while later sweeps run.  *ticket identifies
+ * the save (at most four in flight); dmcmc_save_path_wait blocks until it has landed and fills
+ * x_out [n_sel][(sum_j N_j)+1][d]. */
+int dmcmc_save_path_async(dmcmc_ctx *ctx, int32_t n_sel, const int32_t *chains, int32_t rec,
+                          int32_t *ticket);
+int dmcmc_save_path_wait(dmcmc_ctx *ctx, int32_t ticket, double *x_out);
 /* Full containers in the reference's per-interval shape (N_j+1 points per interval, duplicated
  * joins): X [n_chains][P][d], W [n_chains][P][m] cumulative.  which: 0 accepted, 1 proposal. */
 int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W);
@@ -210,6 +223,9 @@ int64_t dmcmc_launch_count(dmcmc_ctx *ctx);
 int dmcmc_timer_start(dmcmc_ctx *ctx);
 int dmcmc_timer_stop(dmcmc_ctx *ctx, double *ms);
 int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
+/* Measured FP64 FMA throughput of a device in TFLOP/s (independent DFMA chains on every SM, best of five): the
+ * denominator of the FP64-pipe view of the Lorenz-96 kernel (bench.py). */
+double dmcmc_fp64_peak(int32_t device);
 /* Threads per CTA of the solve kernels (32..128, multiple of 32; default 64). */
 int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
 /* Model-specific fused step kernels (FitzHugh-Nagumo with its built-in aux law); on by default.

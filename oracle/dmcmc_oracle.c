@@ -408,15 +408,23 @@ static void bf_step(int d, int pinned, const double *Phi, const double *Q, const
     symmetrize(d, s->H);
 }
 
-void orc_backward_filter(int d, int J, const int32_t *N, const int32_t *pt_off, const double *t,
-                         const double *auxB, const double *auxbeta, const double *auxatil,
-                         const double *Hobs, const double *Fobs, const double *cobs, int nblk,
-                         const int32_t *blk_i1, const int32_t *blk_i2, const int32_t *blk_pinned,
-                         double pin_eps, double *H, double *F0, double *Psi, double *c0,
-                         double *blk_g, double *blk_Qc) {
+/* scheme 0: step by step, grid point k from k+1 by the one-step transition (dt_k);
+ * scheme 1: every grid point of an interval directly from the interval's right-end value by ONE
+ *           transition over tau_k = t_N - t_k (the aux law is constant on the interval, so this is
+ *           the same exact flow; it is what the device kernel bf_par_kernel computes for d <= 3,
+ *           where the N grid points of an interval are independent and run in parallel).
+ * Both are exact solutions of the H, F, c ODEs; they differ by rounding only
+ * (tests/test_oracle.py::test_backward_filter_schemes_agree). */
+void orc_backward_filter_scheme(int d, int J, const int32_t *N, const int32_t *pt_off, const double *t,
+                                const double *auxB, const double *auxbeta, const double *auxatil,
+                                const double *Hobs, const double *Fobs, const double *cobs, int nblk,
+                                const int32_t *blk_i1, const int32_t *blk_i2, const int32_t *blk_pinned,
+                                double pin_eps, int scheme, double *H, double *F0, double *Psi, double *c0,
+                                double *blk_g, double *blk_Qc) {
     (void)J;
     for (int b = 0; b < nblk; ++b) {
         bf_state *s = (bf_state *)calloc(1, sizeof(bf_state));
+        bf_state *send = (bf_state *)calloc(1, sizeof(bf_state));
         double *work = (double *)malloc(sizeof(double) * 4 * MD * MD);
         double *Phi = (double *)malloc(sizeof(double) * 2 * MD * MD + sizeof(double) * MD);
         double *Q = Phi + MD * MD, *mvec = Q + MD * MD;
@@ -439,6 +447,21 @@ void orc_backward_filter(int d, int J, const int32_t *N, const int32_t *pt_off, 
             memcpy(F0 + (base + Nj) * d, s->F0, sizeof(double) * (size_t)d);
             if (Psi) memcpy(Psi + (base + Nj) * d * d, s->Psi, sizeof(double) * (size_t)d * d);
             c0[base + Nj] = s->c0;
+            if (scheme == 1) {
+                *send = *s;
+                double tN = t[base + Nj];
+                for (int k = Nj - 1; k >= 0; --k) {
+                    orc_transition(d, auxB + (size_t)j * d * d, auxbeta + (size_t)j * d,
+                                   auxatil + (size_t)j * d * d, tN - t[base + k], Phi, Q, mvec);
+                    *s = *send;
+                    bf_step(d, pinned, Phi, Q, mvec, s, work);
+                    memcpy(H + (base + k) * d * d, s->H, sizeof(double) * (size_t)d * d);
+                    memcpy(F0 + (base + k) * d, s->F0, sizeof(double) * (size_t)d);
+                    if (Psi) memcpy(Psi + (base + k) * d * d, s->Psi, sizeof(double) * (size_t)d * d);
+                    c0[base + k] = s->c0;
+                }
+                continue; /* s holds the value at k = 0: the next interval (to the left) continues from it */
+            }
             double dt_cached = -1.0;
             for (int k = Nj - 1; k >= 0; --k) {
                 double dt = t[base + k + 1] - t[base + k];
@@ -461,8 +484,19 @@ void orc_backward_filter(int d, int J, const int32_t *N, const int32_t *pt_off, 
         memcpy(blk_Qc + (size_t)b * d * d, s->Qc, sizeof(double) * (size_t)d * d);
         free(Phi);
         free(work);
+        free(send);
         free(s);
     }
+}
+
+void orc_backward_filter(int d, int J, const int32_t *N, const int32_t *pt_off, const double *t,
+                         const double *auxB, const double *auxbeta, const double *auxatil,
+                         const double *Hobs, const double *Fobs, const double *cobs, int nblk,
+                         const int32_t *blk_i1, const int32_t *blk_i2, const int32_t *blk_pinned,
+                         double pin_eps, double *H, double *F0, double *Psi, double *c0,
+                         double *blk_g, double *blk_Qc) {
+    orc_backward_filter_scheme(d, J, N, pt_off, t, auxB, auxbeta, auxatil, Hobs, Fobs, cobs, nblk, blk_i1, blk_i2,
+                               blk_pinned, pin_eps, 0, H, F0, Psi, c0, blk_g, blk_Qc);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -100,6 +100,15 @@ void orc_backward_filter(int d, int J, const int32_t *N, const int32_t *pt_off, 
                          const int32_t *blk_pinned, double pin_eps,
                          double *H, double *F0, double *Psi, double *c0,
                          double *blk_g, double *blk_Qc);
+/* scheme 0 = step by step (above); scheme 1 = every grid point of an interval from the interval's right-end value by
+ * one transition over t_N - t_k (what the device computes for d <= 3).  Same exact flow, different rounding. */
+void orc_backward_filter_scheme(int d, int J, const int32_t *N, const int32_t *pt_off, const double *t,
+                                const double *auxB, const double *auxbeta, const double *auxatil,
+                                const double *Hobs, const double *Fobs, const double *cobs,
+                                int nblk, const int32_t *blk_i1, const int32_t *blk_i2,
+                                const int32_t *blk_pinned, double pin_eps, int scheme,
+                                double *H, double *F0, double *Psi, double *c0,
+                                double *blk_g, double *blk_Qc);
 
 /* ---- a2 pCN refresh, a4+a5 solve, a3 guiding term ---- */
 void orc_wiener_refresh(int N, int m, const double *t, const double *Z, double *Wp);

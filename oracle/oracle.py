@@ -213,8 +213,12 @@ class Oracle:
     x0[C][R][d], rho[J], pin_eps.
     """
 
-    def __init__(self, spec, nthreads=1, chain_offset=0, interval_offset=0):
+    def __init__(self, spec, nthreads=1, chain_offset=0, interval_offset=0, bf_scheme=None):
         self.nthreads = nthreads
+        # backward-filter scheme (both exact flows of the H, F, c ODEs, see orc_backward_filter_scheme): by default
+        # the one the device kernel of that state dimension uses -- 1 (every grid point from the interval's right
+        # end) for d <= 3, 0 (step by step) for Lorenz-96
+        self.bf_scheme = bf_scheme if bf_scheme is not None else (1 if int(spec["d"]) <= 3 else 0)
         self.chain_offset, self.interval_offset = chain_offset, interval_offset
         self.model, self.d, self.m = int(spec["model"]), int(spec["d"]), int(spec["m"])
         self.N = i32(spec["N"])
@@ -248,6 +252,7 @@ class Oracle:
     # -- law ------------------------------------------------------------------------------
     def set_theta(self, theta, custom_aux=None):
         self.theta = f64(theta)
+        self.__dict__.pop("_bf_cache", None)
         d, m, J = self.d, self.m, self.J
         self.auxB, self.auxbeta, self.auxsig = np.zeros((J, d, d)), np.zeros((J, d)), np.zeros((J, d, m))
         for j in range(J):
@@ -271,14 +276,25 @@ class Oracle:
         self.backward_filter()
 
     def backward_filter(self):
+        # tables are a function of (law, layout): kept per layout until the law changes, like the device's cache
+        # (a chequerboard sampler alternates between two layouts; recomputing them every sweep would only slow the
+        # CPU baseline down)
+        key = (self.blk_i1.tobytes(), self.blk_i2.tobytes(), self.blk_pinned.tobytes(), self.bf_scheme)
+        cache = self.__dict__.setdefault("_bf_cache", {})
+        if key in cache:
+            self.H, self.F0, self.Psi, self.c0, self.blk_g, self.blk_Qc = cache[key]
+            return
         d, P, nb = self.d, self.P, self.nblk
         self.H, self.F0, self.Psi = np.zeros((P, d, d)), np.zeros((P, d)), np.zeros((P, d, d))
         self.c0, self.blk_g, self.blk_Qc = np.zeros(P), np.zeros((nb, d)), np.zeros((nb, d, d))
-        lib().orc_backward_filter(
+        lib().orc_backward_filter_scheme(
             d, self.J, _i(self.N), _i(self.pt_off), _d(self.t), _d(self.auxB), _d(self.auxbeta),
             _d(self.auxatil), _d(self.Hobs), _d(self.Fobs), _d(self.cobs), nb, _i(self.blk_i1),
-            _i(self.blk_i2), _i(self.blk_pinned), C.c_double(self.pin_eps), _d(self.H),
+            _i(self.blk_i2), _i(self.blk_pinned), C.c_double(self.pin_eps), int(self.bf_scheme), _d(self.H),
             _d(self.F0), _d(self.Psi), _d(self.c0), _d(self.blk_g), _d(self.blk_Qc))
+        if len(cache) >= 4:
+            cache.clear()
+        cache[key] = (self.H, self.F0, self.Psi, self.c0, self.blk_g, self.blk_Qc)
 
     # -- ctypes views -----------------------------------------------------------------------
     def _problem(self):
@@ -368,6 +384,7 @@ class Oracle:
         elif not accepted.any():
             (self.theta, self.auxB, self.auxbeta, self.auxsig, self.auxatil, self.H, self.F0,
              self.Psi, self.c0, self.blk_g, self.blk_Qc) = self._saved_law
+            self.__dict__.pop("_bf_cache", None)   # it holds the rejected law's tables
         else:
             raise ValueError("one theta-instance per Oracle: accept all chains or none")
         p, s = self._problem(), self._state()

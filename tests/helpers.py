@@ -1,4 +1,6 @@
 """Shared comparison helpers for the parity tests (oracle vs CUDA path)."""
+import os
+
 import numpy as np
 
 RTOL = 1e-10  # north_star: imputed paths and per-block ll within 1e-10 relative (FP64)
@@ -19,6 +21,38 @@ def maxrel(a, b):
     if not fin.any():
         return 0.0
     return float(np.max(np.abs(a - b)[fin] / np.maximum(1.0, np.abs(b)[fin])))
+
+
+_REPORT = os.environ.get("DMCMC_PARITY_REPORT", "")
+
+
+def check(what, got, ref, rtol=RTOL):
+    """Parity assertion that also RECORDS the achieved error: |got - ref| <= rtol * max(1, |ref|)
+    element-wise; one line `what, max-rel, tolerance` goes to stdout (pytest -s / -rA) and, when
+    DMCMC_PARITY_REPORT names a file, is appended there (profiles/r2_parity_report.txt is such a run)."""
+    err = maxrel(got, ref)
+    line = f"parity {what}: max-rel {err:.3e} (tol {rtol:.0e})"
+    print(line)
+    if _REPORT:
+        with open(_REPORT, "a") as f:
+            f.write(line + "\n")
+    assert close(got, ref, rtol), line
+    return err
+
+
+def check_scaled(what, got, ref, rtol=RTOL):
+    """Norm-wise variant for tables whose entries span orders of magnitude (H, Psi ~ 1/pin_eps next to O(1) entries):
+    max |got - ref| <= rtol * max(1, max |ref|)."""
+    got, ref = np.asarray(got, float), np.asarray(ref, float)
+    sc = max(1.0, float(np.abs(ref).max())) if ref.size else 1.0
+    err = float(np.abs(got - ref).max()) / sc if ref.size else 0.0
+    line = f"parity {what}: max-abs/scale {err:.3e} (scale {sc:.2e}, tol {rtol:.0e})"
+    print(line)
+    if _REPORT:
+        with open(_REPORT, "a") as f:
+            f.write(line + "\n")
+    assert err <= rtol, line
+    return err
 
 
 def interior_mask(N):

@@ -114,3 +114,49 @@ def test_path_saving_buffer_ring(pkg):
     buf.save([2 * np.ones((5, 2))])
     buf.save([3 * np.ones((5, 2))])
     assert buf.XX[0][0]["x"][0, 0] == 3 and buf.XX[1][0]["x"][0, 0] == 2
+
+
+def test_blocking_plan_carries_the_pattern_across_iterations(pkg):
+    """extra_schedule_params with update_layout defined: each BlockingChequerboardSwitch moves to the other pattern.
+    Even number of switches per pass (the reference's assertion, src/schedule.jl:89): an update keeps its pattern;
+    odd number: the switch count carries over, so the pattern alternates from one MCMC iteration to the next --
+    in the general path exactly as in the device loop (otherwise [Switch, Imputation, ParamUpdate] would never
+    re-impute the block end points)."""
+    from diffusionmcmc_jl_b200.backend import _BlockingPlan
+    S, I, R = pkg.BlockingChequerboardSwitch, pkg.PathImputation, pkg.RandomWalkUpdate
+    plan = _BlockingPlan([10], [S(2), I(0.9), S(2), I(0.9)])
+    assert [plan.pattern(0, it) for it in (1, 2, 3)] == [0, 0, 0] and [plan.pattern(1, it) for it in (1, 2, 3)] == [1, 1, 1]
+    assert plan.patterns_seen(0) == [0] and plan.patterns_seen(1) == [1]
+    plan = _BlockingPlan([10], [S(1), I(0.9), R(0.1, [2])])
+    assert [plan.pattern(0, it) for it in (1, 2, 3, 4)] == [0, 1, 0, 1]
+    assert [plan.pattern(1, it) for it in (1, 2, 3, 4)] == [0, 1, 0, 1]    # the parameter step runs under the same layout
+    assert plan.patterns_seen(0) == [0, 1]
+    lay0, lay1 = plan.layout(0, 0), plan.layout(0, 1)
+    assert list(lay0[0]) == [0, 2, 4, 6, 8] and list(lay1[0]) == [0, 1, 3, 5, 7, 9]
+    plan = _BlockingPlan([10], [I(0.9), R(0.1, [2])])
+    assert plan.pattern(0, 5) is None and plan.patterns_seen(0) == [None]
+    assert list(plan.layout(0, None)[1]) == [9]
+    plan = _BlockingPlan([10], [S(1), I(0.9), S(1), I(0.9), S(1), I(0.9)])   # three switches per pass
+    assert [[plan.pattern(u, it) for u in range(3)] for it in (1, 2)] == [[0, 1, 0], [1, 0, 1]]
+
+
+def test_imputation_state_keeps_rho_per_block_and_adapts(pkg):
+    from diffusionmcmc_jl_b200.backend import _ImputationState
+    lay = pkg.problems.chequerboard_layout([10], 2, 1)       # blocks [0,1] [2..5] [6..9]
+    u = pkg.PathImputation(0.5, adpt=pkg.AdaptationPathImputation(adapt_every_k_steps=4, scale=1.0, offset=0.0))
+    st = _ImputationState(u, lay)
+    assert [len(r) for r in st.rho_s] == [2, 4, 4] and st.rho_per_interval(10).tolist() == [0.5] * 10
+    assert st.adpt is not u.adpt and len(st.adpt.v) == 3
+    assert not st.register_and_adapt(np.array([2, 0, 2]), np.full(3, 2), 1)
+    assert st.register_and_adapt(np.array([2, 0, 0]), np.full(3, 2), 2)        # 4 proposals per block registered
+    r = st.rho_per_interval(10)
+    # acceptance 100 % and 50 % are above the 0.234 target: rho goes down (src/adaptation.jl:82-90); 0 %: up
+    assert r[0] < 0.5 and r[2] > 0.5 and r[6] < 0.5 and r[1] == r[0] and r[9] == r[6]
+
+
+def test_parameter_updates_refuse_a_chain_batch(pkg):
+    """The chains of one context share theta: a joint accept/reject over C chains would target likelihood^C."""
+    data = pkg.problems.fhn_spec(n_obs=5, C=4, dt=0.01)
+    mcmc = pkg.MCMC([pkg.PathImputation(0.9), pkg.RandomWalkUpdate(0.1, [2])])
+    with pytest.raises(ValueError, match="n_chains == 1"):
+        pkg.run_(mcmc, 3, data, data["theta"])

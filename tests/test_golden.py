@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import close, interior_mask, maxrel
+from helpers import check, interior_mask
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
@@ -46,18 +46,18 @@ def test_cuda_matches_golden(pkg, path):
     g = np.load(path)
     e = Engine(_spec(g))
     e.init_paths(Z=g["Z0"])
-    tol = 1e-10 if not int(g["half_len"]) else 1e-8  # pinned tables: 1/pin_eps conditioning
-    assert close(e.get_ll(), g["ll_init"], tol), maxrel(e.get_ll(), g["ll_init"])
+    name = os.path.basename(path)[:-4]
+    check(f"golden {name} init ll", e.get_ll(), g["ll_init"])
     h = int(g["half_len"])
     im = interior_mask(e.N)
     for it in range(3):
         if h:
             e.relayout(*pkg.problems.chequerboard_layout(e.rec_nobs, h, it % 2))
-            assert close(e.get_ll(), g[f"ll_relayout_{it}"], tol), maxrel(e.get_ll(), g[f"ll_relayout_{it}"])
+            check(f"golden {name} it {it} relayout ll", e.get_ll(), g[f"ll_relayout_{it}"])
         llp, ll, acc = e.impute(it, g[f"Z_{it}"], g[f"E_{it}"])
-        assert close(llp, g[f"llp_{it}"], tol), maxrel(llp, g[f"llp_{it}"])
+        check(f"golden {name} it {it} ll deg", llp, g[f"llp_{it}"])
         assert np.array_equal(acc, g[f"acc_{it}"])
         X, W = e.download_state(0)
-        assert close(X[:, im], g[f"Xacc_{it}"][:, im], tol)
-        assert close(W[:, im], g[f"Wacc_{it}"][:, im], tol)
-    assert close(e.download_path(0), g["glued_chain0"], tol)
+        check(f"golden {name} it {it} X", X[:, im], g[f"Xacc_{it}"][:, im])
+        check(f"golden {name} it {it} W", W[:, im], g[f"Wacc_{it}"][:, im])
+    check(f"golden {name} glued path", e.download_path(0), g["glued_chain0"])

@@ -3,7 +3,7 @@ CTA-cooperative backward filter against the CPU oracle."""
 import numpy as np
 import pytest
 
-from helpers import accept_mismatch_is_tie, close, interior_mask, maxrel
+from helpers import accept_mismatch_is_tie, check, check_scaled, close, interior_mask, maxrel
 
 pytestmark = pytest.mark.gpu
 
@@ -20,8 +20,8 @@ def _pair(pkg, orc, spec, upload=True, **kw):
 def _state_ok(o, e, tol, what):
     Xg, Wg = e.download_state(0)
     im = interior_mask(o.N)
-    assert close(Xg[:, im], o.accepted_X()[:, im], tol), (what, maxrel(Xg[:, im], o.accepted_X()[:, im]))
-    assert close(Wg[:, im], o.accepted_W()[:, im], tol), (what, maxrel(Wg[:, im], o.accepted_W()[:, im]))
+    check(f"l96 {what} X", Xg[:, im], o.accepted_X()[:, im], tol)
+    check(f"l96 {what} W", Wg[:, im], o.accepted_W()[:, im], tol)
 
 
 def test_l96_impute_parity_explicit_noise(pkg, orc):
@@ -31,7 +31,7 @@ def test_l96_impute_parity_explicit_noise(pkg, orc):
     Z0 = rng.standard_normal((o.C, o.S, o.m))
     o.init_paths(Z=Z0)
     e.init_paths(Z=Z0)
-    assert close(e.get_ll(), o.ll), maxrel(e.get_ll(), o.ll)
+    check("l96 init ll", e.get_ll(), o.ll)
     _state_ok(o, e, 1e-10, "init")
     for it in range(3):
         Z = rng.standard_normal((o.C, o.S, o.m))
@@ -39,7 +39,7 @@ def test_l96_impute_parity_explicit_noise(pkg, orc):
         ll_before = o.ll.copy()
         llp_o, ll_o, acc_o = o.impute(Z, E)
         llp_g, ll_g, acc_g = e.impute(it, Z, E)
-        assert close(llp_g, llp_o), maxrel(llp_g, llp_o)
+        check(f"l96 it {it} ll deg", llp_g, llp_o)
         assert accept_mismatch_is_tie(acc_g, acc_o, E, llp_o, ll_before)
         assert np.array_equal(acc_g, acc_o)
         _state_ok(o, e, 1e-10, f"it {it}")
@@ -49,9 +49,8 @@ def test_l96_device_backward_filter(pkg, orc):
     spec = pkg.problems.l96_spec(n_obs=4, C=1, dt=2e-3)
     o, e = _pair(pkg, orc, spec, upload=False)
     t = e.download_tables()
-    assert np.abs(t["H"] - o.H).max() <= 1e-11 * max(1.0, np.abs(o.H).max())
-    assert np.abs(t["F0"] - o.F0).max() <= 1e-11 * max(1.0, np.abs(o.F0).max())
-    assert np.abs(t["c0"] - o.c0).max() <= 1e-10 * max(1.0, np.abs(o.c0).max())
+    for k, ref in (("H", o.H), ("F0", o.F0), ("c0", o.c0)):
+        check_scaled(f"l96 device filter {k}", t[k], ref)
     # pinned layout: Psi, g, Qc
     lay = pkg.problems.chequerboard_layout(o.rec_nobs, 1, 0)
     o.set_layout(*lay)
@@ -59,7 +58,7 @@ def test_l96_device_backward_filter(pkg, orc):
     e.backward_filter()
     t = e.download_tables()
     for k, ref in (("H", o.H), ("F0", o.F0), ("Psi", o.Psi), ("blk_g", o.blk_g), ("blk_Qc", o.blk_Qc)):
-        assert np.abs(t[k] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), k
+        check_scaled(f"l96 device filter pinned {k}", t[k], ref)
 
 
 def test_l96_fused_blocked_and_philox(pkg, orc):
@@ -68,7 +67,7 @@ def test_l96_fused_blocked_and_philox(pkg, orc):
     P = pkg.problems
     o.init_paths(seed=1234)
     e.init_paths()
-    assert close(e.get_ll(), o.ll), maxrel(e.get_ll(), o.ll)
+    check("l96 philox init ll", e.get_ll(), o.ll)
     im = interior_mask(o.N)
     for it in range(4):
         lay = P.chequerboard_layout(o.rec_nobs, 1, it % 2)
@@ -77,8 +76,8 @@ def test_l96_fused_blocked_and_philox(pkg, orc):
         e.upload_tables(o.H, o.F0, o.Psi, o.c0, o.blk_g, o.blk_Qc)
         llp_o, ll_o, acc_o = o.impute(seed=1234, it=it)
         llp_g, ll_g, acc_g = e.impute(it)
-        assert close(llp_g, llp_o, 1e-8), (it, maxrel(llp_g, llp_o))
+        check(f"l96 fused blocked it {it} ll deg", llp_g, llp_o)
         assert np.array_equal(acc_g, acc_o)
-        assert close(ll_g, ll_o, 1e-8)
+        check(f"l96 fused blocked it {it} ll", ll_g, ll_o)
         Xg, _ = e.download_state(0)
-        assert close(Xg[:, im], o.accepted_X()[:, im], 1e-8), maxrel(Xg[:, im], o.accepted_X()[:, im])
+        check(f"l96 fused blocked it {it} X", Xg[:, im], o.accepted_X()[:, im])

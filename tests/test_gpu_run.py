@@ -87,3 +87,43 @@ def test_single_update_with_switch_alternates_patterns(pkg):
     assert acc.shape == (7, 3, 6) and ll.shape == (7, 3, 6)      # 5 blocks (pattern 0) / 6 blocks (pattern 1)
     assert np.isfinite(ll[:, :, :5]).all()
     assert np.isfinite(ll[1::2, :, 5]).all()                     # the sixth block exists in every other iteration
+
+
+def test_odd_switch_count_with_a_parameter_update_moves_the_block_ends(pkg):
+    """[Switch, PathImputation, RandomWalkUpdate] walks the general path (update by update).  The pattern must alternate
+    from one MCMC iteration to the next there as well, otherwise the points at the pattern-0 block ends are pinned
+    forever and never re-imputed."""
+    data = pkg.problems.fhn_spec(n_obs=12, C=1, dt=0.01, rho=0.5)
+    mcmc = pkg.MCMC([pkg.BlockingChequerboardSwitch(1), pkg.PathImputation(0.5, "FitzHughNagumoAux"),
+                     pkg.RandomWalkUpdate(0.05, [2])])
+    saved = []
+
+    def cb(gws, lws, step):
+        if step.pidx == 2:
+            saved.append(gws.engine.download_path(0))
+    gws, lws = pkg.run_(mcmc, 40, data, data["theta"].copy(), callbacks=[cb], seed=4)
+    P = np.array(saved)                        # [iter][point][d]; 10 steps per interval
+    ends0 = np.arange(2, 12, 2) * 10           # pattern-0 block ends (pinned in pattern 0, interior in pattern 1)
+    moved = np.abs(np.diff(P[:, ends0, 1], axis=0)).max(axis=0)
+    assert (moved > 0).all(), moved
+    acc = lws[0].acceptance_history
+    assert acc.shape == (40, 7)                # pattern 0: 6 blocks, pattern 1: 7 blocks
+    assert np.isnan(lws[0].ll_history[0::2, 6]).all() and np.isfinite(lws[0].ll_history[1::2, 6]).all()
+    assert acc[1::2].any() and acc[0::2].any()
+
+
+def test_two_adaptive_imputations_both_adapt_and_save_several_chains(pkg):
+    """Fast path with two PathImputation updates: each keeps its own acceptance counters (from its own history rows),
+    so both rho's move; the path ring holds the chosen chains."""
+    data = pkg.problems.fhn_spec(n_obs=10, C=8, dt=0.01)
+    mk = lambda r: pkg.PathImputation(r, "FitzHughNagumoAux",
+                                      adpt=pkg.AdaptationPathImputation(adapt_every_k_steps=20, scale=1.0, offset=0.0))
+    u1, u2 = mk(0.05), mk(0.999999)
+    mcmc = pkg.MCMC([pkg.BlockingChequerboardSwitch(2), u1, pkg.BlockingChequerboardSwitch(2), u2])
+    gws, lws = pkg.run_(mcmc, 200, data, n_chains=8, seed=6, save_every=50, path_buffer_size=3, save_chains=(0, 5))
+    assert u1.rho_s[0][0] != 0.05 and u2.rho_s[0][0] < 0.999999      # both adapted (the second one used to see 0/0)
+    assert len(u1.rho_s) == 3 and len(u2.rho_s) == 3          # 10 obs, half_len 2: 3 blocks in either pattern
+    x = gws.XX_buffer.XX[0][0]["x"]
+    assert x.shape == (2, 101, 2) and np.isfinite(x).all() and not np.array_equal(x[0], x[1])
+    last = gws.XX_buffer.XX[0][0]["x"]           # ring of 3, 4 saves: slot 0 holds the 4th (iteration 200 = final state)
+    assert np.array_equal(last[0], gws.engine.download_path(0)) and np.array_equal(last[1], gws.engine.download_path(5))
