@@ -666,6 +666,45 @@ __global__ void __launch_bounds__(256) bf_big_kernel(const BFParams b) {
     for (int e = tid; e < DD; e += nt) b.blk_Qc[(size_t)blk * DD + e] = Qc[e];
 }
 
+// Built-in auxiliary law of every interval from theta and the interval's end observation, on the device: a critical
+// parameter proposal (DD.set_parameters! + backward_filter!, src/run!_alterations.jl:188-204) no longer rebuilds and
+// uploads J aux laws on the host (measured on C4, 10^4 intervals: 0.57 of the 0.68 ms parameter step).  Lives in this
+// translation unit because it is compiled without FMA contraction: the aux law feeds the filter, and the CPU restatement
+// builds it with separately rounded operations.
+__global__ void aux_build_kernel(int model, int d, int m, int p, int J, Theta th, const double *__restrict__ v,
+                                 double *__restrict__ B, double *__restrict__ beta, double *__restrict__ atil) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= J) return;
+    double *Bj = B + (size_t)j * d * d, *bj = beta + (size_t)j * d, *aj = atil + (size_t)j * d * d;
+    if (d <= 3) {
+        double sig[9];
+        aux_build_host(model, d, m, th.v, v + (size_t)j * p, p, Bj, bj, sig);
+        for (int i = 0; i < d; ++i)
+            for (int k = 0; k < d; ++k) {
+                double s = 0.0;
+                for (int c = 0; c < m; ++c) s += sig[i * m + c] * sig[k * m + c];
+                aj[i * d + k] = s;
+            }
+    } else {  // Lorenz-96: sigma~ = sigma I (the d x m scratch would not fit a thread's registers)
+        for (int i = 0; i < d * d; ++i) { Bj[i] = 0.0; aj[i] = 0.0; }
+        const double c = th.v[2];
+        for (int i = 0; i < d; ++i) {
+            Bj[i * d + i] += -1.0;
+            Bj[i * d + (i + 1) % d] += c;
+            Bj[i * d + (i + d - 2) % d] += -c;
+            bj[i] = th.v[0];
+            aj[i * d + i] = th.v[1] * th.v[1];
+        }
+    }
+}
+
+cudaError_t launch_aux_build(int model, int d, int m, int p, int J, const Theta &th, const double *v, double *B, double *beta,
+                             double *atil, cudaStream_t s) {
+    if (J <= 0) return cudaSuccess;
+    aux_build_kernel<<<(unsigned)((J + 127) / 128), 128, 0, s>>>(model, d, m, p, J, th, v, B, beta, atil);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_backward_filter(const BFParams &b, cudaStream_t s) {
     if (b.nblk == 0) return cudaSuccess;
     if (b.D == 40) {

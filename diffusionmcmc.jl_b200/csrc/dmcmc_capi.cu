@@ -15,6 +15,8 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "../../include/dmcmc.h"
 #include "dmcmc_device.cuh"
@@ -73,6 +75,7 @@ struct Law {
     std::vector<double> auxB, auxbeta, auxsig, auxatil;
     DevBuf<double> d_auxB, d_auxbeta, d_auxatil;
     bool have_theta = false, custom_aux = false;
+    bool host_aux_valid = false;  // auxB / auxbeta / auxsig hold this law (false: built on the device only)
 };
 }  // namespace
 
@@ -143,7 +146,7 @@ struct dmcmc_ctx {
     // device
     DevBuf<int32_t> d_N, d_tile_off, d_first, d_rec, d_pt_off, d_st_off, d_xs;
     DevBuf<int64_t> d_xoff;
-    DevBuf<double> d_t, d_rho, d_Hobs, d_Fobs, d_cobs, d_x0, d_ll, d_Z, d_E;
+    DevBuf<double> d_t, d_rho, d_Hobs, d_Fobs, d_cobs, d_x0, d_ll, d_Z, d_E, d_v;
     DevBuf<double> d_X[2], d_W[2];
     DevBuf<uint8_t> d_selX[2], d_selW[2], d_mask, d_out_acc;
     int sel_cur = 0;
@@ -158,6 +161,11 @@ struct dmcmc_ctx {
     SweepIO io;
     PathSave saves[4];
     cudaStream_t save_stream = nullptr;
+    // block-sharded recording: NCCL communicator of the ranks that share it, and its message buffers
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf<double> cb_send, cb_recv, d_gl_llp, d_gl_ll;
+    DevBuf<int32_t> d_gl_ok, d_gidx;
 };
 
 namespace {
@@ -285,6 +293,18 @@ int compute_obs_terms(dmcmc_ctx *ctx) {
 int build_aux(dmcmc_ctx *ctx, int slot) {
     Law &law = ctx->law[slot];
     const int d = ctx->d, m = ctx->m, J = ctx->J;
+    if (!law.custom_aux && ctx->d_v.p) {
+        REQUIRE(ctx->have_obs, "auxiliary laws need the observations: call dmcmc_set_obs first");
+        CK(law.d_auxB.ensure((size_t)J * d * d));
+        CK(law.d_auxbeta.ensure((size_t)J * d));
+        CK(law.d_auxatil.ensure((size_t)J * d * d));
+        Theta th{};
+        for (int i = 0; i < DMCMC_MAX_THETA; ++i) th.v[i] = law.theta[i];
+        CK(launch_aux_build(ctx->cfg.model, d, m, ctx->p, J, th, ctx->d_v.p, law.d_auxB.p, law.d_auxbeta.p, law.d_auxatil.p, ctx->stream));
+        law.host_aux_valid = false;
+        for (auto &lay : ctx->layout) lay.tab[slot].valid = lay.tab[slot].fvalid = false;
+        return 0;
+    }
     if (!law.custom_aux) {
         REQUIRE(ctx->have_obs, "auxiliary laws need the observations: call dmcmc_set_obs first");
         law.auxB.assign((size_t)J * d * d, 0.0);
@@ -307,6 +327,7 @@ int build_aux(dmcmc_ctx *ctx, int slot) {
     if (upload(ctx, law.d_auxB, law.auxB)) return -1;
     if (upload(ctx, law.d_auxbeta, law.auxbeta)) return -1;
     if (upload(ctx, law.d_auxatil, law.auxatil)) return -1;
+    law.host_aux_valid = true;
     for (auto &lay : ctx->layout) lay.tab[slot].valid = lay.tab[slot].fvalid = false;
     return 0;
 }
@@ -533,6 +554,80 @@ int resize_ll(dmcmc_ctx *ctx) {
 
 }  // namespace
 
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------------
+// The library has no link-time dependency on NCCL: a process that already carries one (PyTorch's) is reused
+// (RTLD_NOLOAD), otherwise the system libnccl.so.2 is loaded on the first dmcmc_comm_* call.
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_m;
+
+NcclApi *nccl_api(std::string &err) {
+    std::lock_guard<std::mutex> lk(g_nccl_m);
+    if (g_nccl.h) return &g_nccl;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("NCCL not found: ") + dlerror(); return nullptr; }
+#define DMCMC_NCCL_SYM(field, name)                                             \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));     \
+    if (!g_nccl.field) { err = std::string("NCCL symbol missing: ") + name; return nullptr; }
+    DMCMC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    DMCMC_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    DMCMC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    DMCMC_NCCL_SYM(Send, "ncclSend")
+    DMCMC_NCCL_SYM(Recv, "ncclRecv")
+    DMCMC_NCCL_SYM(AllReduce, "ncclAllReduce")
+    DMCMC_NCCL_SYM(GroupStart, "ncclGroupStart")
+    DMCMC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    DMCMC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef DMCMC_NCCL_SYM
+    g_nccl.h = h;
+    return &g_nccl;
+}
+
+void comm_release(dmcmc_ctx *ctx) {
+    if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->cb_send.release(); ctx->cb_recv.release(); ctx->d_gl_llp.release(); ctx->d_gl_ll.release();
+    ctx->d_gl_ok.release(); ctx->d_gidx.release();
+}
+
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r__ = (call);                                                                        \
+        if (r__ != ncclSuccess) return fail(ctx, std::string(#call) + ": " + nc->GetErrorString(r__));   \
+    } while (0)
+
+// owned blocks of a rank scattered into vectors over the GLOBAL block index (zero elsewhere): summing the ranks'
+// vectors then reproduces every block's value bit for bit (x + 0 is exact), whatever the number of ranks
+__global__ void scatter_blocks_kernel(const double *llp, const double *ll, const uint8_t *ok, const int32_t *gidx, int C,
+                                      int nblk, int nblk_g, double *g_llp, double *g_ll, int32_t *g_ok) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= C * nblk) return;
+    const int c = u / nblk, b = u % nblk, g = gidx[b];
+    if (g < 0) return;
+    g_llp[(size_t)c * nblk_g + g] = llp[u];
+    g_ll[(size_t)c * nblk_g + g] = ll[u];
+    if (!ok[u]) atomicMin(g_ok + c, 0);
+}
+__global__ void fill_i32_kernel(int32_t *p, int n, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+}  // namespace
+
 // =================================================================================================
 extern "C" {
 
@@ -601,6 +696,7 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
             if (sv.snap) { cudaEventDestroy(sv.snap); cudaEventDestroy(sv.landed); }
         }
     }
+    comm_release(ctx);
     auto rel_law = [](Law &l) { l.d_auxB.release(); l.d_auxbeta.release(); l.d_auxatil.release(); };
     rel_law(ctx->law[0]);
     rel_law(ctx->law[1]);
@@ -615,7 +711,7 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     ctx->d_xoff.release(); ctx->d_xs.release();
     ctx->d_pt_off.release(); ctx->d_st_off.release(); ctx->d_t.release(); ctx->d_rho.release(); ctx->d_Hobs.release();
     ctx->d_Fobs.release(); ctx->d_cobs.release(); ctx->d_x0.release(); ctx->d_ll.release();
-    ctx->d_Z.release(); ctx->d_E.release();
+    ctx->d_Z.release(); ctx->d_E.release(); ctx->d_v.release();
     for (int b = 0; b < 2; ++b) {
         ctx->d_X[b].release(); ctx->d_W[b].release(); ctx->d_selX[b].release(); ctx->d_selW[b].release();
     }
@@ -693,6 +789,7 @@ int dmcmc_set_obs(dmcmc_ctx *ctx, int32_t p, const double *L, const double *Sigm
     ctx->Sigma.assign(Sigma, Sigma + J * p * p);
     ctx->v.assign(v, v + J * p);
     if (compute_obs_terms(ctx)) return -1;
+    if (upload(ctx, ctx->d_v, ctx->v)) return -1;
     ctx->have_obs = true;
     for (int s = 0; s < 2; ++s)
         if (ctx->law[s].have_theta && build_aux(ctx, s)) return -1;
@@ -1309,8 +1406,10 @@ int dmcmc_relayout(dmcmc_ctx *ctx, int32_t nblk, const int32_t *i1, const int32_
     return sync(ctx);
 }
 
-int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical,
-                       double *out_ll_prop, uint8_t *out_success) {
+// set_proposal! up to and including the solve (src/run!_alterations.jl:177-208): theta deg into the proposal law, aux law
+// and backward filter when critical, fixed-noise solve of every (chain, block) -- enqueued; per-unit ll deg and success
+// are left on the device (d_param_llprop, d_out_acc)
+static int param_solve_async(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical, int *nblk_out) {
     REQUIRE(ctx && theta_prop, "dmcmc_param_loglik: bad argument");
     REQUIRE(ntheta == ctx->nth, "dmcmc_param_loglik: wrong number of parameters for this model");
     REQUIRE(ctx->lay_cur >= 0, "dmcmc_param_loglik: no layout set");
@@ -1328,7 +1427,8 @@ int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta,
     } else {
         // non-critical: aux law and tables are those of the current law
         Law &lc = ctx->law[cur];
-        lp.auxB = lc.auxB; lp.auxbeta = lc.auxbeta; lp.auxsig = lc.auxsig; lp.custom_aux = lc.custom_aux;
+        lp.custom_aux = lc.custom_aux;
+        if (lc.custom_aux) { lp.auxB = lc.auxB; lp.auxbeta = lc.auxbeta; lp.auxsig = lc.auxsig; }
         if (build_aux(ctx, prop)) return -1;
         Tables &tc = lay.tab[cur], &tp = lay.tab[prop];
         REQUIRE(tc.valid, "dmcmc_param_loglik: current tables missing");
@@ -1352,6 +1452,15 @@ int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta,
     sp.out_llprop = ctx->d_param_llprop.p;
     sp.out_acc = ctx->d_out_acc.p;
     if (timed_launch(ctx, MODE_PARAM, sp)) return -1;
+    *nblk_out = sp.nblk;
+    return 0;
+}
+
+int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical,
+                       double *out_ll_prop, uint8_t *out_success) {
+    int nblk = 0;
+    if (param_solve_async(ctx, theta_prop, ntheta, critical, &nblk)) return -1;
+    const size_t n = (size_t)ctx->C * nblk;
     ctx->h_param_llprop.resize(n);
     std::vector<uint8_t> okb(n);
     CK(cudaMemcpyAsync(ctx->h_param_llprop.data(), ctx->d_param_llprop.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1361,7 +1470,7 @@ int dmcmc_param_loglik(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta,
     if (out_success)
         for (int c = 0; c < ctx->C; ++c) {
             uint8_t ok = 1;
-            for (int b = 0; b < sp.nblk; ++b) ok &= okb[(size_t)c * sp.nblk + b];
+            for (int b = 0; b < nblk; ++b) ok &= okb[(size_t)c * nblk + b];
             out_success[c] = ok;
         }
     ctx->param_pending = true;
@@ -1703,4 +1812,158 @@ extern "C" double dmcmc_fp64_peak(int32_t device) {
     cudaEventDestroy(e1);
     cudaFree(out);
     return best;
+}
+
+// =================================================================================================
+// Block-sharded recording over the GPUs of one box: the collectives live in the library, so a host without
+// torch.distributed (the Julia plugin) gets the end-point exchange and the parameter-step all-reduce through ccall.
+// =================================================================================================
+extern "C" int dmcmc_comm_unique_id(void *id128) {
+    dmcmc_ctx *ctx = nullptr;
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    if (!nc) return fail(nullptr, err);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NK(nc->GetUniqueId(reinterpret_cast<ncclUniqueId *>(id128)));
+    return 0;
+}
+
+extern "C" int dmcmc_comm_init(dmcmc_ctx *ctx, const void *id128, int32_t rank, int32_t world) {
+    REQUIRE(ctx && id128 && world >= 1 && rank >= 0 && rank < world, "dmcmc_comm_init: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    REQUIRE(nc, "dmcmc_comm_init: " + err);
+    if (ctx->comm) { nc->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NK(nc->CommInitRank(&ctx->comm, world, id, rank));
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    return 0;
+}
+
+extern "C" int dmcmc_comm_destroy(dmcmc_ctx *ctx) {
+    REQUIRE(ctx, "dmcmc_comm_destroy: null context");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (sync(ctx)) return -1;
+    comm_release(ctx);
+    ctx->comm_rank = 0;
+    ctx->comm_world = 1;
+    return 0;
+}
+
+static int seg_on_stream(dmcmc_ctx *ctx, int j0, int j1, double *dev, int64_t stride, int up) {
+    const int steps = ctx->st_off[j1] - ctx->st_off[j0];
+    SegmentParams g{};
+    g.C = ctx->C; g.D = ctx->d; g.j0 = j0; g.j1 = j1; g.steps = steps; g.TT = ctx->TT;
+    g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_st_off = ctx->d_st_off.p;
+    g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
+    g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
+    g.selX = ctx->d_selX[ctx->sel_cur].p;
+    g.packed = dev; g.upload = up; g.pk_stride = stride;
+    CK(launch_segment(g, ctx->stream));
+    return 0;
+}
+
+// The exchange that follows a sweep of a block-sharded chequerboard sampler.  This context holds the contiguous
+// interval range its rank owns followed by a halo of n_halo intervals owned by the right neighbour (0 on the last rank).
+//   after_pattern 0 (blocks end on rank edges):  rank r -> r-1 : accepted path of my first n_first intervals
+//                                                (the left neighbour's halo: n_first there == its n_halo)
+//   after_pattern 1 (blocks straddle the edges): rank r -> r+1 : my last owned interval (its end point is the
+//                                                neighbour's new starting point) followed by the halo I just updated
+// left_edge_steps = Euler steps of the left neighbour's last owned interval (0 on rank 0).  Everything is enqueued on the
+// context's stream (pack kernel, ncclSend/ncclRecv, unpack kernel): no host synchronisation.
+extern "C" int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_t n_first, int32_t n_halo,
+                                   int32_t left_edge_steps) {
+    REQUIRE(ctx && ctx->comm, "dmcmc_halo_exchange: call dmcmc_comm_init first");
+    REQUIRE(ctx->R == 1, "dmcmc_halo_exchange: block sharding is defined for a single recording");
+    const int r = ctx->comm_rank, w = ctx->comm_world, J = ctx->J, d = ctx->d;
+    REQUIRE(n_first > 0 && n_first <= J - n_halo && n_halo >= 0 && n_halo < J, "dmcmc_halo_exchange: bad interval counts");
+    REQUIRE((r < w - 1) == (n_halo > 0) || w == 1, "dmcmc_halo_exchange: every rank but the last holds a halo");
+    CK(cudaSetDevice(ctx->cfg.device));
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    REQUIRE(nc, "dmcmc_halo_exchange: " + err);
+    const int n_own = J - n_halo;
+    const size_t C = (size_t)ctx->C;
+    if (after_pattern == 0) {
+        const size_t send_n = r > 0 ? C * (size_t)(ctx->st_off[n_first] - ctx->st_off[0]) * d : 0;
+        const size_t recv_n = r < w - 1 ? C * (size_t)(ctx->st_off[J] - ctx->st_off[n_own]) * d : 0;
+        CK(ctx->cb_send.ensure(std::max<size_t>(send_n, 1)));
+        CK(ctx->cb_recv.ensure(std::max<size_t>(recv_n, 1)));
+        if (send_n && seg_on_stream(ctx, 0, n_first, ctx->cb_send.p, (int64_t)(send_n / C), 0)) return -1;
+        NK(nc->GroupStart());
+        if (send_n) NK(nc->Send(ctx->cb_send.p, send_n, ncclDouble, r - 1, ctx->comm, ctx->stream));
+        if (recv_n) NK(nc->Recv(ctx->cb_recv.p, recv_n, ncclDouble, r + 1, ctx->comm, ctx->stream));
+        NK(nc->GroupEnd());
+        if (recv_n && seg_on_stream(ctx, n_own, J, ctx->cb_recv.p, (int64_t)(recv_n / C), 1)) return -1;
+        if (recv_n) ctx->w_valid = false;
+    } else {
+        const size_t send_n = r < w - 1 ? C * (size_t)(ctx->st_off[J] - ctx->st_off[n_own - 1]) * d : 0;
+        const size_t first_steps = (size_t)(ctx->st_off[n_first] - ctx->st_off[0]);
+        const size_t recv_n = r > 0 ? C * ((size_t)left_edge_steps + first_steps) * d : 0;
+        REQUIRE(r == 0 || left_edge_steps > 0, "dmcmc_halo_exchange: left_edge_steps missing");
+        CK(ctx->cb_send.ensure(std::max<size_t>(send_n, 1)));
+        CK(ctx->cb_recv.ensure(std::max<size_t>(recv_n, 1)));
+        if (send_n && seg_on_stream(ctx, n_own - 1, J, ctx->cb_send.p, (int64_t)(send_n / C), 0)) return -1;
+        NK(nc->GroupStart());
+        if (send_n) NK(nc->Send(ctx->cb_send.p, send_n, ncclDouble, r + 1, ctx->comm, ctx->stream));
+        if (recv_n) NK(nc->Recv(ctx->cb_recv.p, recv_n, ncclDouble, r - 1, ctx->comm, ctx->stream));
+        NK(nc->GroupEnd());
+        if (recv_n) {
+            const int64_t stride = (int64_t)(recv_n / C);
+            // the edge interval's last point is my new starting point; the rest are my first n_first intervals
+            CK(launch_set_start(ctx->d_x0.p, ctx->cb_recv.p + (size_t)(left_edge_steps - 1) * d, stride, ctx->C, ctx->R, d, ctx->stream));
+            if (seg_on_stream(ctx, 0, n_first, ctx->cb_recv.p + (size_t)left_edge_steps * d, stride, 1)) return -1;
+            ctx->w_valid = false;
+        }
+    }
+    return 0;
+}
+
+// a9 for a block-sharded recording: set_proposal! on every rank's blocks, then ONE decision for all blocks
+// (src/run!_alterations.jl:177-211, :367) needs the ll deg of every block of every rank.  blk_global[b] = global index of
+// local block b under the current layout, or -1 when another rank owns it (halo).  Out (identical on every rank, and
+// bit for bit what the unsharded context gives): ll deg and current ll of every global block [n_chains][nblk_global],
+// success AND-reduced over all blocks [n_chains].  Follow with dmcmc_param_commit(accepted) on every rank.
+extern "C" int dmcmc_param_loglik_sharded(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical,
+                                          int32_t nblk_global, const int32_t *blk_global, double *out_ll_prop_global,
+                                          double *out_ll_global, uint8_t *out_success) {
+    REQUIRE(ctx && ctx->comm, "dmcmc_param_loglik_sharded: call dmcmc_comm_init first");
+    REQUIRE(blk_global && nblk_global > 0, "dmcmc_param_loglik_sharded: bad argument");
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    REQUIRE(nc, "dmcmc_param_loglik_sharded: " + err);
+    int nblk = 0;
+    if (param_solve_async(ctx, theta_prop, ntheta, critical, &nblk)) return -1;
+    for (int b = 0; b < nblk; ++b) REQUIRE(blk_global[b] < nblk_global, "dmcmc_param_loglik_sharded: global block index out of range");
+    const size_t ng = (size_t)ctx->C * nblk_global;
+    CK(ctx->d_gl_llp.ensure(ng));
+    CK(ctx->d_gl_ll.ensure(ng));
+    CK(ctx->d_gl_ok.ensure(ctx->C));
+    CK(ctx->d_gidx.ensure(nblk));
+    CK(cudaMemcpyAsync(ctx->d_gidx.p, blk_global, nblk * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_gl_llp.p, 0, ng * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_gl_ll.p, 0, ng * sizeof(double), ctx->stream));
+    fill_i32_kernel<<<(unsigned)((ctx->C + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_gl_ok.p, ctx->C, 1);
+    const int nu = ctx->C * nblk;
+    scatter_blocks_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, ctx->stream>>>(
+        ctx->d_param_llprop.p, ctx->d_ll.p, ctx->d_out_acc.p, ctx->d_gidx.p, ctx->C, nblk, nblk_global, ctx->d_gl_llp.p,
+        ctx->d_gl_ll.p, ctx->d_gl_ok.p);
+    CK(cudaGetLastError());
+    NK(nc->GroupStart());
+    NK(nc->AllReduce(ctx->d_gl_llp.p, ctx->d_gl_llp.p, ng, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    NK(nc->AllReduce(ctx->d_gl_ll.p, ctx->d_gl_ll.p, ng, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    NK(nc->AllReduce(ctx->d_gl_ok.p, ctx->d_gl_ok.p, (size_t)ctx->C, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+    NK(nc->GroupEnd());
+    std::vector<int32_t> okh(ctx->C);
+    if (out_ll_prop_global) CK(cudaMemcpyAsync(out_ll_prop_global, ctx->d_gl_llp.p, ng * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ll_global) CK(cudaMemcpyAsync(out_ll_global, ctx->d_gl_ll.p, ng * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(okh.data(), ctx->d_gl_ok.p, ctx->C * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    if (out_success)
+        for (int c = 0; c < ctx->C; ++c) out_success[c] = (uint8_t)(okh[c] != 0);
+    ctx->param_pending = true;
+    return 0;
 }

@@ -144,5 +144,8 @@ struct BFParams {
     double *blk_c0, *blk_g, *blk_Qc;
 };
 cudaError_t launch_backward_filter(const BFParams &b, cudaStream_t s);
+// built-in aux law (B, beta, a~ = sigma~ sigma~') of every interval from theta and the end observations v [J][p]
+cudaError_t launch_aux_build(int model, int d, int m, int p, int J, const Theta &th, const double *v, double *B, double *beta,
+                             double *atil, cudaStream_t s);
 
 }  // namespace dmcmc

@@ -173,8 +173,8 @@ inline int model_dims(int model, int d_in, int *d, int *m, int *nth) {
     return -1;
 }
 
-inline void aux_build_host(int model, int d, int m, const double *th, const double *v, int p,
-                           double *B, double *beta, double *sig) {
+__host__ __device__ inline void aux_build_host(int model, int d, int m, const double *th, const double *v, int p,
+                                               double *B, double *beta, double *sig) {
     for (int i = 0; i < d * d; ++i) B[i] = 0.0;
     for (int i = 0; i < d; ++i) beta[i] = 0.0;
     for (int i = 0; i < d * m; ++i) sig[i] = 0.0;

@@ -242,6 +242,35 @@ class Engine:
     def param_commit(self, accepted):
         self._ck(self.lib.dmcmc_param_commit(self.h, int(bool(accepted))))
 
+    # -- block-sharded recording: collectives inside the library (NCCL bound at run time) ----------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (dmcmc_comm_unique_id): made by one rank, handed to the others by the host."""
+        buf = C.create_string_buffer(128)
+        if _lib.load().dmcmc_comm_unique_id(buf) != 0:
+            raise DmcmcError(_lib.load().dmcmc_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        self._ck(self.lib.dmcmc_comm_init(self.h, C.c_char_p(unique_id), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.dmcmc_comm_destroy(self.h))
+
+    def halo_exchange(self, after_pattern, n_first, n_halo, left_edge_steps):
+        self._ck(self.lib.dmcmc_halo_exchange(self.h, int(after_pattern), int(n_first), int(n_halo), int(left_edge_steps)))
+
+    def param_loglik_sharded(self, theta_prop, nblk_global, blk_global, critical=True):
+        """dmcmc_param_loglik_sharded: (ll deg, ll) of every GLOBAL block [C][nblk_global] and success [C], identical on
+        every rank."""
+        th, gi = _f64(theta_prop), _i32(blk_global)
+        assert len(gi) == self._sync_nblk()
+        llp, ll = np.empty((self.C, nblk_global)), np.empty((self.C, nblk_global))
+        ok = np.empty(self.C, np.uint8)
+        self._ck(self.lib.dmcmc_param_loglik_sharded(self.h, _dp(th), len(th), int(critical), int(nblk_global), _ip(gi),
+                                                     _dp(llp), _dp(ll), _bp(ok)))
+        return llp, ll, ok.astype(bool)
+
     def conjugate_coords(self):
         """theta indices of the law's conjugate parameters (dmcmc_conjugate_dim)."""
         idx = np.zeros(8, np.int32)

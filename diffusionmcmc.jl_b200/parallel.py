@@ -277,6 +277,52 @@ class DeviceHalo:
             self.take_b()
 
 
+class LibHalo:
+    """The same exchange with the collectives INSIDE the library (dmcmc_comm_init / dmcmc_halo_exchange /
+    dmcmc_param_loglik_sharded: NCCL send/recv and all-reduce enqueued on the context's stream by the C ABI itself) --
+    what a host without torch.distributed, i.e. the Julia plugin, calls.  `unique_id` comes from
+    Engine.comm_unique_id() on one rank and is handed to the others by the host."""
+
+    def __init__(self, sampler, unique_id):
+        s = self.s = sampler
+        s.engine.comm_init(unique_id, s.rank, s.world)
+        n_own = s.b - s.a
+        self.n_first = min(s.h, n_own)
+        self.n_halo = s.b_ext - s.b
+        self.left_edge_steps = int(s.N_left_edge) if s.rank > 0 else 0
+
+    def iterate(self, it):
+        s, e = self.s, self.s.engine
+        s.sweep_async(0, 2 * it)
+        if s.world > 1:
+            e.halo_exchange(0, self.n_first, self.n_halo, self.left_edge_steps)
+        s.sweep_async(1, 2 * it + 1)
+        if s.world > 1:
+            e.halo_exchange(1, self.n_first, self.n_halo, self.left_edge_steps)
+
+    def global_blocks(self):
+        """(nblk_global, global index of every local block of pattern 0, -1 for the halo filler)."""
+        s = self.s
+        i1, i2, pin, act = s.lays[0]
+        unit = 2 * s.h
+        gidx = np.where(act > 0, (s.a + i1) // unit, -1).astype(np.int32)
+        return (s.n + unit - 1) // unit, gidx
+
+    def param_step(self, theta_prop, decide, critical=True):
+        """Parameter update on the sharded recording under pattern 0 (its blocks never cross a rank edge): every rank
+        solves its blocks, ll deg is all-reduced per global block, `decide(llp_global, ll_global, ok)` -> bool must be
+        the same function of the same numbers on every rank (shared seed), then every rank commits."""
+        s, e = self.s, self.s.engine
+        i1, i2, pin, act = s.lays[0]
+        e.relayout(i1, i2, pin)
+        e.set_block_mask(act)
+        nb_g, gidx = self.global_blocks()
+        llp, ll, ok = e.param_loglik_sharded(theta_prop, nb_g, gidx, critical)
+        accepted = bool(decide(llp, ll, ok))
+        e.param_commit(accepted)
+        return llp, ll, ok, accepted
+
+
 class TorchComm:
     """send/recv of float64 NumPy arrays over torch.distributed (NCCL: staged through a CUDA
     tensor; gloo: CPU tensor)."""

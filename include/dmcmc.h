@@ -208,6 +208,32 @@ void *dmcmc_stream(dmcmc_ctx *ctx);
  * (dmcmc_get_ll / dmcmc_accept_counts read them later). */
 int dmcmc_impute_async(dmcmc_ctx *ctx, uint32_t iter);
 
+/* -- collectives of a block-sharded recording, inside the library -----------------------
+ * One context per GPU/process; the ranks that share one long recording form an NCCL communicator.  The
+ * unique id (128 bytes) is made by one rank and handed to the others by the host (file, socket, MPI ...).
+ * NCCL is bound at run time (libnccl.so.2); a process that already carries one (PyTorch) is reused. */
+int dmcmc_comm_unique_id(void *id128);
+int dmcmc_comm_init(dmcmc_ctx *ctx, const void *id128, int32_t rank, int32_t world);
+int dmcmc_comm_destroy(dmcmc_ctx *ctx);
+/* End-point / halo exchange after a sweep (ncclSend / ncclRecv on the context's stream, packed by the
+ * library, no host synchronisation).  The context holds its rank's contiguous interval range followed by
+ * a halo of n_halo intervals owned by the right neighbour (0 on the last rank); n_first = my first
+ * intervals that the LEFT neighbour holds as its halo.
+ *   after_pattern 0: rank r -> r-1 accepted path of my first n_first intervals
+ *   after_pattern 1: rank r -> r+1 my last owned interval (its end = the neighbour's new start point) + halo
+ * left_edge_steps: Euler steps of the left neighbour's last owned interval (0 on rank 0). */
+int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_t n_first, int32_t n_halo,
+                        int32_t left_edge_steps);
+/* a9 on a block-sharded recording (set_proposal!, src/run!_alterations.jl:177-211; ONE accept decision
+ * for all blocks, :367): every rank solves its blocks, the per-block ll deg / ll are all-reduced over the
+ * GLOBAL block index (blk_global[b] = global index of local block b, -1 = owned by another rank) and
+ * `success` is AND-reduced.  Outputs are identical on all ranks and bit-identical to the unsharded
+ * context's: out_ll_prop_global, out_ll_global [n_chains][nblk_global], out_success [n_chains].
+ * Follow with dmcmc_param_commit(accepted) on every rank. */
+int dmcmc_param_loglik_sharded(dmcmc_ctx *ctx, const double *theta_prop, int32_t ntheta, int32_t critical,
+                               int32_t nblk_global, const int32_t *blk_global, double *out_ll_prop_global,
+                               double *out_ll_global, uint8_t *out_success);
+
 /* -- measurement helpers (bench.py) ----------------------------------------------------------- */
 /* Device time (ms, CUDA events on the context's stream) and launch count of the solve kernels
  * since the previous call, per kernel mode: [0] imputation, [1] parameter-step solve,
