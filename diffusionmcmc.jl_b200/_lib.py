@@ -20,6 +20,12 @@ class Config(C.Structure):
 
 ABI_VERSION = 5
 
+
+class Adapt(C.Structure):
+    _fields_ = [("target_accpt_rate", C.c_double), ("scale", C.c_double), ("min", C.c_double), ("max", C.c_double),
+                ("offset", C.c_double), ("adapt_every_k_steps", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/dmcmc.h declares
 SYMBOLS = {
     "dmcmc_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -41,6 +47,8 @@ SYMBOLS = {
     "dmcmc_impute": (C.c_int, [C.c_void_p, C.c_uint32, _dp, _dp, _dp, _dp, _bp]),
     "dmcmc_run_sweeps": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, _dp,
                                    C.c_int32, _dp, _dp, _bp]),
+    "dmcmc_set_adaptation": (C.c_int, [C.c_void_p, C.POINTER(Adapt), C.c_int32, _dp, _dp]),
+    "dmcmc_get_rho": (C.c_int, [C.c_void_p, C.c_int32, _dp]),
     "dmcmc_host_alloc": (C.c_void_p, [C.c_size_t]),
     "dmcmc_host_free": (None, [C.c_void_p]),
     "dmcmc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),

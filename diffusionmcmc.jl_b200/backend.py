@@ -264,7 +264,7 @@ class _ImputationState:
 
 def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, path_buffer_size=1,
          n_chains=None, device=0, seed=0, chain_offset=0, save_every=100, rng=None,
-         exclude_updates=(), save_chains=(0,)):
+         exclude_updates=(), save_chains=(0,), device_adaptation=True):
     """`run!(mcmc, num_mcmc_steps, data, θinit, callbacks; dt, path_buffer_size, ...)`.
 
     `data` is a spec dict from problems.make_spec (the `AllObservations` stand-in).  When `dt`
@@ -272,7 +272,8 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
     (OBS.setup_time_grids, src/workspaces.jl:164-170; default there is 0.01).
     `save_every` replaces the reference's hard-coded 100 (src/run!_alterations.jl:52); `save_chains` are the chains
     whose glued accepted paths go into `XX_buffer` (one: `x` is [points][d] like the reference's; several:
-    [chain][points][d]).  Returns (global_ws, local_wss)."""
+    [chain][points][d]).  `device_adaptation`: in a pure-imputation schedule the pCN memory is adapted on the device
+    (dmcmc_set_adaptation), so the sweep loop only returns to the host to save paths.  Returns (global_ws, local_wss)."""
     spec = dict(data)
     if dt is not None:
         N, t = setup_time_grids(spec.get("t0", 0.0), spec["obs_times"], dt)
@@ -360,27 +361,42 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
         # (dmcmc_run_sweeps) between the points where the host must look: adaptation and saving.
         half_len = plan.half_len[0] if has_switch else 0
         stride = max(w._acc.shape[2] for w in lws)
-        k_adapt = min([st.adpt.v[0].adapt_every_k_steps for st in states.values()
-                       if isinstance(st.adpt, AdaptationMultiPathImputation)] or [save_every])
-        max_sw = max(1, min(k_adapt, save_every, num_mcmc_steps)) * nu
+        adaptive = [st for st in states.values() if isinstance(st.adpt, AdaptationMultiPathImputation)]
+        k_adapt = min([st.adpt.v[0].adapt_every_k_steps for st in adaptive] or [save_every])
+        # device-side adaptation (dmcmc_set_adaptation): one rho vector and one set of counters per chequerboard pattern,
+        # so it applies when every (update, pattern) state has its own pattern slot and all share one configuration
+        slot = {key: (key[1] if key[1] is not None else 0) for key in states}
+        cfgs = {tuple(getattr(st.adpt.v[0], f) for f in ("target_accpt_rate", "adapt_every_k_steps", "scale", "min", "max", "offset"))
+                for st in adaptive}
+        dev_adapt = (device_adaptation and adaptive and len(adaptive) == len(states) and len(cfgs) == 1
+                     and len(set(slot.values())) == len(slot))
+        by_slot = {slot[key]: st for key, st in states.items()}
+        if dev_adapt:
+            eng.set_adaptation(adaptive[0].adpt.v[0], nu, by_slot[0].rho_per_interval(J),
+                               by_slot.get(1, by_slot[0]).rho_per_interval(J))
+            k_adapt = save_every            # no reason to come back to the host for the adaptation
+        row_bytes = C * stride * 17 * nu    # history bytes per MCMC iteration
+        max_it = max(1, min(k_adapt, save_every, num_mcmc_steps, (256 << 20) // max(1, row_bytes)))
+        max_sw = max_it * nu
         # pinned host arrays (dmcmc_host_alloc): the history rows land in them by DMA, no staging copy
         rho_buf = eng.pinned((max_sw, J), np.float64)
         hist_buf = (eng.pinned((max_sw, C, stride), np.float64), eng.pinned((max_sw, C, stride), np.float64),
                     eng.pinned((max_sw, C, stride), np.uint8))
         it = 0
         while it < num_mcmc_steps:
-            chunk = min(num_mcmc_steps - it, max(1, min(k_adapt, save_every - (it % save_every))))
+            chunk = min(num_mcmc_steps - it, max_it, max(1, min(k_adapt, save_every - (it % save_every))))
             nsw = chunk * nu
             sweep_state = []
             for s in range(nsw):
                 ui, mcmciter = s % nu, it + s // nu + 1
                 sweep_state.append(states[(ui, plan.pattern(ui, mcmciter))])
-                rho_buf[s] = sweep_state[-1].rho_per_interval(J)
+                if not dev_adapt:
+                    rho_buf[s] = sweep_state[-1].rho_per_interval(J)
             hist = tuple(h[:nsw] for h in hist_buf)
             if half_len == 0 and not same(cur_layout, sweep_state[0].layout):
                 eng.relayout(*sweep_state[0].layout)
             first_pattern = plan.pattern(0, it + 1) or 0
-            eng.run_sweeps(it * nu, nsw, half_len, first_pattern, rho_buf[:nsw], hist)
+            eng.run_sweeps(it * nu, nsw, half_len, first_pattern, None if dev_adapt else rho_buf[:nsw], hist)
             cur_layout = sweep_state[-1].layout
             eng.nblk = len(cur_layout[0])
             for s, st in enumerate(sweep_state):
@@ -391,10 +407,16 @@ def run_(mcmc, num_mcmc_steps, data, theta_init=None, callbacks=(), dt=None, pat
                 w._acc[row, :, :nb] = hist[2][s][:, :nb].astype(bool)
                 w._llp[row, :, nb:] = np.nan     # blocks this sweep's pattern does not have
                 w._ll[row, :, nb:] = np.nan
-                st.register_and_adapt(hist[2][s][:, :nb].sum(axis=0, dtype=np.int64), np.full(nb, C), row + 1)
+                if not dev_adapt:
+                    st.register_and_adapt(hist[2][s][:, :nb].sum(axis=0, dtype=np.int64), np.full(nb, C), row + 1)
             it += chunk
             if it % save_every == 0:
                 save_paths()
+        if dev_adapt:   # bring the adapted rho back into the host-side states
+            for sl, st in by_slot.items():
+                rho = eng.get_rho(sl)
+                st.rho_s = [[float(rho[a])] * int(e - a + 1) for a, e in zip(st.layout[0], st.layout[1])]
+            eng.set_adaptation(None)
         gws.state_history = [theta.copy() for _ in range(num_mcmc_steps)]
         return finish()
 

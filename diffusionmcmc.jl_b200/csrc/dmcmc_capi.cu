@@ -155,12 +155,19 @@ struct dmcmc_ctx {
     std::vector<double> h_param_llprop;
     bool param_pending = false;
     bool w_valid = false;  // stored accepted W is consistent with the accepted X under the current law/layout
-    int threads = 64;
+    int threads = 0;      // threads per CTA of the thread-per-unit solve kernel (0: chosen by the launcher)
     bool fast_step = true;  // allow model-specific fused steps (dmcmc_set_fast_step)
     int coop = -1;          // warp-per-unit imputation kernel: -1 auto, 0 never, 1 always (dmcmc_set_cooperative)
     SweepIO io;
     PathSave saves[4];
     cudaStream_t save_stream = nullptr;
+    // device-side adaptation of the pCN memory inside dmcmc_run_sweeps (src/adaptation.jl:82-149): per chequerboard
+    // pattern a rho vector [J] and accept / proposal counters per block [2][J]
+    bool adapt_on = false;
+    dmcmc_adapt adapt{};
+    int adapt_spi = 1;
+    DevBuf<double> d_rho_pat[2];
+    DevBuf<unsigned long long> d_cnt_pat[2];
     // block-sharded recording: NCCL communicator of the ranks that share it, and its message buffers
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_world = 1;
@@ -597,6 +604,27 @@ NcclApi *nccl_api(std::string &err) {
     return &g_nccl;
 }
 
+// readjust! on the device (src/adaptation.jl:82-90 with eMCMC.compute_delta / compute_eps [UPSTREAM-RECALL], the host
+// mirror's AdaptationPathImputation.readjust): one thread per block of the sweep's layout; a block whose counter has
+// reached adapt_every_k_steps proposals takes a step of size delta in logit space, DOWN when its acceptance rate is
+// above the target, and starts counting afresh
+__global__ void adapt_rho_kernel(int nblk, const int32_t *i1, const int32_t *i2, unsigned long long *acc,
+                                 unsigned long long *prop, double *rho, dmcmc_adapt a, double mcmciter) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const unsigned long long np = prop[b];
+    if (np < (unsigned long long)a.adapt_every_k_steps) return;
+    const double rate = (double)acc[b] / (double)np;
+    const double delta = a.scale / sqrt(fmax(1.0, mcmciter / (double)a.adapt_every_k_steps - a.offset));
+    const double r = fmin(fmax(rho[i1[b]], a.min), a.max);
+    const double step = rate > a.target_accpt_rate ? -delta : delta;
+    const double lg = log(r) - log(1.0 - r) + step;
+    const double nr = fmin(fmax(1.0 / (1.0 + exp(-lg)), a.min), a.max);
+    for (int j = i1[b]; j <= i2[b]; ++j) rho[j] = nr;
+    acc[b] = 0;
+    prop[b] = 0;
+}
+
 void comm_release(dmcmc_ctx *ctx) {
     if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
     ctx->comm = nullptr;
@@ -717,6 +745,7 @@ void dmcmc_destroy(dmcmc_ctx *ctx) {
     }
     ctx->d_mask.release(); ctx->d_out_acc.release(); ctx->d_out_llprop.release();
     ctx->d_out_ll.release(); ctx->d_param_llprop.release(); ctx->d_counts.release();
+    for (int i = 0; i < 2; ++i) { ctx->d_rho_pat[i].release(); ctx->d_cnt_pat[i].release(); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1244,6 +1273,7 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
                      double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted) {
     REQUIRE(ctx && n_sweeps >= 0, "dmcmc_run_sweeps: bad argument");
     REQUIRE(ctx->lay_cur >= 0, "dmcmc_run_sweeps: no layout set");
+    REQUIRE(!(ctx->adapt_on && rho_sched), "dmcmc_run_sweeps: with dmcmc_set_adaptation the pCN memory lives on the device; pass rho_sched = NULL");
     CK(cudaSetDevice(ctx->cfg.device));
     const bool want_hist = hist_ll_prop || hist_ll || hist_accepted;
     // the two chequerboard layouts (integer ranges; src/blocking.jl:7-9)
@@ -1330,12 +1360,14 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             SolveParams sp;
             if (fill_params(ctx, sp, ctx->law_cur)) return -1;
             if (rho_sched) sp.rho = io.d_rho.p + J * (size_t)(it % CHUNK);
+            const int aslot = half_len > 0 ? pat : 0;
+            if (ctx->adapt_on) sp.rho = ctx->d_rho_pat[aslot].p;
             sp.iter = iter0 + (uint32_t)it;
             sp.reinvert = !ctx->w_valid;  // fused layout switch: noise and ll recovered from the accepted X
             sp.store_w = ctx->w_valid;
             sp.out_stride = want_hist ? nblk_stride : sp.nblk;
-            sp.acc_count = ctx->d_counts.p;
-            sp.prop_count = ctx->d_counts.p + ctx->J;
+            sp.acc_count = ctx->adapt_on ? ctx->d_cnt_pat[aslot].p : ctx->d_counts.p;
+            sp.prop_count = sp.acc_count + ctx->J;
             if (want_hist) {
                 uint8_t *d = io.d_hist.p + slot_bytes * slot;
                 sp.out_llprop = hist_ll_prop ? (double *)d : nullptr;
@@ -1345,6 +1377,14 @@ int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t h
             }
             if (timed_launch(ctx, MODE_IMPUTE, sp)) return -1;
             ctx->sel_cur ^= 1;
+            if (ctx->adapt_on) {  // register! + time_to_update + readjust!, stream-ordered behind the sweep
+                const Layout &lay = ctx->layout[ctx->lay_cur];
+                const double mcmciter = (double)((iter0 + (uint32_t)it) / (uint32_t)ctx->adapt_spi + 1u);
+                adapt_rho_kernel<<<(unsigned)((lay.nblk + 127) / 128), 128, 0, ctx->stream>>>(
+                    lay.nblk, lay.d_i1.p, lay.d_i2.p, ctx->d_cnt_pat[aslot].p, ctx->d_cnt_pat[aslot].p + ctx->J,
+                    ctx->d_rho_pat[aslot].p, ctx->adapt, mcmciter);
+                CK(cudaGetLastError());
+            }
             if (want_hist) {
                 CK(cudaEventRecord(io.kernel_done[slot], ctx->stream));
                 CK(cudaStreamWaitEvent(io.s_out, io.kernel_done[slot], 0));
@@ -1965,5 +2005,44 @@ extern "C" int dmcmc_param_loglik_sharded(dmcmc_ctx *ctx, const double *theta_pr
     if (out_success)
         for (int c = 0; c < ctx->C; ++c) out_success[c] = (uint8_t)(okh[c] != 0);
     ctx->param_pending = true;
+    return 0;
+}
+
+// =================================================================================================
+// Device-side adaptation of the pCN memory (src/adaptation.jl:82-149): with it dmcmc_run_sweeps runs
+// straight through the adaptation points -- register!, time_to_update and readjust! happen in a one-thread-per-block
+// kernel behind every sweep -- instead of returning to the host every adapt_every_k_steps iterations.
+// =================================================================================================
+extern "C" int dmcmc_set_adaptation(dmcmc_ctx *ctx, const dmcmc_adapt *cfg, int32_t sweeps_per_iteration,
+                                    const double *rho_pattern0, const double *rho_pattern1) {
+    REQUIRE(ctx && ctx->have_grid, "dmcmc_set_adaptation: call dmcmc_set_grid first");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (!cfg) {
+        ctx->adapt_on = false;
+        return 0;
+    }
+    REQUIRE(cfg->adapt_every_k_steps > 0 && cfg->min > 0.0 && cfg->max < 1.0 && cfg->min < cfg->max && sweeps_per_iteration > 0,
+            "dmcmc_set_adaptation: bad configuration");
+    const size_t J = ctx->J;
+    for (int pat = 0; pat < 2; ++pat) {
+        const double *src = pat == 0 ? rho_pattern0 : (rho_pattern1 ? rho_pattern1 : rho_pattern0);
+        CK(ctx->d_rho_pat[pat].ensure(J));
+        CK(ctx->d_cnt_pat[pat].ensure(2 * J));
+        if (src) CK(cudaMemcpyAsync(ctx->d_rho_pat[pat].p, src, J * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemcpyAsync(ctx->d_rho_pat[pat].p, ctx->d_rho.p, J * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_cnt_pat[pat].p, 0, 2 * J * sizeof(unsigned long long), ctx->stream));
+    }
+    ctx->adapt = *cfg;
+    ctx->adapt_spi = sweeps_per_iteration;
+    ctx->adapt_on = true;
+    return sync(ctx);
+}
+
+extern "C" int dmcmc_get_rho(dmcmc_ctx *ctx, int32_t pattern, double *rho) {
+    REQUIRE(ctx && rho && (pattern == 0 || pattern == 1), "dmcmc_get_rho: bad argument");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (sync(ctx)) return -1;
+    const double *src = ctx->adapt_on ? ctx->d_rho_pat[pattern].p : ctx->d_rho.p;
+    CK(cudaMemcpy(rho, src, (size_t)ctx->J * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }

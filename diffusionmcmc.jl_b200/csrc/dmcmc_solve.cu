@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? 3 : 2) solve_kernel(const So
 
     extern __shared__ __align__(256) double dsm[];
     __shared__ alignas(8) uint64_t full[MAX_DEPTH];
-    const int depth = p.depth, dmask = depth - 1;
+    const int depth = p.depth, dmask = depth - 1, dlog = 31 - __clz(depth);  // depth is 2, 4 or 8
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *stab = dsm;                                                            // [depth][TS][RS]
     double *sinp = dsm + (size_t)depth * TS * RS + (size_t)warp * depth * IS::WARP;  // [depth][NPT][32][2]
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? 3 : 2) solve_kernel(const So
             // ---- table records of this tile: wait, refill the stage freed by the previous tile ----
             __syncthreads();  // every thread is done with tile q-1 (a full/empty mbarrier handshake was measured: no faster)
             if (threadIdx.x == 0) issue_table();
-            mbar_wait(&full[q & dmask], (uint32_t)((q / depth) & 1));
+            mbar_wait(&full[q & dmask], (uint32_t)((q >> dlog) & 1));
             const double *srec = stab + (size_t)(q & dmask) * TS * RS;
             // ---- this tile's input has landed; refill the stage freed by the previous tile ----
             cp_async_wait_depth(depth);
@@ -512,6 +512,9 @@ static cudaError_t launch_one(const SolveParams &p0, int threads, cudaStream_t s
     SolveParams p = p0;
     // few long units (e.g. one block per chain): one warp per CTA so that more SMs take part
     const long long units = (long long)p.C * p.nblk;
+    // CTA size when the caller did not fix it (dmcmc_set_threads): four warps share a table stage when the grid still
+    // fills the machine (C3: 76.7 us per sweep against 77.7 us with two warps), two warps otherwise
+    if (threads <= 0) threads = (MD::D == 2 && units >= 148LL * 128 * 2) ? 128 : 64;
     if (units < 148LL * 64 * 2) threads = 32;
     const unsigned groups = (unsigned)((p.C + threads - 1) / threads);
     const unsigned grid = groups * (unsigned)p.nblk;
@@ -551,7 +554,7 @@ static cudaError_t launch_one(const SolveParams &p0, int threads, cudaStream_t s
 template <class MD, bool PSI, bool FAST>
 static cudaError_t launch_model(int mode, const SolveParams &p, int threads, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
-    threads = ((threads + 31) / 32) * 32;
+    if (threads > 0) threads = ((threads + 31) / 32) * 32;
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
     switch (mode) {
     case MODE_IMPUTE:

@@ -200,6 +200,21 @@ class Engine:
         if want:
             return llp, ll, acc.astype(bool)
 
+    def set_adaptation(self, adpt, sweeps_per_iteration=1, rho0=None, rho1=None):
+        """dmcmc_set_adaptation: `adpt` is an AdaptationPathImputation (or None to switch the device-side adaptation off)."""
+        if adpt is None:
+            self._ck(self.lib.dmcmc_set_adaptation(self.h, None, 1, None, None))
+            return
+        cfg = _lib.Adapt(adpt.target_accpt_rate, adpt.scale, adpt.min, adpt.max, adpt.offset, adpt.adapt_every_k_steps)
+        r0 = None if rho0 is None else _f64(rho0)
+        r1 = None if rho1 is None else _f64(rho1)
+        self._ck(self.lib.dmcmc_set_adaptation(self.h, C.byref(cfg), int(sweeps_per_iteration), _dp(r0), _dp(r1)))
+
+    def get_rho(self, pattern=0):
+        rho = np.empty(self.J)
+        self._ck(self.lib.dmcmc_get_rho(self.h, int(pattern), _dp(rho)))
+        return rho
+
     def pinned(self, shape, dtype):
         """NumPy array over pinned host memory (dmcmc_host_alloc); freed with the engine."""
         dtype = np.dtype(dtype)

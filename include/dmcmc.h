@@ -137,6 +137,23 @@ int dmcmc_impute(dmcmc_ctx *ctx, uint32_t iter, const double *Z, const double *E
 int dmcmc_run_sweeps(dmcmc_ctx *ctx, uint32_t iter0, int32_t n_sweeps, int32_t half_len,
                      int32_t first_pattern, const double *rho_sched, int32_t nblk_stride,
                      double *hist_ll_prop, double *hist_ll, uint8_t *hist_accepted);
+/* Device-side adaptation of the pCN memory (AdaptationPathImputation, src/adaptation.jl:22-41, :82-149; same
+ * field names and meaning): once set, dmcmc_run_sweeps keeps rho per block on the device -- one vector per
+ * chequerboard pattern, started from rho_pattern0 / rho_pattern1 ([J]; NULL: the current dmcmc_set_rho values) --
+ * and after every sweep registers the accept counts and, for every block whose counter has reached
+ * adapt_every_k_steps proposals, takes the logit-space step of readjust! (delta = scale / sqrt(max(1, iter /
+ * adapt_every_k_steps - offset)), iter = MCMC iteration = sweep index / sweeps_per_iteration + 1).  rho_sched must
+ * then be NULL.  cfg = NULL switches it off.  dmcmc_get_rho reads the current vector of a pattern. */
+typedef struct {
+    double target_accpt_rate; /* 0.234 */
+    double scale;             /* 1.0   */
+    double min, max;          /* 1e-12, 1 - 1e-12 */
+    double offset;            /* 1e2   */
+    int32_t adapt_every_k_steps; /* 100: proposals per block between adjustments */
+} dmcmc_adapt;
+int dmcmc_set_adaptation(dmcmc_ctx *ctx, const dmcmc_adapt *cfg, int32_t sweeps_per_iteration,
+                         const double *rho_pattern0, const double *rho_pattern1);
+int dmcmc_get_rho(dmcmc_ctx *ctx, int32_t pattern, double *rho);
 /* Pinned host memory for the streaming buffers above; or page-lock memory the caller already owns
  * (a Julia Array: register once when the workspace is built, unregister before it is freed). */
 void *dmcmc_host_alloc(size_t bytes);
@@ -252,7 +269,7 @@ int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
 /* Measured FP64 FMA throughput of a device in TFLOP/s (independent DFMA chains on every SM, best of five): the
  * denominator of the FP64-pipe view of the Lorenz-96 kernel (bench.py). */
 double dmcmc_fp64_peak(int32_t device);
-/* Threads per CTA of the solve kernels (32..128, multiple of 32; default 64). */
+/* Threads per CTA of the solve kernels (32..128, multiple of 32; default: chosen per launch by unit count). */
 int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
 /* Model-specific fused step kernels (FitzHugh-Nagumo with its built-in aux law); on by default.
  * Off = the generic step for every model (same mathematics, different rounding). */

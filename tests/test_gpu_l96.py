@@ -8,6 +8,14 @@ from helpers import accept_mismatch_is_tie, check, check_scaled, close, interior
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["4_chains_per_warp", "8_chains_per_warp"])
+def l96_mapping(request, monkeypatch):
+    """Every Lorenz-96 test runs under both warp mappings of solve_big_kernel (one or two chains per eight-lane group;
+    the launcher chooses by unit count, these problems are small enough that it would always take the first)."""
+    monkeypatch.setenv("DMCMC_BIG_NC", "1" if request.param == "4_chains_per_warp" else "2")
+    return request.param
+
+
 def _pair(pkg, orc, spec, upload=True, **kw):
     from diffusionmcmc_jl_b200.engine import Engine
     o = orc.Oracle(spec)
@@ -81,3 +89,26 @@ def test_l96_fused_blocked_and_philox(pkg, orc):
         check(f"l96 fused blocked it {it} ll", ll_g, ll_o)
         Xg, _ = e.download_state(0)
         check(f"l96 fused blocked it {it} X", Xg[:, im], o.accepted_X()[:, im])
+
+
+def test_l96_warp_mappings_are_bit_identical(pkg, monkeypatch):
+    """One or two chains per lane group must never change a sample (the per-chain arithmetic is the same, operation for
+    operation): stored-noise sweeps, fused blocked sweeps, parameter-step solve, layout switch -- ragged chain count."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = pkg.problems.l96_spec(n_obs=6, C=11, dt=1e-3, rho=0.8)
+    out = []
+    for nc in ("1", "2"):
+        monkeypatch.setenv("DMCMC_BIG_NC", nc)
+        e = Engine(spec, seed=77)
+        e.init_paths()
+        e.run_sweeps(0, 2, 0)
+        e.run_sweeps(10, 3, 1)
+        X, W = e.download_state(0)
+        llp, ok = e.param_loglik(np.array(spec["theta"]) * (1 + 1e-3), critical=True)
+        e.param_commit(False)
+        e.relayout(*pkg.problems.chequerboard_layout(e.rec_nobs, 2, 1))
+        _, Wr = e.download_state(0)
+        out.append((X, W, e.get_ll().copy(), llp, ok, Wr, e.accept_counts()[0].copy()))
+        e.close()
+    for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "parameter-step ll", "success", "W after a layout switch", "accept counts")):
+        assert np.array_equal(a, b), f"{what} differs between the two warp mappings"

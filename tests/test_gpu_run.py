@@ -127,3 +127,38 @@ def test_two_adaptive_imputations_both_adapt_and_save_several_chains(pkg):
     assert x.shape == (2, 101, 2) and np.isfinite(x).all() and not np.array_equal(x[0], x[1])
     last = gws.XX_buffer.XX[0][0]["x"]           # ring of 3, 4 saves: slot 0 holds the 4th (iteration 200 = final state)
     assert np.array_equal(last[0], gws.engine.download_path(0)) and np.array_equal(last[1], gws.engine.download_path(5))
+
+
+def test_device_side_adaptation_matches_the_host_rule(pkg):
+    """dmcmc_set_adaptation: the kernel's logit step equals AdaptationPathImputation.readjust (same formula, CUDA vs
+    libm exp / log: 1e-12), and run_ with the adaptation on the device drives rho to the same region as with the
+    host-side adaptation."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    data = pkg.problems.fhn_spec(n_obs=10, C=64, dt=0.01)
+    e = Engine(data, seed=9)
+    e.init_paths()
+    cfg = pkg.AdaptationPathImputation(adapt_every_k_steps=2 * 64, scale=0.7, offset=0.0)
+    rho0 = np.full(e.J, 0.6)
+    e.set_adaptation(cfg, 1, rho0, rho0)
+    n, stride = 4, 6
+    hist = (np.empty((n, 64, stride)), np.empty((n, 64, stride)), np.empty((n, 64, stride), np.uint8))
+    e.run_sweeps(0, n, half_len=1, first_pattern=0, hist=hist)       # sweeps 0, 2: pattern 0 (5 blocks); 1, 3: pattern 1 (6)
+    for pat, nb in ((0, 5), (1, 6)):
+        lay = pkg.problems.chequerboard_layout(e.rec_nobs, 1, pat)
+        acc = hist[2][pat::2, :, :nb].astype(np.int64).sum(axis=(0, 1))   # two sweeps of 64 proposals per block = k
+        got = e.get_rho(pat)
+        for b in range(nb):
+            a = pkg.AdaptationPathImputation(adapt_every_k_steps=128, scale=0.7, offset=0.0)
+            a.register(int(acc[b]), 128)
+            assert a.time_to_update()
+            want = a.readjust(0.6, 3 + pat)       # MCMC iteration of the adapting sweep: sweep index (2 + pat) + 1
+            assert np.all(np.abs(got[lay[0][b]:lay[1][b] + 1] - want) <= 1e-12), (pat, b, got[lay[0][b]], want)
+    e.close()
+    # end to end: both ways of adapting end up in the same region
+    out = {}
+    for dev in (True, False):
+        u = pkg.PathImputation(0.3, "FitzHughNagumoAux", adpt=pkg.AdaptationPathImputation(adapt_every_k_steps=50, scale=1.0, offset=0.0))
+        gws, lws = pkg.run_(pkg.MCMC([u]), 1500, pkg.problems.fhn_spec(n_obs=50, C=1, dt=1e-3), None, seed=1, device_adaptation=dev)
+        out[dev] = (u.rho_s[0][0], lws[0].acceptance_history[-500:].mean())
+    assert out[True][0] > 0.8 and out[False][0] > 0.8, out
+    assert abs(out[True][1] - out[False][1]) < 0.2, out

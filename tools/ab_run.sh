@@ -1,7 +1,9 @@
 #!/bin/bash
-# A/B harness: run the C3 probe with each library variant found in ab/ (last one restores ab/lib_base.so)
-for f in ab/lib_*.so ab/lib_base.so; do
+# A/B harness: run the C3 probe with each library variant found in ab/ (the in-tree library is restored afterwards)
+cp diffusionmcmc.jl_b200/csrc/libdmcmc_b200.so /tmp/lib_keep.so
+for f in ab/lib_*.so; do
   cp $f diffusionmcmc.jl_b200/csrc/libdmcmc_b200.so
   echo "== $f"
-  python tools/perf_probe.py 1024 100 1 64 2>&1 | tail -1
+  python tools/perf_probe2.py ${1:-400} ${2:-64} 2>&1 | tail -1
 done
+cp /tmp/lib_keep.so diffusionmcmc.jl_b200/csrc/libdmcmc_b200.so
