@@ -517,11 +517,12 @@ static cudaError_t launch_big_nc(int mode, const SolveParams &p, cudaStream_t s)
 template <int D, bool PSI>
 static cudaError_t launch_big_model(int mode, const SolveParams &p, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
-    // two chains per lane group once there are enough chains to keep the machine busy with eight-chain warps
-    const char *env = getenv("DMCMC_BIG_NC");  // test / A-B override: 1 or 2 (read per launch: the two mappings are bit-identical)
-    const int env_nc = env ? atoi(env) : 0;
-    const long long units = (long long)p.nblk * p.C;
-    const bool two = env_nc ? env_nc == 2 : units >= 148LL * 8 * 4;
+    // Two chains per lane group (NC = 2) halve the shared-memory wavefronts per FMA, but need 255 registers (7 warps per
+    // SM instead of 16): measured on B200, 256 chains, half_len 16 -- 1024 obs: 30.5 ms per sweep against 31.6 ms;
+    // 4096 obs (C5): 119.7 ms against 108.4 ms.  The one-chain mapping stays the default; DMCMC_BIG_NC=2 selects the
+    // other (bit-identical results, tests/test_gpu_l96.py runs both).
+    const char *env = getenv("DMCMC_BIG_NC");  // read per launch
+    const bool two = env && atoi(env) == 2;
     return two ? launch_big_nc<D, PSI, 2>(mode, p, s) : launch_big_nc<D, PSI, 1>(mode, p, s);
 }
 
