@@ -71,7 +71,8 @@ int dmcmc_set_grid(dmcmc_ctx *ctx, int32_t n_recordings, const int32_t *rec_nobs
                    const int32_t *n_steps, const double *t);
 /* Linear-Gaussian observations v_j ~ N(L_j x, Sigma_j) at the right end of interval j
  * (LinearGsnObs, docs/src/tutorials/simple_inference.md:52-60).  L [J][p][d], Sigma [J][p][p],
- * v [J][p]. */
+ * v [J][p].  LinearGsnObs also carries a mean mu (v ~ N(L x + mu, Sigma)): the filter only ever sees
+ * v - mu, so the caller passes v - mu here (julia/DiffusionMCMCB200.jl does). */
 int dmcmc_set_obs(dmcmc_ctx *ctx, int32_t p, const double *L, const double *Sigma,
                   const double *v);
 /* Known starting points (KnownStartingPt), x0 [n_chains][n_recordings][d]. */
