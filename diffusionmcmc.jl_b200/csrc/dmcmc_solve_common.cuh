@@ -201,7 +201,17 @@ __device__ __forceinline__ void load_start(const SolveParams &p, int chain, int 
     }
 }
 
-constexpr int TS = 16;        // Euler steps per staged tile: 256 contiguous bytes per chain for d = 2
+// A/B knobs (defaults are what ships).  Measured on the C3 sweep, B200, CTA of 128 threads: TS 16 / 168 registers 76.2 us;
+// TS 16 / 128 registers 77.1; TS 8 / 160 registers 76.5; TS 8 / 128 registers 77.1 -- the sweep has 51,200 units, i.e.
+// 10.8 warps per SM whatever the register or shared-memory budget allows, and a warp's own in-order dependent-issue
+// latency (~7 cycles per instruction) sets the time, so neither knob moves it.
+#ifndef DMCMC_TS
+#define DMCMC_TS 16
+#endif
+#ifndef DMCMC_MINB
+#define DMCMC_MINB 3
+#endif
+constexpr int TS = DMCMC_TS;        // Euler steps per staged tile: 256 contiguous bytes per chain for d = 2
 constexpr int MAX_DEPTH = 8;  // deepest software pipeline (tiles in flight) of the table / input stages
 
 // ---- shared-memory stage of a chain's input stream (accepted path, or stored accepted noise) ------
