@@ -480,372 +480,6 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? DMCMC_MINB : 2) solve_kernel
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// The production sweep of the headline shape -- FitzHugh-Nagumo, fused layout switch, in-register Philox noise -- with
-// TWO (chain, block) units per thread.  The one-unit kernel above is bound by a warp's own in-order dependent-issue
-// latency (~7 cycles per issued instruction; measured: its time does not move with registers per thread, tile size,
-// CTA size or resident warps, see dmcmc_solve_common.cuh), and the C3 sweep has only 51,200 units = 10.8 warps per SM.
-// Two units of the same block in one thread give every warp two independent instruction streams to interleave, and
-// everything that depends only on the block and the step (table record loads, interval bookkeeping, pipeline control)
-// is done once for both.  Per unit the arithmetic is the one-unit kernel's, operation for operation: bit-identical
-// results (tests/test_gpu_parity.py::test_two_units_per_thread_kernel_is_bit_identical).
-// Thread t of a warp owns chains c0 + t and c0 + 32 + t: each of the warp's two input pipelines stages 32 consecutive
-// chains exactly as above.
-// ---------------------------------------------------------------------------------------------------------------
-template <bool PSI>
-__global__ void __launch_bounds__(128, 2) solve_fhn2_kernel(const SolveParams p) {
-    using MD = ModelFHN;
-    constexpr int D = 2, M = 1, U = 2;
-    using R = Rec<D, PSI>;
-    constexpr int RS = R::SIZE;
-    using IS = InStage<D, M, true>;
-
-    extern __shared__ __align__(256) double dsm[];
-    __shared__ alignas(8) uint64_t full[MAX_DEPTH];
-    const int depth = p.depth, dmask = depth - 1, dlog = 31 - __clz(depth);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *stab = dsm;                                                                  // [depth][TS][RS]
-    double *sinp0 = dsm + (size_t)depth * TS * RS + (size_t)(warp * U) * depth * IS::WARP;  // [U][depth][NPT][32][2]
-
-    const int cpc = (int)blockDim.x * U;  // chains per CTA
-    const int groups = (p.C + cpc - 1) / cpc;
-    const int blk = (int)(blockIdx.x / groups);
-    const int i1 = p.blk_i1[blk], i2 = p.blk_i2[blk];
-    int chain_raw[U], chain[U];
-    bool in_range[U], active[U];
-    size_t uo[U];
-    uint32_t gchain[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        chain_raw[u] = (int)(blockIdx.x % groups) * cpc + (warp * U + u) * 32 + lane;
-        in_range[u] = chain_raw[u] < p.C;
-        chain[u] = in_range[u] ? chain_raw[u] : p.C - 1;  // out-of-range lanes shadow the last chain, stores off
-        uo[u] = (size_t)chain[u] * p.nblk + blk;
-        const bool masked = (p.unit_mask && !p.unit_mask[uo[u]]) || (p.blk_active && !p.blk_active[blk]);
-        active[u] = in_range[u] && !masked;
-        gchain[u] = (uint32_t)(chain[u] + p.chain_offset);
-    }
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < depth; ++i) mbar_init(&full[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    // interval metadata (shared by the two units) and the units' selectors, one interval ahead
-    IvMeta mc = load_meta(p, i1, chain[0], D), mn = mc;
-    int sxc[U], sxn[U];
-    sxc[0] = mc.sx;
-    sxc[1] = p.selX_in[(size_t)i1 * p.C + chain[1]];
-    sxn[0] = sxc[0]; sxn[1] = sxc[1];
-    if (i1 < i2) {
-        mn = load_meta(p, i1 + 1, chain[0], D);
-        sxn[0] = mn.sx;
-        sxn[1] = p.selX_in[(size_t)(i1 + 1) * p.C + chain[1]];
-    }
-    int jc = i1;
-    int tj = i1, ttl = 0, tq = 0;
-    auto issue_table = [&]() {
-        if (tj > i2) return;
-        const int Nj = tj == jc ? mc.N : (tj == jc + 1 ? mn.N : p.iv_N[tj]);
-        const int toffj = tj == jc ? mc.tile_off : (tj == jc + 1 ? mn.tile_off : p.iv_tile_off[tj]);
-        const int npad = ((Nj + TILE - 1) >> 3) * TILE;
-        const int nrec = min(TS, npad - ttl * TS);
-        const uint32_t bytes = (uint32_t)(nrec * RS * sizeof(double));
-        uint64_t *bar = &full[tq & dmask];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(stab + (size_t)(tq & dmask) * TS * RS, p.table + ((size_t)toffj * TILE + (size_t)ttl * TS) * RS, bytes, bar);
-        ++tq;
-        if (++ttl * TS >= Nj) { ttl = 0; ++tj; }
-    };
-    if (threadIdx.x == 0)
-        for (int i = 0; i < depth - 1; ++i) issue_table();
-
-    const bool pinned = PSI && p.blk_pinned[blk];
-    double x[U][D], xb[U][D], xa[U][D];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        load_start<D>(p, chain[u], i1, x[u]);
-#pragma unroll
-        for (int c = 0; c < D; ++c) { xb[u][c] = 0.0; xa[u][c] = x[u][c]; }
-        if (pinned) load_end<D>(p, chain[u], i2, xb[u]);
-    }
-    FhnK fk;
-    fk.set_law(p.th);
-
-    double llp[U], lla[U];
-    {
-        // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (loglikhd_obs)
-        double rec[RS];
-        const double *r0 = p.table_raw + (size_t)p.iv_tile_off[i1] * TILE * RS;
-#pragma unroll
-        for (int i = 0; i < RS; ++i) rec[i] = __ldg(r0 + i);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            double F[D];
-            guiding_F<D, PSI>(rec, xb[u], F);
-            double c = p.blk_c0[blk];
-            if (pinned) {
-                double gx = 0.0, qq = 0.0;
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    gx += p.blk_g[(size_t)blk * D + i] * xb[u][i];
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) sacc += p.blk_Qc[(size_t)blk * D * D + i * D + k] * xb[u][k];
-                    qq += xb[u][i] * sacc;
-                }
-                c += gx + 0.5 * qq;
-            }
-            double xHx = 0.0, Fx = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) sacc += rec[R::OFF_H + hidx(D, i, k)] * x[u][k];
-                xHx += x[u][i] * sacc;
-                Fx += F[i] * x[u][i];
-            }
-            llp[u] = -c - 0.5 * xHx + Fx;
-            lla[u] = llp[u];
-        }
-    }
-    double lsum[U] = {0.0, 0.0}, lsum_a[U] = {0.0, 0.0};
-    PhiloxKeys pkeys;
-    pkeys.set(p.seed);
-
-    // ---- input pipelines (one per unit): LDGSTS, depth-1 tiles ahead of the solve, across intervals ----
-    constexpr int RPI = 32 / IS::NPT;
-    const double *src[U][IS::NPT];
-    int ij = i1, itl = 0, int_ = 0, ilim = 0, iq = 0;
-    const size_t iadv = (size_t)TS * D;
-    const int pcl = lane % IS::NPT, rl = lane / IS::NPT;
-    auto setup_issue = [&](int j) {
-        const bool cur = j == jc, nxt = j == jc + 1;
-        const IvMeta mi = cur ? mc : (nxt ? mn : load_meta(p, j, chain[0], D));
-        int_ = (mi.N + TS - 1) / TS;
-        ilim = mi.N * D;
-        const size_t xo = (size_t)mi.xoff;
-        const int xs = mi.xs;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int sel = cur ? sxc[u] : (nxt ? sxn[u] : (int)p.selX_in[(size_t)j * p.C + chain[u]]);
-            const unsigned selmask = __ballot_sync(0xffffffffu, sel);
-            const int c0u = chain_raw[u] - lane;  // first chain of this unit's 32
-#pragma unroll
-            for (int q = 0; q < IS::NPT; ++q) {
-                const int r = q * RPI + rl;
-                const int cr = min(c0u + r, p.C - 1);
-                src[u][q] = p.X[(selmask >> r) & 1] + xo + (size_t)cr * xs + pcl * 2;
-            }
-        }
-    };
-    const uint32_t dst0 = (uint32_t)(rl * IS::RECW * 8 + ((pcl ^ rl) << 4));
-    auto issue_in = [&]() {
-        if (ij <= i2) {
-            const bool lv = itl * TS * D + pcl * 2 < ilim;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t da = smem_u32(sinp0 + ((size_t)u * depth + (iq & dmask)) * IS::WARP) + dst0;
-#pragma unroll
-                for (int q = 0; q < IS::NPT; ++q) {
-                    const uint32_t dst = (da ^ (uint32_t)(((q * RPI) & 7) << 4)) + (uint32_t)(q * RPI * IS::RECW * 8);
-                    if (lv) cp_async16(dst, src[u][q]);
-                    src[u][q] += iadv;
-                }
-            }
-            if (__builtin_expect(++itl == int_, 0)) {
-                itl = 0;
-                if (++ij <= i2) setup_issue(ij);
-            }
-        }
-        ++iq;
-        cp_async_commit();
-    };
-    setup_issue(i1);
-    for (int i = 0; i < depth - 1; ++i) issue_in();
-
-    int q = 0;
-    uint32_t sxbits[U] = {0u, 0u};
-    double *xp_end[U] = {nullptr, nullptr};
-    for (int j = i1; j <= i2; ++j) {
-        if (j > i1) {
-            mc = mn;
-            sxc[0] = sxn[0]; sxc[1] = sxn[1];
-            jc = j;
-            if (j < i2) {
-                mn = load_meta(p, j + 1, chain[0], D);
-                sxn[0] = mn.sx;
-                sxn[1] = p.selX_in[(size_t)(j + 1) * p.C + chain[1]];
-            }
-        }
-        const int N = mc.N;
-        const int nt = (N + TS - 1) / TS;
-        fk.aB0 = mc.aB0;
-        fk.c2 = mc.ab0 - fk.s * fk.ie;
-        const double rho = mc.rho;
-        const double lam = sqrt(1.0 - rho * rho);
-        double *Xp[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (j - i1 < 32) sxbits[u] |= (uint32_t)sxc[u] << (j - i1);
-            Xp[u] = p.X[1 - sxc[u]] + mc.xoff + (size_t)chain[u] * mc.xs;
-            xp_end[u] = Xp[u] + (size_t)(N - 1) * D;
-        }
-
-        for (int tl = 0; tl < nt; ++tl, ++q) {
-            __syncthreads();
-            if (threadIdx.x == 0) issue_table();
-            mbar_wait(&full[q & dmask], (uint32_t)((q >> dlog) & 1));
-            const double *srec = stab + (size_t)(q & dmask) * TS * RS;
-            cp_async_wait_depth(depth);
-            __syncwarp();
-            issue_in();
-            uint32_t hst[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) hst[u] = IS::cursor(sinp0 + ((size_t)u * depth + (q & dmask)) * IS::WARP, lane);
-
-            auto eight = [&](auto check_tag, int half) {
-                constexpr bool CHECK = decltype(check_tag)::value;
-                const int kh = tl * TS + half * TILE;
-                const double *hrec = srec + (size_t)half * TILE * RS;
-                float z[U][TILE];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int h = 0; h < TILE / 4; ++h)
-                        philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain[u], 0u,
-                                        (uint32_t)((kh >> 2) + h), &z[u][4 * h]);
-                double xprev[U][D];
-#pragma unroll
-                for (int u = 0; u < U; ++u) { xprev[u][0] = 0.0; xprev[u][1] = 0.0; }
-#pragma unroll
-                for (int s = 0; s < TILE; ++s) {
-                    const int ks = half * TILE + s;
-                    const bool live = !CHECK || (kh + s < N);  // CTA-uniform
-                    if (live) {
-                        double rec[RS];
-                        load_rec_smem<RS>(hrec + s * RS, rec);  // once for both units
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            double Cf = rec[FD_C1], R0c = rec[FD_R0];
-                            if constexpr (PSI) {
-                                Cf = fma(rec[FD_Q10], xb[u][0], fma(rec[FD_Q11], xb[u][1], Cf));
-                                R0c = fma(rec[FD_T00], xb[u][0], fma(rec[FD_T01], xb[u][1], R0c));
-                            }
-                            // recover the accepted noise increment from the accepted path
-                            double xn[2], g;
-                            IS::state(hst[u], ks, xn);
-                            fhn_dll(fk, rec, R0c, xa[u][0], xa[u][1], g, lsum_a[u]);
-                            const double pred = fma(rec[FD_A1], xa[u][1], fma(rec[FD_B1], xa[u][0], Cf));
-                            double dw = (xn[1] - pred) * fk.isig;
-                            xa[u][0] = xn[0]; xa[u][1] = xn[1];
-                            dw = fma(lam * rec[FD_SQ], (double)z[u][s], rho * dw);  // pCN
-                            fhn_step(fk, rec, R0c, fma(fk.sig, dw, Cf), x[u][0], x[u][1], lsum[u]);
-                        }
-                    }
-                    if (s & 1) {
-                        if (live) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u)
-                                if (active[u]) st_v4(Xp[u] + (size_t)(kh + s - 1) * D, xprev[u][0], xprev[u][1], x[u][0], x[u][1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            if (CHECK && live && kh + s == N - 1 && active[u]) {  // odd N: the last state goes out alone
-                                Xp[u][(size_t)(kh + s) * D] = x[u][0];
-                                Xp[u][(size_t)(kh + s) * D + 1] = x[u][1];
-                            }
-                            xprev[u][0] = x[u][0]; xprev[u][1] = x[u][1];
-                        }
-                    }
-                }
-            };
-#pragma unroll 1
-            for (int half = 0; half < TS / TILE; ++half) {
-                const int kh = tl * TS + half * TILE;
-                if (kh + TILE <= N) eight(std::false_type{}, half);
-                else if (kh < N) eight(std::true_type{}, half);
-            }
-        }
-    }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    cp_async_wait<0>();
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        llp[u] += lsum[u];
-        lla[u] += lsum_a[u];
-        if (pinned && active[u]) {  // pin the proposal's last point to x_b (glued paths stay continuous)
-            xp_end[u][0] = xb[u][0];
-            xp_end[u][1] = xb[u][1];
-        }
-        double llcur = lla[u];
-        const double e = philox_exponential(p.seed, p.iter, (uint32_t)(i1 + p.interval_offset), gchain[u]);
-        // accepted = rand(Exponential(1)) > -(ll deg - ll)   (eMCMC.accept_reject!)
-        const bool acc = active[u] && (p.force_accept ? true : (e > -(llp[u] - llcur)));
-        if (in_range[u]) {
-            for (int j = i1; j <= i2; ++j) {  // swap_paths!: flip the accepted-container selectors
-                const size_t o = (size_t)j * p.C + chain[u];
-                const int b = j - i1;
-                const uint8_t sxj = b < 32 ? (uint8_t)((sxbits[u] >> b) & 1u) : p.selX_in[o];
-                p.selX_out[o] = sxj ^ (uint8_t)acc;
-                p.selW_out[o] = p.selW_in[o];  // W is not stored in this mode
-            }
-        }
-        const unsigned accm = __ballot_sync(0xffffffffu, acc), actm = __ballot_sync(0xffffffffu, active[u]);
-        if (lane == 0) {
-            if (p.acc_count && accm) atomicAdd(p.acc_count + blk, (unsigned long long)__popc(accm));
-            if (p.prop_count && actm) atomicAdd(p.prop_count + blk, (unsigned long long)__popc(actm));
-        }
-        if (active[u]) {
-            if (acc) llcur = llp[u];
-            p.ll[uo[u]] = llcur;
-            if (p.out_llprop) p.out_llprop[(size_t)chain[u] * p.out_stride + blk] = llp[u];
-            if (p.out_ll) p.out_ll[(size_t)chain[u] * p.out_stride + blk] = llcur;
-            if (p.out_acc) p.out_acc[(size_t)chain[u] * p.out_stride + blk] = (uint8_t)acc;
-        } else if (in_range[u] && p.blk_active && !p.blk_active[blk]) {  // block owned by a neighbouring shard
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            if (p.out_llprop) p.out_llprop[(size_t)chain[u] * p.out_stride + blk] = nan;
-            if (p.out_ll) p.out_ll[(size_t)chain[u] * p.out_stride + blk] = nan;
-            if (p.out_acc) p.out_acc[(size_t)chain[u] * p.out_stride + blk] = 0;
-        }
-    }
-}
-
-template <bool PSI>
-static cudaError_t launch_fhn2(const SolveParams &p0, int threads, cudaStream_t s) {
-    using IS = InStage<2, 1, true>;
-    constexpr int U = 2;
-    SolveParams p = p0;
-    if (threads <= 0) threads = 64;
-    const unsigned groups = (unsigned)((p.C + threads * U - 1) / (threads * U));
-    const unsigned grid = groups * (unsigned)p.nblk;
-    p.depth = 2;
-    const size_t smem = sizeof(double) * (size_t)p.depth * ((size_t)TS * Rec<2, PSI>::SIZE + (size_t)(threads / 32) * U * IS::WARP);
-    auto kern = solve_fhn2_kernel<PSI>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
-}
-
 // ---- FitzHugh-Nagumo: rewrite a (layout, law) table into the fused step's coefficients -----------
 template <bool PSI>
 __global__ void fhn_derive_kernel(const double *__restrict__ raw, double *__restrict__ out, long long nrec, Theta th) {
@@ -951,13 +585,6 @@ cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads,
     if (model != 3) {
         const long long units = (long long)p.C * p.nblk;
         if (p.coop > 0 || (p.coop < 0 && units <= COOP_MAX_UNITS)) return launch_solve_coop(model, mode, p, s);
-    }
-    if (model == 0 && p.fast_ok && mode == MODE_IMPUTE && p.Z == nullptr && p.reinvert && !p.force_accept) {
-        // two units per thread (solve_fhn2_kernel) when the sweep has enough units to fill the machine that way
-        const char *env = getenv("DMCMC_U2");  // test / A-B override: 0 never, 1 always (bit-identical results)
-        const long long units = (long long)p.C * p.nblk;
-        const bool two = env ? atoi(env) != 0 : units >= 148LL * 64 * 2;
-        if (two) return p.has_psi ? launch_fhn2<true>(p, threads, s) : launch_fhn2<false>(p, threads, s);
     }
     switch (model) {
     case 0: return p.fast_ok ? launch_psi<ModelFHN, true>(mode, p, threads, s)

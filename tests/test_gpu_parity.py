@@ -452,28 +452,3 @@ def test_warp_per_unit_kernel_is_bit_identical(pkg, monkeypatch, name, kw, half)
                                            "parameter-step X", "W after a layout switch")):
         assert np.array_equal(a, b), f"{what} differs between the two imputation kernels"
 
-
-@pytest.mark.parametrize("kw,half", [(dict(n_obs=9, C=200, dt=0.004), 1), (dict(n_obs=11, C=70, dt=0.01), 2),
-                                     (dict(n_obs=8, C=129, dt=1e-3), 1)])
-def test_two_units_per_thread_kernel_is_bit_identical(pkg, monkeypatch, kw, half):
-    """solve_fhn2_kernel (two (chain, block) units per thread: the kernel the C3 bench sweep runs on) against the
-    one-unit-per-thread kernel: same samples bit for bit -- ragged chain counts (not a multiple of the 128 chains a CTA
-    covers), partial tiles (N = 25, 10), 100-step intervals, both chequerboard patterns, histories and counters."""
-    from diffusionmcmc_jl_b200.engine import Engine
-    spec = _mk(pkg, "fhn", **kw)
-    monkeypatch.setenv("DMCMC_COOP", "0")
-    out = []
-    for u2 in ("0", "1"):
-        monkeypatch.setenv("DMCMC_U2", u2)
-        e = Engine(spec, seed=23)
-        e.init_paths()
-        n = 5
-        nb = max(len(pkg.problems.chequerboard_layout(e.rec_nobs, half, p)[0]) for p in (0, 1))
-        hist = (np.zeros((n, e.C, nb)), np.zeros((n, e.C, nb)), np.zeros((n, e.C, nb), np.uint8))
-        e.run_sweeps(0, n, half, 0, None, hist)
-        X = e.download_segment(0, e.J)
-        out.append((X, e.get_ll().copy(), hist[0].copy(), hist[1].copy(), hist[2].copy(), e.accept_counts()[0].copy()))
-        e.close()
-    for a, b, what in zip(out[0], out[1], ("X", "ll", "ll deg history", "ll history", "accept history", "accept counts")):
-        assert np.array_equal(a, b), f"{what} differs between one and two units per thread"
-    assert out[0][4].any()
