@@ -5,7 +5,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libdmcmc_b200.so")
-SOURCES = ["dmcmc_capi.cu", "dmcmc_solve.cu", "dmcmc_solve_coop.cu", "dmcmc_solve_big.cu", "dmcmc_bf.cu", "dmcmc_conjugate.cu"]
+SOURCES = ["dmcmc_capi.cu", "dmcmc_solve.cu", "dmcmc_solve_coop.cu", "dmcmc_solve_l96.cu", "dmcmc_bf.cu", "dmcmc_conjugate.cu"]
 HEADERS = ["dmcmc_device.cuh", "dmcmc_solve_common.cuh", "dmcmc_internal.h", "dmcmc_models.cuh",
            os.path.join("..", "..", "include", "dmcmc.h")]
 # The backward filter is compiled WITHOUT floating-point contraction: its tables feed log h~ = -c - x'Hx/2 + F'x, a sum of

@@ -542,10 +542,10 @@ __global__ void __launch_bounds__(256) bf_big_kernel(const BFParams b) {
         if (step >= 0) {
             double *r = b.table + (size_t)step * b.rec;
             if (tid == 0) { r[0] = dt; r[1] = sqrt(dt); }
-            for (int e = tid; e < DD; e += nt) r[2 + e] = H[e];
+            for (int e = tid; e < DD; e += nt) r[2 + big_frag(e / D, e % D)] = H[e];  // fragment order (dmcmc_device.cuh)
             for (int e = tid; e < D; e += nt) r[2 + DD + e] = F0[e];
             if (b.has_psi)
-                for (int e = tid; e < DD; e += nt) r[2 + DD + D + e] = Psi[(e % D) * D + (e / D)];  // transposed
+                for (int e = tid; e < DD; e += nt) r[2 + DD + D + big_frag(e / D, e % D)] = Psi[(e % D) * D + (e / D)];  // transposed
         }
         __syncthreads();
     };

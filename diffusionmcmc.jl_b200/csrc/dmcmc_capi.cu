@@ -1039,12 +1039,14 @@ int dmcmc_upload_tables(dmcmc_ctx *ctx, int32_t which, const double *H, const do
             r[0] = dt;
             r[1] = std::sqrt(dt);
             int o = 2;
-            if (d > 3) {  // large-D record: full H, F0, Psi transposed
-                for (int i = 0; i < d * d; ++i) r[o++] = H[pt * d * d + i];
+            if (d > 3) {  // large-D record: full H, F0, Psi transposed; matrices in mma fragment order (dmcmc_device.cuh)
+                for (int k = 0; k < d; ++k)
+                    for (int i = 0; i < d; ++i) r[o + big_frag(k, i)] = H[pt * d * d + (size_t)k * d + i];
+                o += d * d;
                 for (int i = 0; i < d; ++i) r[o++] = F0[pt * d + i];
                 if (lay.has_psi)
                     for (int k = 0; k < d; ++k)
-                        for (int i = 0; i < d; ++i) r[o++] = Psi[pt * d * d + (size_t)i * d + k];
+                        for (int i = 0; i < d; ++i) r[o + big_frag(k, i)] = Psi[pt * d * d + (size_t)i * d + k];
             } else {
                 for (int i = 0; i < d; ++i)
                     for (int q = i; q < d; ++q) r[o++] = H[pt * d * d + i * d + q];

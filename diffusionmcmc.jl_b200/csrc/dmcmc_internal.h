@@ -70,7 +70,7 @@ struct SolveParams {
 
 // launchers (dmcmc_solve.cu); return the CUDA error of the launch
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s);
-cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_big.cu
+cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_l96.cu
 cudaError_t launch_solve_coop(int model, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_coop.cu (MODE_IMPUTE, MODE_PARAM)
 cudaError_t launch_fhn_derive(const double *raw, double *out, long long nrec, int has_psi, const Theta &th, cudaStream_t s);
 

@@ -1,5 +1,5 @@
-"""Lorenz-96 (d = 40, BASELINE config 5 at reduced size): the warp-per-unit solve kernel and the
-CTA-cooperative backward filter against the CPU oracle."""
+"""Lorenz-96 (d = 40, BASELINE config 5 at reduced size): the FP64 tensor-core solve kernel (eight chains per warp,
+dmcmc_solve_l96.cu) and the CTA-cooperative backward filter against the CPU oracle."""
 import numpy as np
 import pytest
 
@@ -8,11 +8,15 @@ from helpers import accept_mismatch_is_tie, check, check_scaled, close, interior
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["4_chains_per_warp", "8_chains_per_warp"])
+@pytest.fixture(autouse=True, params=["auto_cta", "8_warps_per_cta"])
 def l96_mapping(request, monkeypatch):
-    """Every Lorenz-96 test runs under both warp mappings of solve_big_kernel (one or two chains per eight-lane group;
-    the launcher chooses by unit count, these problems are small enough that it would always take the first)."""
-    monkeypatch.setenv("DMCMC_BIG_NC", "1" if request.param == "4_chains_per_warp" else "2")
+    """Every Lorenz-96 test runs with the launcher's own CTA size (one or two warps for these chain counts) and with
+    eight warps per CTA (BASELINE C5's shape: the warps of a CTA share the table stages, the last one to finish with a
+    stage refills it; surplus warps shadow the last chain)."""
+    if request.param == "8_warps_per_cta":
+        monkeypatch.setenv("DMCMC_L96_WARPS", "8")
+    else:
+        monkeypatch.delenv("DMCMC_L96_WARPS", raising=False)
     return request.param
 
 
@@ -91,14 +95,14 @@ def test_l96_fused_blocked_and_philox(pkg, orc):
         check(f"l96 fused blocked it {it} X", Xg[:, im], o.accepted_X()[:, im])
 
 
-def test_l96_warp_mappings_are_bit_identical(pkg, monkeypatch):
-    """One or two chains per lane group must never change a sample (the per-chain arithmetic is the same, operation for
+def test_l96_cta_sizes_are_bit_identical(pkg, monkeypatch):
+    """The number of warps per CTA must never change a sample (the per-chain arithmetic is the same, operation for
     operation): stored-noise sweeps, fused blocked sweeps, parameter-step solve, layout switch -- ragged chain count."""
     from diffusionmcmc_jl_b200.engine import Engine
     spec = pkg.problems.l96_spec(n_obs=6, C=11, dt=1e-3, rho=0.8)
     out = []
-    for nc in ("1", "2"):
-        monkeypatch.setenv("DMCMC_BIG_NC", nc)
+    for nw in ("1", "2", "8"):
+        monkeypatch.setenv("DMCMC_L96_WARPS", nw)
         e = Engine(spec, seed=77)
         e.init_paths()
         e.run_sweeps(0, 2, 0)
@@ -110,5 +114,6 @@ def test_l96_warp_mappings_are_bit_identical(pkg, monkeypatch):
         _, Wr = e.download_state(0)
         out.append((X, W, e.get_ll().copy(), llp, ok, Wr, e.accept_counts()[0].copy()))
         e.close()
-    for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "parameter-step ll", "success", "W after a layout switch", "accept counts")):
-        assert np.array_equal(a, b), f"{what} differs between the two warp mappings"
+    for other in out[1:]:
+        for a, b, what in zip(out[0], other, ("X", "W", "ll", "parameter-step ll", "success", "W after a layout switch", "accept counts")):
+            assert np.array_equal(a, b), f"{what} differs between CTA sizes"
