@@ -15,7 +15,7 @@
 // (kp, nt) tile with one conflict-free 16-byte shared-memory load.
 //
 // The CTA's warps (all on the same block) share the step's table record (H, F0, Psi': 26 KB), brought in by TMA bulk
-// copies into a ring of stages; no CTA barrier: the LAST warp to finish with a stage refills it.  The accepted path
+// copies into a ring of stages guarded by full / empty mbarriers; no CTA barrier in the loop.  The accepted path
 // arrives by cp.async two states ahead in a warp-private ring (neighbour components of the Lorenz-96 drift are read
 // from there), the proposal's neighbours go through a warp-private double buffer.  Path I/O is per step, 16 bytes per
 // lane, 320 contiguous bytes per chain.
@@ -43,6 +43,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(b)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm_u32(b)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     asm volatile(
         "{\n .reg .pred p;\n WAITL_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
@@ -65,6 +68,15 @@ constexpr int AST = 3;        // accepted-state stages (A_t neighbours, A_{t+1},
 constexpr int ROW = 8 * D;    // doubles per (stage, warp): eight chains' states
 constexpr int WARP_DOUBLES = AST * ROW + 2 * ROW + (4 * 10 * 32) / 2;  // + proposal double buffer + four steps of normals (float)
 
+// auxiliary drift of a custom law (dmcmc_set_aux), row c: kept out of line so that the unrolled step body of the built-in
+// law stays inside the instruction cache (the loop body was 80 KB with this inlined 20 times)
+__device__ __noinline__ double aux_drift_general(const double *aB, const double *abeta, int c, const double *xrow) {
+    double a = 0.0;
+#pragma unroll 1
+    for (int kk = 0; kk < 40; ++kk) a += aB[(size_t)c * 40 + kk] * xrow[kk];
+    return a + abeta[c];
+}
+
 struct Cursor {  // (interval, step) walking a layout block
     int j, k, N;
 };
@@ -75,7 +87,9 @@ size_t l96_smem_bytes(bool psi, int warps) {
     return (size_t)(NST * rec_size_big(D, psi) + warps * WARP_DOUBLES) * sizeof(double);
 }
 
-template <bool PSI, int MODE, bool PHILOX, bool REINV>
+// FAST: the law uses the model's built-in auxiliary law (a compile-time switch: a run-time branch per component cut the
+// unrolled element-wise part into small basic blocks and dragged generic-address arithmetic for the call into the loop)
+template <bool PSI, int MODE, bool PHILOX, bool REINV, bool FAST>
 __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) {
     constexpr int REC = rec_size_big(D, PSI);
     constexpr int OFF_H = 2, OFF_F = 2 + D * D, OFF_PSI = 2 + D * D + D;
@@ -85,8 +99,7 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
     constexpr bool STORE_W_MODE = ((MODE == MODE_IMPUTE && !REINV) || MODE == MODE_RELAYOUT);
     constexpr bool ZSM = (MODE == MODE_IMPUTE) && PHILOX;
     extern __shared__ __align__(128) double dsm[];
-    __shared__ __align__(8) uint64_t full[NST];
-    __shared__ int done[NST];
+    __shared__ __align__(8) uint64_t full[NST], empty[NST];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int c8 = lane >> 2, q = lane & 3;  // chain within the warp, position in the chain's quad
     double *wbase = dsm + NST * REC + (size_t)warp * WARP_DOUBLES;
@@ -108,19 +121,18 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
 
     const double Fth = p.th.v[0], sig = p.th.v[1], caux = p.th.v[2];
     const double sig2 = sig * sig, isig = 1.0 / sig;
-    const bool fast_aux = p.fast_ok != 0;
     const bool pinned = PSI && p.blk_pinned[blk];
     PhiloxKeys pkeys;
     pkeys.set(p.seed);
 
     // neighbour offsets of the Lorenz-96 drift inside a chain row: pair (i-2, i-1) left of the own pair (i, i+1), and
     // i+2 right of it; only tile 0 of quad lane 0 and tile 4 of quad lane 3 wrap around
-    const int offL0 = q ? 2 * q - 2 : D - 2;
-    const int offR4 = (q == 3) ? 0 : 32 + 2 * q + 2;
+    const int relL0 = q ? -2 : D - 2;       // relative to the own pair of tile 0 (component 2 q)
+    const int relR4 = (q == 3) ? -6 : 34;   // relative to component 2 q: component 34 + 2 q, or 0 for quad lane 3
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)nwarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -128,7 +140,6 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
         if (++c.k == c.N) { ++c.j; c.k = 0; c.N = (c.j <= i2) ? p.iv_N[c.j] : 0; }
     };
     auto issue_table = [&](const Cursor &c, int s) {  // one thread: stage the record of one Euler step
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&full[s], (uint32_t)(REC * sizeof(double)));
         bulk_g2s(dsm + s * REC, p.table + ((size_t)p.iv_tile_off[c.j] * TILE + c.k) * REC, (uint32_t)(REC * sizeof(double)), &full[s]);
     };
@@ -174,6 +185,7 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
             for (int e = 0; e < 2; ++e) {
                 const int c = 8 * nt + 2 * q + e;
                 double qx = 0.0;
+#pragma unroll 1
                 for (int kk = 0; kk < D; ++kk) qx += p.blk_Qc[(size_t)blk * D * D + (size_t)kk * D + c] * xbuf[ROW + kk];
                 pin_part += p.blk_g[(size_t)blk * D + c] * xb[nt][e] + 0.5 * xb[nt][e] * qx;
             }
@@ -219,8 +231,8 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
             // ---- noise of the next four steps: one Philox call per owned component -> shared memory ----
             if constexpr (ZSM) {
                 if ((k & 3) == 0) {
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll 1
+                    for (int nt = 0; nt < NT; ++nt)  // rolled: code size (instruction cache), not speed, is what matters here
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             float z4[4];
@@ -256,28 +268,23 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                 for (int kp = 0; kp < NT; ++kp)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
+                        // the two k-steps of a tile go to the same accumulator: keep them apart (DMMA latency 26 cycles,
+                        // issue interval 16)
                         const double2 h = hf[(kp * NT + nt) * 32];
-                        if constexpr (SOLVE) { dmma(Hx[nt], x[kp][0], h.x); dmma(Hx[nt], x[kp][1], h.y); }
-                        if constexpr (NEED_XA) { dmma(Hxa[nt], xa[kp][0], h.x); dmma(Hxa[nt], xa[kp][1], h.y); }
-                        if constexpr (PSI) {
-                            const double2 pp = pf[(kp * NT + nt) * 32];
-                            dmma(Fv[nt], xb[kp][0], pp.x); dmma(Fv[nt], xb[kp][1], pp.y);
-                        }
+                        double2 pp;
+                        if constexpr (PSI) pp = pf[(kp * NT + nt) * 32];
+                        if constexpr (SOLVE) dmma(Hx[nt], x[kp][0], h.x);
+                        if constexpr (NEED_XA) dmma(Hxa[nt], xa[kp][0], h.x);
+                        if constexpr (PSI) dmma(Fv[nt], xb[kp][0], pp.x);
+                        if constexpr (SOLVE) dmma(Hx[nt], x[kp][1], h.y);
+                        if constexpr (NEED_XA) dmma(Hxa[nt], xa[kp][1], h.y);
+                        if constexpr (PSI) dmma(Fv[nt], xb[kp][1], pp.y);
                     }
             }
             const double dt = rec[0], sq = rec[1];
-            // ---- done with the table stage: the last warp to get here refills it with the record NST steps ahead ----
+            // ---- done with the table stage (warp 0 refills it at the end of the step, when every warp has said so) ----
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                const int old = atomicAdd(&done[ts], 1);
-                if (old == nwarps - 1) {
-                    atomicExch(&done[ts], 0);
-                    __threadfence_block();
-                    if (tc.j <= i2) issue_table(tc, ts);
-                }
-            }
-            if (tc.j <= i2) advance(tc);
+            if (lane == 0) mbar_arrive(&empty[ts]);
             if (t == 0) {
                 // log h~(t_a, x_a) = -c - 1/2 x'Hx + F'x at the block's first grid point (x = x_acc there)
                 double part = 0.0;
@@ -295,18 +302,19 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
 
             // ---- element-wise part, one tile of eight components at a time (short live ranges).  Neighbours of the
             //      Lorenz-96 drift: accepted state A_t from its ring stage, proposal from the double buffer ----
-            const double *arow = ast + a0 * ROW, *nrow = ast + a1 * ROW;
+            const double *arow = ast + a0 * ROW, *nrow = ast + a1 * ROW + 2 * q;   // chain row; own pair of tile 0
             const double *xrow = xbuf + (t & 1) * ROW;
-            double *xout = xbuf + ((t + 1) & 1) * ROW;
+            double *xout = xbuf + ((t + 1) & 1) * ROW + 2 * q;
+            const double *aq = arow + 2 * q, *xq = xrow + 2 * q;
+            const double *aL0 = aq + relL0, *aR4 = aq + relR4, *xL0 = xq + relL0, *xR4 = xq + relR4;
             const bool pin_here = pinned && j == i2 && k == N - 1;  // the block's right end stays x_b
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const int oL = (nt == 0) ? offL0 : 8 * nt + 2 * q - 2, oR = (nt == NT - 1) ? offR4 : 8 * nt + 2 * q + 2;
                 double dwv[2] = {0.0, 0.0}, xnew[2] = {0.0, 0.0};
                 if constexpr (NEED_XA) {  // recover the accepted noise increments
-                    const double2 l = *reinterpret_cast<const double2 *>(arow + oL);
-                    const double rgt = reinterpret_cast<const double2 *>(arow + oR)->x;  // 16-byte access: no bank conflict
-                    const double2 nx = *reinterpret_cast<const double2 *>(nrow + 8 * nt + 2 * q);
+                    const double2 l = *reinterpret_cast<const double2 *>(nt == 0 ? aL0 : aq + 8 * nt - 2);
+                    const double rgt = reinterpret_cast<const double2 *>(nt == NT - 1 ? aR4 : aq + 8 * nt + 2)->x;  // 16-byte access: no bank conflict
+                    const double2 nx = *reinterpret_cast<const double2 *>(nrow + 8 * nt);
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int c = 8 * nt + 2 * q + e;
@@ -318,12 +326,8 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                         const double xim2 = e == 0 ? l.x : l.y;
                         const double b = (xip - xim2) * xim1 - xi + Fth;
                         double bt;
-                        if (fast_aux) bt = ((-xi) + caux * xip + (-caux) * xim2) + Fth;  // B = -I + c (S_{+1} - S_{-2}), beta = F
-                        else {
-                            double a = 0.0;
-                            for (int kk = 0; kk < D; ++kk) a += aB[(size_t)c * D + kk] * arow[kk];
-                            bt = a + abeta[c];
-                        }
+                        if constexpr (FAST) bt = ((-xi) + caux * xip + (-caux) * xim2) + Fth;  // B = -I + c (S_{+1} - S_{-2}), beta = F
+                        else bt = aux_drift_general(aB, abeta, c, arow);
                         lsum_a += ((b - bt) * r) * dt;
                         const double res = (e == 0 ? nx.x : nx.y) - xi - (b + sig2 * r) * dt;
                         dwv[e] = res * isig;
@@ -343,8 +347,8 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                     }
                 }
                 if constexpr (SOLVE) {
-                    const double2 l = *reinterpret_cast<const double2 *>(xrow + oL);
-                    const double rgt = reinterpret_cast<const double2 *>(xrow + oR)->x;
+                    const double2 l = *reinterpret_cast<const double2 *>(nt == 0 ? xL0 : xq + 8 * nt - 2);
+                    const double rgt = reinterpret_cast<const double2 *>(nt == NT - 1 ? xR4 : xq + 8 * nt + 2)->x;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int c = 8 * nt + 2 * q + e;
@@ -355,18 +359,14 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                         const double xim2 = e == 0 ? l.x : l.y;
                         const double b = (xip - xim2) * xim1 - xi + Fth;
                         double bt;
-                        if (fast_aux) bt = ((-xi) + caux * xip + (-caux) * xim2) + Fth;
-                        else {
-                            double a = 0.0;
-                            for (int kk = 0; kk < D; ++kk) a += aB[(size_t)c * D + kk] * xrow[kk];
-                            bt = a + abeta[c];
-                        }
+                        if constexpr (FAST) bt = ((-xi) + caux * xip + (-caux) * xim2) + Fth;
+                        else bt = aux_drift_general(aB, abeta, c, xrow);
                         lsum += ((b - bt) * r) * dt;
                         xnew[e] = xi + (b + sig2 * r) * dt + sig * dwv[e];
                     }
                     // new state: registers (next step's A operands), the other half of the proposal buffer, global
                     x[nt][0] = xnew[0]; x[nt][1] = xnew[1];
-                    *reinterpret_cast<double2 *>(xout + 8 * nt + 2 * q) = make_double2(xnew[0], xnew[1]);
+                    *reinterpret_cast<double2 *>(xout + 8 * nt) = make_double2(xnew[0], xnew[1]);
                     if (active) {
                         if (pin_here) st_v2(Xp + (size_t)k * D + 8 * nt, xb[nt][0], xb[nt][1]);
                         else st_v2(Xp + (size_t)k * D + 8 * nt, xnew[0], xnew[1]);
@@ -379,6 +379,16 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                             Wdst[w_off(wt0 + (size_t)(k >> 3), chain, 8 * nt + 2 * q + e, p.C, D) + (k & 7)] = dwv[e];
                     }
                 }
+            }
+            // ---- warp 0: the record NST steps ahead goes into the stage this step has used.  No fence and no atomics
+            //      (a membar here also waits for the step's global stores and prefetches);
+            //      by now the other warps are normally past their mat-vecs, so the wait does not spin ----
+            if (tc.j <= i2) {
+                if (threadIdx.x == 0) {
+                    mbar_wait(&empty[ts], (uint32_t)tpar);
+                    issue_table(tc, ts);
+                }
+                advance(tc);
             }
             ++t;
             if (++ts == NST) { ts = 0; tpar ^= 1; }
@@ -440,9 +450,11 @@ static cudaError_t launch_l96(int mode, const SolveParams &p, cudaStream_t s) {
     if ((long long)p.nblk * p.C == 0) return cudaSuccess;
     // warps per CTA (eight chains each, all on one block: the per-step table record is staged once per CTA): the largest
     // CTA whose grid still covers every SM; DMCMC_L96_WARPS pins it
+    // (one CTA per SM: 255 registers, 52 KB of table stages + 18 KB per warp).  Smaller CTAs only while all of them are
+    // resident at once (measured, 33 blocks x 256 chains: 132 CTAs of 8 warps 20.6 ms, 264 CTAs of 4 warps = two rounds 25 ms)
     int warps = 8;
-    while (warps > 1 && (long long)p.nblk * ((p.C + warps * 8 - 1) / (warps * 8)) < 148) warps >>= 1;
     while (warps > 1 && (warps / 2) * 8 >= p.C) warps >>= 1;  // no CTA of nothing but surplus warps
+    while (warps > 1 && (long long)p.nblk * ((p.C + warps * 4 - 1) / (warps * 4)) <= 148) warps >>= 1;
     if (const char *env = getenv("DMCMC_L96_WARPS")) {
         const int w = atoi(env);
         if (w >= 1 && w <= 8) warps = w;
@@ -454,10 +466,10 @@ static cudaError_t launch_l96(int mode, const SolveParams &p, cudaStream_t s) {
     const bool philox = (p.Z == nullptr), reinv = p.reinvert != 0;
 #define DMCMC_LAUNCH(MODE_, PH_, RE_)                                                                         \
     do {                                                                                                       \
-        cudaError_t e_ = cudaFuncSetAttribute(solve_l96_kernel<PSI, MODE_, PH_, RE_>,                          \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);        \
+        auto kern_ = p.fast_ok ? solve_l96_kernel<PSI, MODE_, PH_, RE_, true> : solve_l96_kernel<PSI, MODE_, PH_, RE_, false>; \
+        cudaError_t e_ = cudaFuncSetAttribute(kern_, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
         if (e_ != cudaSuccess) return e_;                                                                      \
-        solve_l96_kernel<PSI, MODE_, PH_, RE_><<<grid, threads, smem, s>>>(p);                                \
+        kern_<<<grid, threads, smem, s>>>(p);                                                                  \
     } while (0)
     switch (mode) {
     case MODE_IMPUTE:
