@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
     for (int j = i1; j <= i2; ++j) {
         const int N = p.iv_N[j];
         const double rho = (MODE == MODE_IMPUTE) ? p.rho[j] : 1.0;
-        const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0;
+        const double lam = (MODE == MODE_IMPUTE) ? sqrt(1.0 - rho * rho) : 0.0, rho_isig = rho * isig;
         const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
         const double *Wa = p.W[sw];
         double *Wdst = (MODE == MODE_RELAYOUT) ? p.W[sw] : p.W[1 - sw];
@@ -232,9 +232,9 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
             if constexpr (ZSM) {
                 if ((k & 3) == 0) {
 #pragma unroll 1
-                    for (int nt = 0; nt < NT; ++nt)  // rolled: code size (instruction cache), not speed, is what matters here
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
+                    for (int e = 0; e < 2; ++e)  // half rolled: five independent Philox / Box-Muller chains in flight, and
+#pragma unroll                                   // the step body still fits the instruction cache
+                        for (int nt = 0; nt < NT; ++nt) {
                             float z4[4];
                             philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)(8 * nt + 2 * q + e), (uint32_t)(k >> 2), z4);
 #pragma unroll
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                         if constexpr (PSI) dmma(Fv[nt], xb[kp][1], pp.y);
                     }
             }
-            const double dt = rec[0], sq = rec[1];
+            const double dt = rec[0], lamsq = lam * rec[1];
             // ---- done with the table stage (warp 0 refills it at the end of the step, when every warp has said so) ----
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[ts]);
@@ -324,13 +324,13 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                         const double xip = e == 0 ? xa[nt][1] : rgt;
                         const double xim1 = e == 0 ? l.y : xa[nt][0];
                         const double xim2 = e == 0 ? l.x : l.y;
-                        const double b = (xip - xim2) * xim1 - xi + Fth;
-                        double bt;
-                        if constexpr (FAST) bt = ((-xi) + caux * xip + (-caux) * xim2) + Fth;  // B = -I + c (S_{+1} - S_{-2}), beta = F
-                        else bt = aux_drift_general(aB, abeta, c, arow);
-                        lsum_a += ((b - bt) * r) * dt;
+                        const double dd = xip - xim2;
+                        const double b = dd * xim1 - xi + Fth;
+                        // built-in aux law B = -I + c (S_{+1} - S_{-2}), beta = F:  b - b~ = (x_{i+1} - x_{i-2}) (x_{i-1} - c)
+                        const double bmbt = FAST ? dd * (xim1 - caux) : b - aux_drift_general(aB, abeta, c, arow);
+                        lsum_a += (bmbt * r) * dt;
                         const double res = (e == 0 ? nx.x : nx.y) - xi - (b + sig2 * r) * dt;
-                        dwv[e] = res * isig;
+                        dwv[e] = (MODE == MODE_IMPUTE) ? res : res * isig;  // imputation: 1 / sigma is folded into the pCN mix
                     }
                     xa[nt][0] = nx.x; xa[nt][1] = nx.y;
                 } else if constexpr (NEED_WA) {
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                         double z;
                         if constexpr (ZSM) z = (double)zsm[((k & 3) * 10 + nt * 2 + e) * 32];
                         else z = p.Z[w_off(wt0 + (size_t)(k >> 3), chain, 8 * nt + 2 * q + e, p.C, D) + (k & 7)];
-                        dwv[e] = lam * (sq * z) + rho * dwv[e];
+                        dwv[e] = lamsq * z + (NEED_XA ? rho_isig : rho) * dwv[e];  // dW deg = lambda sqrt(dt) Z + rho dW
                     }
                 }
                 if constexpr (SOLVE) {
@@ -357,11 +357,10 @@ __global__ void __launch_bounds__(256, 1) solve_l96_kernel(const SolveParams p) 
                         const double xip = e == 0 ? x[nt][1] : rgt;
                         const double xim1 = e == 0 ? l.y : x[nt][0];
                         const double xim2 = e == 0 ? l.x : l.y;
-                        const double b = (xip - xim2) * xim1 - xi + Fth;
-                        double bt;
-                        if constexpr (FAST) bt = ((-xi) + caux * xip + (-caux) * xim2) + Fth;
-                        else bt = aux_drift_general(aB, abeta, c, xrow);
-                        lsum += ((b - bt) * r) * dt;
+                        const double dd = xip - xim2;
+                        const double b = dd * xim1 - xi + Fth;
+                        const double bmbt = FAST ? dd * (xim1 - caux) : b - aux_drift_general(aB, abeta, c, xrow);
+                        lsum += (bmbt * r) * dt;
                         xnew[e] = xi + (b + sig2 * r) * dt + sig * dwv[e];
                     }
                     // new state: registers (next step's A operands), the other half of the proposal buffer, global
