@@ -426,8 +426,13 @@ def config_c5(pkg, K, W, local_rank, rank, world, n_obs=4096, chains=256):
     flops = 2 * 3 * 40 * 40 + 30 * 40
     tf = out["value"] * flops / 1e12
     peak = _lib.load().dmcmc_fp64_peak(local_rank)
+    tpeak = _lib.load().dmcmc_fp64_tensor_peak(local_rank)
     out["fp64"] = {"bound": "fp64", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak if peak > 0 else None,
-                   "flops_per_step": flops, "peak_source": "measured here: dependent-free DFMA streams on every SM (dmcmc_fp64_peak)"}
+                   "flops_per_step": flops, "peak_source": "measured here: dependent-free DFMA streams on every SM (dmcmc_fp64_peak)",
+                   "tensor_peak": tpeak, "frac_of_tensor_peak": tf / tpeak if tpeak > 0 else None,
+                   "tensor_peak_source": "measured here: independent mma.sync m8n8k4.f64 (DMMA) chains on every SM "
+                                         "(dmcmc_fp64_tensor_peak); the kernel's three 40 x 40 mat-vecs per step run as DMMA, "
+                                         "DMMA and DFMA share one FP64 datapath on B200"}
     if world > 1:
         out["n_gpus"], out["scaling"] = world, "strong: 256 chains / N per GPU; value = all ranks' path-steps / slowest rank's time"
     eng.close()

@@ -81,6 +81,7 @@ SYMBOLS = {
     "dmcmc_kernel_times": (C.c_int, [C.c_void_p, _dp, _lp]),
     "dmcmc_device_bytes": (C.c_int64, [C.c_void_p]),
     "dmcmc_fp64_peak": (C.c_double, [C.c_int32]),
+    "dmcmc_fp64_tensor_peak": (C.c_double, [C.c_int32]),
     "dmcmc_set_threads": (C.c_int, [C.c_void_p, C.c_int32]),
     "dmcmc_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "dmcmc_launch_count": (C.c_int64, [C.c_void_p]),

@@ -1856,6 +1856,55 @@ extern "C" double dmcmc_fp64_peak(int32_t device) {
     return best;
 }
 
+// FP64 tensor-core peak (mma.sync m8n8k4.f64 = SASS DMMA.8x8x4, the instruction the Lorenz-96 solve kernel's mat-vecs run
+// on): eight independent accumulator pairs per warp, 16 warps per SM.  On B200 DMMA and DFMA share the FP64 datapath
+// (36.8 against 34.2 TFLOP/s; a DFMA stream next to a DMMA stream is throttled), so this is the ceiling of that kernel.
+__global__ void __launch_bounds__(256) fp64_dmma_peak_kernel(double *out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k][0] = k; c[k][1] = 1e-9 * threadIdx.x; }
+    const double av = a + 1e-9 * threadIdx.x, bv = b + 1e-12 * threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(av), "d"(bv));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" double dmcmc_fp64_tensor_peak(int32_t device) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 2, threads = 256, iters = 4096;
+    double *out = nullptr;
+    if (cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_dmma_peak_kernel<<<blocks, threads>>>(out, iters, 1e-3, 1e-3);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 256 * 4 * 8 * (double)iters * blocks * (threads / 32);  // 8 x 8 x 4 FMAs per warp instruction
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
 // =================================================================================================
 // Block-sharded recording over the GPUs of one box: the collectives live in the library, so a host without
 // torch.distributed (the Julia plugin) gets the end-point exchange and the parameter-step all-reduce through ccall.

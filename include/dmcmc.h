@@ -270,6 +270,9 @@ int64_t dmcmc_device_bytes(const dmcmc_ctx *ctx);
 /* Measured FP64 FMA throughput of a device in TFLOP/s (independent DFMA chains on every SM, best of five): the
  * denominator of the FP64-pipe view of the Lorenz-96 kernel (bench.py). */
 double dmcmc_fp64_peak(int32_t device);
+/* The same through the FP64 tensor cores (mma.sync m8n8k4.f64, SASS DMMA.8x8x4), the instruction the Lorenz-96 kernel's
+ * 40 x 40 mat-vecs run on; on B200 both share one FP64 datapath, so this is that kernel's ceiling. */
+double dmcmc_fp64_tensor_peak(int32_t device);
 /* Threads per CTA of the solve kernels (32..128, multiple of 32; default: chosen per launch by unit count). */
 int dmcmc_set_threads(dmcmc_ctx *ctx, int32_t threads);
 /* Model-specific fused step kernels (FitzHugh-Nagumo with its built-in aux law); on by default.
