@@ -347,18 +347,26 @@ def config_c4(pkg, K, W, local_rank, rank, world):
     # torch.distributed only carries the 128-byte NCCL id to the other ranks
     uid = [Engine.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    halo = parallel.LibHalo(s, uid[0])
+    halo = parallel.LibHalo(s, uid[0], p2p=False)
     n = max(K, 100)
-    for it in range(max(W, 3)):
-        halo.iterate(it)
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(10, 10 + n):
-        halo.iterate(it)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+
+    def timed_iterations(first):
+        for it in range(first, first + max(W, 3)):
+            halo.iterate(it)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(first + 10, first + 10 + n):
+            halo.iterate(it)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+    # A/B in the same run: the exchange by ncclSend / ncclRecv first, then by peer-memory mailboxes (NVLink stores +
+    # sequence flags from the pack / unpack kernels, dmcmc_comm_enable_p2p); the line's value is the second when it is on
+    dt_nccl = timed_iterations(0)
+    p2p_on = os.environ.get("DMCMC_P2P", "1") != "0" and s.engine.comm_enable_p2p((s.h + 1) * s.N_max * s.engine.d * 8 * s.engine.C)
+    halo.p2p = p2p_on
+    dt = timed_iterations(1000) if p2p_on else dt_nccl
     # what the two parts cost on their own: the exchanges alone (same messages, nothing computed in between) and the
     # sweeps alone (no exchange; the halo goes stale, which does not change the work)
     e = s.engine
@@ -386,15 +394,17 @@ def config_c4(pkg, K, W, local_rank, rank, world):
     for i in range(20):
         halo.param_step(th * (1 + 1e-4 * (i + 2)), lambda llp, ll, ok: False)
     dtp = (time.perf_counter() - t1) / 20
-    tt = torch.tensor([dt, dtp, dt_x, dt_k], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([dt, dtp, dt_x, dt_k, dt_nccl], device="cuda", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt, dtp, dt_x, dt_k = (float(x) for x in tt)
+    dt, dtp, dt_x, dt_k, dt_nccl = (float(x) for x in tt)
     out = {"workload": "C4: Lorenz-63 1 chain x 10^4 obs, chequerboard half_len=5, interval blocks sharded over the GPUs, "
-                       "NCCL end-point / halo exchange after every sweep (inside the library)",
+                       "end-point / halo exchange after every sweep (inside the library)",
            "n_chains": 1, "n_obs": 10_000, "n_gpus": world, "scaling": "strong", "path_steps_per_sweep": steps,
            "value": 2 * steps * n / dt, "unit": UNIT, "ms_per_iteration": dt / n * 1e3,
            "parameter_step_ms": dtp * 1e3, "mcmc_iters_per_sec": 1.0 / (dt / n / 2 + dtp),
            "exchanges_alone_ms_per_iteration": dt_x * 1e3, "sweeps_alone_ms_per_iteration": dt_k * 1e3,
+           "halo": "peer memory (CUDA IPC mailboxes, NVLink stores + flags from the pack / unpack kernels)" if p2p_on else "ncclSend / ncclRecv",
+           "ms_per_iteration_with_nccl_halo": dt_nccl / n * 1e3,
            "what": "one imputation iteration = sweep A + exchange + sweep B + exchange; wall clock, MAX over ranks; parameter "
                    "step = relayout + backward filter + fixed-noise solve + all-reduce of per-block ll deg + commit; "
                    "mcmc_iters_per_sec counts one sweep + one parameter step per iteration like the N=1 entry"}

@@ -172,6 +172,16 @@ struct dmcmc_ctx {
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_world = 1;
     DevBuf<double> cb_send, cb_recv, d_gl_llp, d_gl_ll;
+    // halo exchange over peer memory (dmcmc_comm_enable_p2p): one IPC-shared region per rank = [flags 256 B | mailbox of
+    // messages going left | mailbox of messages going right]; flags: data_seq[2] (written by the sender), ack_seq[2]
+    // (written by the receiver into the SENDER's region)
+    bool p2p_on = false;
+    size_t p2p_cap = 0;                        // bytes per mailbox
+    char *p2p_region = nullptr;                // mine
+    char *p2p_peer[2] = {nullptr, nullptr};    // left (rank - 1) and right (rank + 1) neighbour's region, mapped here
+    unsigned long long p2p_sent[2] = {0, 0}, p2p_recvd[2] = {0, 0};   // per direction (0: leftwards, 1: rightwards)
+    unsigned int *p2p_counter = nullptr;       // device: [4] CTA counters (push / pull per direction)
+    int *p2p_err = nullptr, *p2p_err_dev = nullptr;  // host-mapped time-out flag
     DevBuf<int32_t> d_gl_ok, d_gidx;
 };
 
@@ -573,6 +583,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -596,6 +607,7 @@ NcclApi *nccl_api(std::string &err) {
     DMCMC_NCCL_SYM(Send, "ncclSend")
     DMCMC_NCCL_SYM(Recv, "ncclRecv")
     DMCMC_NCCL_SYM(AllReduce, "ncclAllReduce")
+    DMCMC_NCCL_SYM(AllGather, "ncclAllGather")
     DMCMC_NCCL_SYM(GroupStart, "ncclGroupStart")
     DMCMC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
     DMCMC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -625,7 +637,21 @@ __global__ void adapt_rho_kernel(int nblk, const int32_t *i1, const int32_t *i2,
     prop[b] = 0;
 }
 
+static void p2p_release(dmcmc_ctx *ctx) {
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->p2p_peer[i]) cudaIpcCloseMemHandle(ctx->p2p_peer[i]);
+        ctx->p2p_peer[i] = nullptr;
+    }
+    if (ctx->p2p_region) cudaFree(ctx->p2p_region);
+    if (ctx->p2p_counter) cudaFree(ctx->p2p_counter);
+    if (ctx->p2p_err) cudaFreeHost(ctx->p2p_err);
+    ctx->p2p_region = nullptr; ctx->p2p_counter = nullptr; ctx->p2p_err = nullptr; ctx->p2p_err_dev = nullptr;
+    ctx->p2p_on = false; ctx->p2p_cap = 0;
+    ctx->p2p_sent[0] = ctx->p2p_sent[1] = ctx->p2p_recvd[0] = ctx->p2p_recvd[1] = 0;
+}
+
 void comm_release(dmcmc_ctx *ctx) {
+    p2p_release(ctx);
     if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
     ctx->comm = nullptr;
     ctx->cb_send.release(); ctx->cb_recv.release(); ctx->d_gl_llp.release(); ctx->d_gl_ll.release();
@@ -1944,6 +1970,119 @@ extern "C" int dmcmc_comm_destroy(dmcmc_ctx *ctx) {
     return 0;
 }
 
+// Collective over the communicator: every rank allocates its mailbox region, the CUDA IPC handles travel by one
+// ncclAllGather, each rank maps its two neighbours' regions.  Peer memory is used only if EVERY rank got that far (the
+// ranks agree through an all-reduce); otherwise dmcmc_halo_exchange stays on ncclSend / ncclRecv.  mailbox_bytes: the
+// largest halo message (n_chains x Euler steps of half_len + 1 intervals x d doubles); larger messages go through NCCL.
+extern "C" int dmcmc_comm_enable_p2p(dmcmc_ctx *ctx, int64_t mailbox_bytes) {
+    REQUIRE(ctx && ctx->comm, "dmcmc_comm_enable_p2p: call dmcmc_comm_init first");
+    REQUIRE(mailbox_bytes > 0, "dmcmc_comm_enable_p2p: bad mailbox size");
+    CK(cudaSetDevice(ctx->cfg.device));
+    if (sync(ctx)) return -1;
+    std::string err;
+    NcclApi *nc = nccl_api(err);
+    REQUIRE(nc, "dmcmc_comm_enable_p2p: " + err);
+    p2p_release(ctx);
+    const int r = ctx->comm_rank, w = ctx->comm_world;
+    if (w == 1) return 0;
+    const size_t cap = ((size_t)mailbox_bytes + 255) & ~(size_t)255;
+    struct Rec { cudaIpcMemHandle_t h; int32_t ok; int32_t pad[15]; };
+    static_assert(sizeof(Rec) == 128, "IPC record");
+    Rec mine{};
+    int ok = 1;
+    if (cudaMalloc((void **)&ctx->p2p_region, 256 + 2 * cap) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(ctx->p2p_region, 0, 256 + 2 * cap) != cudaSuccess) ok = 0;
+    if (ok && cudaMalloc((void **)&ctx->p2p_counter, 4 * sizeof(unsigned int)) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(ctx->p2p_counter, 0, 4 * sizeof(unsigned int)) != cudaSuccess) ok = 0;
+    if (ok && cudaHostAlloc((void **)&ctx->p2p_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) ok = 0;
+    if (ok) { *ctx->p2p_err = 0; if (cudaHostGetDevicePointer((void **)&ctx->p2p_err_dev, ctx->p2p_err, 0) != cudaSuccess) ok = 0; }
+    if (ok && cudaIpcGetMemHandle(&mine.h, ctx->p2p_region) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    mine.ok = ok;
+    // all-gather the records (device buffers: NCCL)
+    Rec *d_all = nullptr, *d_mine = nullptr;
+    CK(cudaMalloc((void **)&d_all, sizeof(Rec) * w));
+    CK(cudaMalloc((void **)&d_mine, sizeof(Rec)));
+    CK(cudaMemcpyAsync(d_mine, &mine, sizeof(Rec), cudaMemcpyHostToDevice, ctx->stream));
+    NK(nc->AllGather(d_mine, d_all, sizeof(Rec), ncclChar, ctx->comm, ctx->stream));
+    std::vector<Rec> all(w);
+    CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * w, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    for (int i = 0; i < w; ++i) ok = ok && all[i].ok;
+    if (ok) {
+        for (int side = 0; side < 2 && ok; ++side) {
+            const int peer = side == 0 ? r - 1 : r + 1;
+            if (peer < 0 || peer >= w) continue;
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[peer].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            ctx->p2p_peer[side] = (char *)ptr;
+        }
+    }
+    // every rank must have mapped its neighbours
+    int32_t *d_ok = reinterpret_cast<int32_t *>(d_mine);
+    const int32_t okv = ok;
+    CK(cudaMemcpyAsync(d_ok, &okv, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NK(nc->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+    int32_t all_ok = 0;
+    CK(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sync(ctx)) return -1;
+    cudaFree(d_all);
+    cudaFree(d_mine);
+    if (!all_ok) { p2p_release(ctx); return 0; }
+    ctx->p2p_on = true;
+    ctx->p2p_cap = cap;
+    return 0;
+}
+
+extern "C" int dmcmc_comm_p2p_enabled(const dmcmc_ctx *ctx) { return ctx && ctx->p2p_on ? 1 : 0; }
+
+static SegmentParams seg_params(dmcmc_ctx *ctx, int j0, int j1, double *dev, int64_t stride, int up) {
+    SegmentParams g{};
+    g.C = ctx->C; g.D = ctx->d; g.j0 = j0; g.j1 = j1; g.steps = ctx->st_off[j1] - ctx->st_off[j0]; g.TT = ctx->TT;
+    g.iv_N = ctx->d_N.p; g.iv_tile_off = ctx->d_tile_off.p; g.iv_st_off = ctx->d_st_off.p;
+    g.iv_xoff = ctx->d_xoff.p; g.iv_xs = ctx->d_xs.p;
+    g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
+    g.selX = ctx->d_selX[ctx->sel_cur].p;
+    g.packed = dev; g.upload = up; g.pk_stride = stride;
+    return g;
+}
+
+// one direction of the exchange over peer memory.  dir 0: messages go to rank - 1, dir 1: to rank + 1.
+//   send: intervals [sj0, sj1) -> the neighbour's mailbox[dir];   receive: own mailbox[dir] -> intervals [rj0, rj1),
+//   preceded (dir 1) by `lead` doubles per chain whose last d are the new starting point
+static int halo_p2p(dmcmc_ctx *ctx, int dir, bool send, int sj0, int sj1, bool recv, int rj0, int rj1, size_t lead) {
+    if (!send && !recv) return 0;
+    REQUIRE(*ctx->p2p_err == 0, "dmcmc_halo_exchange: a wait on the neighbouring GPU timed out (peer gone?)");
+    char *flags = ctx->p2p_region;
+    auto data_seq = [](char *region, int d) { return reinterpret_cast<unsigned long long *>(region) + d; };
+    auto ack_seq = [](char *region, int d) { return reinterpret_cast<unsigned long long *>(region) + 2 + d; };
+    auto mailbox = [&](char *region, int d) { return reinterpret_cast<double *>(region + 256 + (size_t)d * ctx->p2p_cap); };
+    SegmentParams gs{}, gr{};
+    P2PSync ys{}, yr{};
+    const double *start_src = nullptr;
+    int64_t stride = 0;
+    if (send) {
+        char *peer = ctx->p2p_peer[dir == 0 ? 0 : 1];
+        gs = seg_params(ctx, sj0, sj1, mailbox(peer, dir), (int64_t)(ctx->st_off[sj1] - ctx->st_off[sj0]) * ctx->d, 0);
+        ys = P2PSync{ack_seq(flags, dir), ctx->p2p_sent[dir], data_seq(peer, dir), ctx->p2p_sent[dir] + 1,
+                     ctx->p2p_counter + dir, ctx->p2p_err_dev};
+        ++ctx->p2p_sent[dir];
+    }
+    if (recv) {
+        char *peer = ctx->p2p_peer[dir == 0 ? 1 : 0];   // the sender: right neighbour for leftward messages
+        stride = (int64_t)lead + (int64_t)(ctx->st_off[rj1] - ctx->st_off[rj0]) * ctx->d;
+        double *mb = mailbox(flags, dir);
+        gr = seg_params(ctx, rj0, rj1, mb + lead, stride, 1);
+        yr = P2PSync{data_seq(flags, dir), ctx->p2p_recvd[dir] + 1, ack_seq(peer, dir), ctx->p2p_recvd[dir] + 1,
+                     ctx->p2p_counter + 2 + dir, ctx->p2p_err_dev};
+        start_src = lead ? mb + lead - ctx->d : nullptr;
+        ++ctx->p2p_recvd[dir];
+        ctx->w_valid = false;
+    }
+    CK(launch_halo_exchange(send ? &gs : nullptr, ys, recv ? &gr : nullptr, ctx->d_x0.p, start_src, stride, ctx->R, yr, ctx->stream));
+    return 0;
+}
+
 static int seg_on_stream(dmcmc_ctx *ctx, int j0, int j1, double *dev, int64_t stride, int up) {
     const int steps = ctx->st_off[j1] - ctx->st_off[j0];
     SegmentParams g{};
@@ -1979,8 +2118,14 @@ extern "C" int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_
     const int n_own = J - n_halo;
     const size_t C = (size_t)ctx->C;
     if (after_pattern == 0) {
-        const size_t send_n = r > 0 ? C * (size_t)(ctx->st_off[n_first] - ctx->st_off[0]) * d : 0;
-        const size_t recv_n = r < w - 1 ? C * (size_t)(ctx->st_off[J] - ctx->st_off[n_own]) * d : 0;
+        size_t send_n = r > 0 ? C * (size_t)(ctx->st_off[n_first] - ctx->st_off[0]) * d : 0;
+        size_t recv_n = r < w - 1 ? C * (size_t)(ctx->st_off[J] - ctx->st_off[n_own]) * d : 0;
+        // per link: a message that fits the mailbox goes over peer memory (both ends see the same size), else NCCL
+        const bool ps = ctx->p2p_on && send_n * sizeof(double) <= ctx->p2p_cap, pr = ctx->p2p_on && recv_n * sizeof(double) <= ctx->p2p_cap;
+        if (halo_p2p(ctx, 0, ps && send_n > 0, 0, n_first, pr && recv_n > 0, n_own, J, 0)) return -1;
+        if (ps) send_n = 0;
+        if (pr) recv_n = 0;
+        if (send_n == 0 && recv_n == 0) return 0;
         CK(ctx->cb_send.ensure(std::max<size_t>(send_n, 1)));
         CK(ctx->cb_recv.ensure(std::max<size_t>(recv_n, 1)));
         if (send_n && seg_on_stream(ctx, 0, n_first, ctx->cb_send.p, (int64_t)(send_n / C), 0)) return -1;
@@ -1991,10 +2136,15 @@ extern "C" int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_
         if (recv_n && seg_on_stream(ctx, n_own, J, ctx->cb_recv.p, (int64_t)(recv_n / C), 1)) return -1;
         if (recv_n) ctx->w_valid = false;
     } else {
-        const size_t send_n = r < w - 1 ? C * (size_t)(ctx->st_off[J] - ctx->st_off[n_own - 1]) * d : 0;
+        size_t send_n = r < w - 1 ? C * (size_t)(ctx->st_off[J] - ctx->st_off[n_own - 1]) * d : 0;
         const size_t first_steps = (size_t)(ctx->st_off[n_first] - ctx->st_off[0]);
-        const size_t recv_n = r > 0 ? C * ((size_t)left_edge_steps + first_steps) * d : 0;
+        size_t recv_n = r > 0 ? C * ((size_t)left_edge_steps + first_steps) * d : 0;
         REQUIRE(r == 0 || left_edge_steps > 0, "dmcmc_halo_exchange: left_edge_steps missing");
+        const bool ps = ctx->p2p_on && send_n * sizeof(double) <= ctx->p2p_cap, pr = ctx->p2p_on && recv_n * sizeof(double) <= ctx->p2p_cap;
+        if (halo_p2p(ctx, 1, ps && send_n > 0, n_own - 1, J, pr && recv_n > 0, 0, n_first, (size_t)left_edge_steps * d)) return -1;
+        if (ps) send_n = 0;
+        if (pr) recv_n = 0;
+        if (send_n == 0 && recv_n == 0) return 0;
         CK(ctx->cb_send.ensure(std::max<size_t>(send_n, 1)));
         CK(ctx->cb_recv.ensure(std::max<size_t>(recv_n, 1)));
         if (send_n && seg_on_stream(ctx, n_own - 1, J, ctx->cb_send.p, (int64_t)(send_n / C), 0)) return -1;

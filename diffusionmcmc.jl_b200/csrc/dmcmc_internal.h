@@ -107,6 +107,24 @@ struct SegmentParams {
     int32_t upload;   // 0: X -> packed, 1: packed -> X
 };
 cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s);
+
+// Halo exchange over peer memory (NVLink P2P, CUDA IPC mailboxes; dmcmc_comm_enable_p2p): the pack kernel of the sending
+// rank writes straight into the neighbour's mailbox and raises a sequence flag there, the unpack kernel of the receiving
+// rank spins on that flag, unpacks and acknowledges -- no NCCL call, no host involvement (one ncclSend / ncclRecv pair
+// of a few hundred bytes costs ~25 us, measured).
+struct P2PSync {
+    const unsigned long long *wait_flag;  // memory of THIS GPU, written by the peer; nullptr: nothing to wait for
+    unsigned long long wait_val;          // proceed when *wait_flag >= wait_val
+    unsigned long long *signal_flag;      // memory of the PEER (mapped through CUDA IPC); nullptr: nothing to signal
+    unsigned long long signal_val;
+    unsigned int *counter;                // this GPU: CTAs of the launch that are done (reset by the last one)
+    int *err;                             // host-mapped: set to 1 when a wait times out (the peer died)
+};
+// one launch per rank and exchange: `push` (accepted X of intervals [j0, j1) -> push->packed = the peer's mailbox) and / or
+// `pull` (pull->packed = own mailbox -> accepted X; with start_src the new starting point
+// x0[(rec * D + comp) * C + chain] = start_src[chain * start_stride + rec * D + comp] as well); either may be null
+cudaError_t launch_halo_exchange(const SegmentParams *push, const P2PSync &ys, const SegmentParams *pull, double *x0,
+                                 const double *start_src, int64_t start_stride, int R, const P2PSync &yr, cudaStream_t s);
 cudaError_t launch_set_start(double *x0, const double *src, int64_t chain_stride, int C, int R, int D, cudaStream_t s);
 
 // noise transposition [C][S][M] -> [M][TT][C][8] is done on the host in the C-ABI layer.

@@ -669,6 +669,120 @@ cudaError_t launch_segment(const SegmentParams &g, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---- halo exchange over peer memory --------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// every CTA: thread 0 spins on the flag (three seconds at most: a dead peer must not hang the GPU), then the CTA goes on
+__device__ __forceinline__ void p2p_wait(const P2PSync &y) {
+    if (y.wait_flag && threadIdx.x == 0) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(y.wait_flag) < y.wait_val) {
+            if (global_ns() - t0 > 3000000000ULL) { *y.err = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+// the last CTA (of the nb CTAs in this role) to finish raises the flag in the peer's memory, after every CTA's writes.
+// ONE st.release.sys by one thread: the release is cumulative over what the CTA barrier (and, across CTAs, the gpu-scope
+// fence around the counter) has ordered before it.  Measured between two B200s (tools/micro/p2p_latency.cu): 4.2 us per
+// hand-over of 150 doubles this way, 5.8 us with an extra __threadfence_system() by the signalling thread, 9.2 us with
+// one by every thread (the first version here).
+__device__ __forceinline__ void p2p_signal(const P2PSync &y, unsigned nb) {
+    if (!y.signal_flag) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool last = true;
+        if (nb > 1) {
+            __threadfence();
+            last = atomicAdd(y.counter, 1u) == nb - 1;
+            if (last) { *y.counter = 0; __threadfence(); }
+        }
+        if (last) st_release_sys(y.signal_flag, y.signal_val);
+    }
+}
+// element u of the packed message -> its address in the accepted container and (pk) in the message
+__device__ __forceinline__ double *halo_element(const SegmentParams &g, long long u, size_t &pk) {
+    const long long per = (long long)g.steps * g.D;
+    const int ci = (int)(u / per);
+    const int rem = (int)(u - (long long)ci * per), step = rem / g.D, c = rem - step * g.D;
+    int j = g.j0;
+    const int base = g.iv_st_off[g.j0];
+    while (j + 1 < g.j1 && g.iv_st_off[j + 1] - base <= step) ++j;
+    const int k = step - (g.iv_st_off[j] - base), chain = g.c0 + ci;
+    pk = (size_t)ci * g.pk_stride + (size_t)step * g.D + c;
+    return g.X[g.selX[(size_t)j * g.C + chain]] + g.iv_xoff[j] + (size_t)chain * g.iv_xs[j] + (size_t)k * g.D + c;
+}
+
+// One launch per rank and exchange.  CTAs [0, nb_push) SEND: wait until the neighbour has taken the previous message out
+// of its mailbox, store the accepted X of intervals [gs.j0, gs.j1) straight into that mailbox (peer memory: the stores go
+// out over NVLink), raise its data flag.  The other CTAs RECEIVE: spin on the own data flag, unpack the own mailbox into
+// intervals [gr.j0, gr.j1) (and the new starting point), acknowledge in the sender's memory.  Launched with programmatic
+// stream serialisation like the sweeps around it, so its launch latency hides behind the sweep's tail.
+__global__ void __launch_bounds__(128) halo_xchg_kernel(const SegmentParams gs, const P2PSync ys, const unsigned nb_push,
+                                                        const SegmentParams gr, double *x0, const double *start_src,
+                                                        const long long start_stride, const int R, const P2PSync yr) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the sweep before this has written the paths and selectors
+    if (blockIdx.x < nb_push) {
+        p2p_wait(ys);
+        const long long n = (long long)(gs.nc > 0 ? gs.nc : gs.C) * gs.steps * gs.D;
+        for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (long long)nb_push * blockDim.x) {
+            size_t pk;
+            const double *x = halo_element(gs, u, pk);
+            gs.packed[pk] = *x;
+        }
+        p2p_signal(ys, nb_push);
+    } else {
+        const unsigned nb = gridDim.x - nb_push, bid = blockIdx.x - nb_push;
+        p2p_wait(yr);
+        const long long n = (long long)(gr.nc > 0 ? gr.nc : gr.C) * gr.steps * gr.D;
+        const long long ns = start_src ? (long long)gr.C * R * gr.D : 0;
+        for (long long u = (long long)bid * blockDim.x + threadIdx.x; u < n + ns; u += (long long)nb * blockDim.x) {
+            if (u < n) {
+                size_t pk;
+                double *x = halo_element(gr, u, pk);
+                *x = __ldcg(gr.packed + pk);
+            } else {
+                const long long v = u - n;
+                const int chain = (int)(v % gr.C), rc = (int)(v / gr.C);
+                x0[(size_t)rc * gr.C + chain] = __ldcg(start_src + (size_t)chain * start_stride + rc);
+            }
+        }
+        p2p_signal(yr, nb);  // acknowledge: the mailbox may be overwritten
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+cudaError_t launch_halo_exchange(const SegmentParams *push, const P2PSync &ys, const SegmentParams *pull, double *x0,
+                                 const double *start_src, int64_t start_stride, int R, const P2PSync &yr, cudaStream_t s) {
+    auto ctas = [](long long n) { return (unsigned)std::min<long long>(std::max<long long>((n + 127) / 128, 1), 148 * 2); };
+    SegmentParams gs{}, gr{};
+    unsigned nb_push = 0, nb_pull = 0;
+    if (push) { gs = *push; nb_push = ctas((long long)(gs.nc > 0 ? gs.nc : gs.C) * gs.steps * gs.D); }
+    if (pull) { gr = *pull; nb_pull = ctas((long long)(gr.nc > 0 ? gr.nc : gr.C) * gr.steps * gr.D + (start_src ? (long long)gr.C * R * gr.D : 0)); }
+    if (nb_push + nb_pull == 0) return cudaSuccess;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nb_push + nb_pull);
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, halo_xchg_kernel, gs, ys, nb_push, gr, x0, start_src, (long long)start_stride, R, yr);
+}
+
 cudaError_t launch_gather(const GatherParams &g, cudaStream_t s) {
     const long long n = (long long)g.J * g.C;
     if (n == 0) return cudaSuccess;

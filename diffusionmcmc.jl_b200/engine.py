@@ -269,6 +269,12 @@ class Engine:
     def comm_init(self, unique_id, rank, world):
         self._ck(self.lib.dmcmc_comm_init(self.h, C.c_char_p(unique_id), int(rank), int(world)))
 
+    def comm_enable_p2p(self, mailbox_bytes):
+        """Halo exchange over peer memory (CUDA IPC mailboxes, NVLink stores + flags) instead of NCCL send / recv;
+        collective.  Returns True when every rank could map its neighbours (otherwise the exchange stays on NCCL)."""
+        self._ck(self.lib.dmcmc_comm_enable_p2p(self.h, int(mailbox_bytes)))
+        return bool(self.lib.dmcmc_comm_p2p_enabled(self.h))
+
     def comm_destroy(self):
         self._ck(self.lib.dmcmc_comm_destroy(self.h))
 

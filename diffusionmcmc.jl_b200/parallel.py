@@ -18,6 +18,8 @@ Two ways the path shards, both one process/context per GPU:
   index (`interval_offset`), and each block's backward-filter table depends only on the block's own
   observations, so a sharded run reproduces the single-GPU run bit for bit.
 """
+import os
+
 import numpy as np
 
 
@@ -98,6 +100,7 @@ class BlockShardedSampler:
         self.rank, self.world, self.h = rank, world, half_len
         N = np.asarray(spec["N"])
         self.n = len(N)
+        self.N_max = int(N.max())   # longest interval of the whole recording (the same number on every rank)
         edges = shard_intervals(self.n, world, half_len)
         self.a, self.b = edges[rank], edges[rank + 1]
         self.b_ext = min(self.b + half_len, self.n) if rank < world - 1 else self.b
@@ -283,13 +286,21 @@ class LibHalo:
     what a host without torch.distributed, i.e. the Julia plugin, calls.  `unique_id` comes from
     Engine.comm_unique_id() on one rank and is handed to the others by the host."""
 
-    def __init__(self, sampler, unique_id):
+    def __init__(self, sampler, unique_id, p2p=None):
         s = self.s = sampler
         s.engine.comm_init(unique_id, s.rank, s.world)
         n_own = s.b - s.a
         self.n_first = min(s.h, n_own)
         self.n_halo = s.b_ext - s.b
         self.left_edge_steps = int(s.N_left_edge) if s.rank > 0 else 0
+        # peer-memory mailboxes for the exchange (DMCMC_P2P=0: stay on ncclSend / ncclRecv).  Size: the largest message of
+        # any rank, h + 1 intervals of the longest interval of the whole recording (the same number on every rank)
+        self.p2p = False
+        if p2p is None:
+            p2p = os.environ.get("DMCMC_P2P", "1") != "0"
+        if p2p and s.world > 1:
+            e = s.engine
+            self.p2p = e.comm_enable_p2p((s.h + 1) * s.N_max * e.d * 8 * e.C)
 
     def iterate(self, it):
         s, e = self.s, self.s.engine

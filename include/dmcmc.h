@@ -242,6 +242,16 @@ int dmcmc_comm_destroy(dmcmc_ctx *ctx);
  * left_edge_steps: Euler steps of the left neighbour's last owned interval (0 on rank 0). */
 int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_t n_first, int32_t n_halo,
                         int32_t left_edge_steps);
+/* The same exchange over peer memory instead of NCCL (collective over the communicator, once after dmcmc_comm_init):
+ * every rank allocates a mailbox per direction, the CUDA IPC handles travel by one ncclAllGather, each rank maps its two
+ * neighbours.  From then on dmcmc_halo_exchange is two small kernels per rank: the sender's pack kernel stores straight
+ * into the neighbour's mailbox over NVLink and raises a sequence flag there, the receiver's unpack kernel spins on the
+ * flag, unpacks and acknowledges -- no NCCL call, no host synchronisation (a ncclSend / ncclRecv pair of a few hundred
+ * bytes costs ~25 us; this is what a single chain's block sharding is bound by).  Messages larger than mailbox_bytes,
+ * and every exchange when IPC is unavailable on any rank, still go through NCCL; results are identical either way.
+ * dmcmc_comm_p2p_enabled: 1 when peer memory is in use. */
+int dmcmc_comm_enable_p2p(dmcmc_ctx *ctx, int64_t mailbox_bytes);
+int dmcmc_comm_p2p_enabled(const dmcmc_ctx *ctx);
 /* a9 on a block-sharded recording (set_proposal!, src/run!_alterations.jl:177-211; ONE accept decision
  * for all blocks, :367): every rank solves its blocks, the per-block ll deg / ll are all-reduced over the
  * GLOBAL block index (blk_global[b] = global index of local block b, -1 = owned by another rank) and

@@ -39,7 +39,7 @@ def _thetas(spec):
     return th1, th2
 
 
-def _worker(rank, world, uid, q):
+def _worker(rank, world, uid, q, p2p):
     sys.path.insert(0, ROOT)
     import dmcmc_pkg
     pkg = dmcmc_pkg.load()
@@ -49,7 +49,7 @@ def _worker(rank, world, uid, q):
     mk = lambda sp, off: Engine(sp, device=rank, seed=SEED, interval_offset=off)
     full0 = parallel.initial_full_path(spec, mk)
     s = parallel.BlockShardedSampler(spec, rank, world, H, mk, full0)
-    halo = parallel.LibHalo(s, uid)
+    halo = parallel.LibHalo(s, uid, p2p=p2p)
     th1, th2 = _thetas(spec)
     for it in range(ITERS):
         halo.iterate(it)
@@ -58,7 +58,7 @@ def _worker(rank, world, uid, q):
         halo.iterate(it)
     p2 = halo.param_step(th2, lambda llp, ll, ok: False)
     halo.iterate(2 * ITERS)
-    q.put((rank, s.owned_path(), p1[:3], p2[:3]))
+    q.put((rank, s.owned_path(), p1[:3], p2[:3], halo.p2p))
     s.engine.comm_destroy()
     s.engine.close()
 
@@ -98,8 +98,11 @@ def _unsharded(pkg):
     return X, p1, p2
 
 
+@pytest.mark.parametrize("halo", ["nccl", "peer_memory"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_block_sharded_sweeps_and_parameter_step_in_library_nccl(pkg, world):
+def test_block_sharded_sweeps_and_parameter_step_in_library_nccl(pkg, world, halo):
+    """halo = nccl: end-point exchange by ncclSend / ncclRecv; peer_memory: by stores into the neighbour's CUDA-IPC mailbox
+    and sequence flags (dmcmc_comm_enable_p2p).  Both must reproduce one GPU bit for bit."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -108,18 +111,19 @@ def test_block_sharded_sweeps_and_parameter_step_in_library_nccl(pkg, world):
     uid = Engine.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, uid, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, uid, q, halo == "peer_memory")) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    assert all(r[4] == (halo == "peer_memory") for r in res), "peer-memory mailboxes could not be set up (CUDA IPC)"
     X = np.concatenate([r[1] for r in res], axis=1)
     assert np.array_equal(X, Xref), f"sharded over {world} GPUs != unsharded: max diff {np.abs(X - Xref).max()}"
-    for rank, _, p1, p2 in res:
+    for rank, _, p1, p2, _ in res:
         for got, ref, what in ((p1, r1, "accepted"), (p2, r2, "rejected")):
             assert np.array_equal(got[0], ref[0]), f"rank {rank}: ll deg of the {what} parameter step differs from the unsharded run"
             assert np.array_equal(got[1], ref[1]), f"rank {rank}: ll of the {what} parameter step differs"
             assert np.array_equal(got[2], ref[2])
-    print(f"block sharding over {world} GPUs (in-library NCCL): paths, per-block ll deg / ll, success bitwise equal to one GPU")
+    print(f"block sharding over {world} GPUs (in-library collectives, halo by {halo}): paths, per-block ll deg / ll, success bitwise equal to one GPU")
