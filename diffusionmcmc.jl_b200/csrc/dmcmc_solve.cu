@@ -296,26 +296,39 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? DMCMC_MINB : 2) solve_kernel
                 const double *hrec = srec + (size_t)half * TILE * RS;
                 const uint32_t hst = IS::cursor(sst, lane);
                 [[maybe_unused]] double *xph = Xp + (size_t)kh * D;
-                [[maybe_unused]] double dwo[STORE_W_MODE ? M : 1][TILE];
-                [[maybe_unused]] ZT z[(MODE == MODE_IMPUTE) ? M : 1][TILE];
+                // The fused FitzHugh-Nagumo step keeps all eight steps in one basic block.  The generic step is ~450
+                // instructions: eight copies (times two CHECK variants) made the loop 126 KB of code against a 32 KB
+                // instruction cache (ncu on Lorenz-63: no_instruction 0.5 warps per issue), so it is unrolled by FOUR
+                // steps -- one Philox call per Wiener component -- inside a rolled loop of two.
+                constexpr int QN = FAST ? 1 : 2, SL = TILE / QN;
+#pragma unroll 1
+              for (int hq = 0; hq < QN; ++hq) {
+                const int s0 = hq * SL;
+                [[maybe_unused]] double dwo[STORE_W_MODE ? M : 1][SL];
+                [[maybe_unused]] ZT z[(MODE == MODE_IMPUTE) ? M : 1][SL];
                 if constexpr (MODE == MODE_IMPUTE) {
                     if constexpr (PHILOX) {
 #pragma unroll
                         for (int w = 0; w < M; ++w)
 #pragma unroll
-                            for (int h = 0; h < TILE / 4; ++h)
+                            for (int h = 0; h < SL / 4; ++h)
                                 philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w,
-                                                (uint32_t)((kh >> 2) + h), (float *)&z[w][4 * h]);
+                                                (uint32_t)(((kh + s0) >> 2) + h), (float *)&z[w][4 * h]);
                     } else {
 #pragma unroll
-                        for (int w = 0; w < M; ++w) ld_tile_stream(p.Z + w_off(wtile, chain, w, p.C, M), (double *)z[w]);
+                        for (int w = 0; w < M; ++w) {
+                            const double *zsrc = p.Z + w_off(wtile, chain, w, p.C, M) + s0;
+                            if constexpr (SL == TILE) ld_tile_stream(zsrc, (double *)z[w]);
+                            else asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(z[w][0]), "=d"(z[w][1]), "=d"(z[w][2]), "=d"(z[w][3]) : "l"(zsrc));
+                        }
                     }
                 }
                 double xprev[D];  // proposal state after the previous (even) step: stored together with the odd one
 #pragma unroll
                 for (int c = 0; c < D; ++c) xprev[c] = 0.0;
 #pragma unroll
-                for (int s = 0; s < TILE; ++s) {
+                for (int si = 0; si < SL; ++si) {
+                    const int s = s0 + si;
                     const int ks = half * TILE + s;  // step within the tile
                     const bool live = !CHECK || (kh + s < N);  // CTA-uniform
                     const double *rp = hrec + s * RS;
@@ -341,7 +354,7 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? DMCMC_MINB : 2) solve_kernel
                             } else if constexpr (NEED_WA) {
                                 IS::noise(hst, ks, dw);
                             }
-                            if constexpr (MODE == MODE_IMPUTE) dw[0] = fma(lam * rec[FD_SQ], (double)z[0][s], rho * dw[0]);  // pCN
+                            if constexpr (MODE == MODE_IMPUTE) dw[0] = fma(lam * rec[FD_SQ], (double)z[0][si], rho * dw[0]);  // pCN
                             if constexpr (SOLVE) {
                                 fhn_step(fk, rec, R0c, fma(fk.sig, dw[0], Cf), x[0], x[1], lsum);
                             }
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? DMCMC_MINB : 2) solve_kernel
                             }
                             if constexpr (MODE == MODE_IMPUTE) {  // pCN: W deg = sqrt(1-rho^2) W_fresh + rho W
 #pragma unroll
-                                for (int w = 0; w < M; ++w) dw[w] = lam * (rec[1] * (double)z[w][s]) + rho * dw[w];
+                                for (int w = 0; w < M; ++w) dw[w] = lam * (rec[1] * (double)z[w][si]) + rho * dw[w];
                             }
                             if constexpr (SOLVE) {
                                 double dr[D], sdw[D], gg;
@@ -380,10 +393,10 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? DMCMC_MINB : 2) solve_kernel
                     }
                     if constexpr (STORE_W_MODE) {
 #pragma unroll
-                        for (int w = 0; w < M; ++w) dwo[w][s] = dw[w];
+                        for (int w = 0; w < M; ++w) dwo[w][si] = dw[w];
                     }
                     if constexpr (SOLVE) {
-                        if (s & 1) {  // two steps per store: 16-byte aligned (32 for d = 2)
+                        if (si & 1) {  // two steps per store: 16-byte aligned (32 for d = 2)
                             if (live && active) {
                                 double *dst = xph + (s - 1) * D;
                                 if constexpr (D == 2) {
@@ -413,14 +426,22 @@ __global__ void __launch_bounds__(128, MD::D == 2 ? DMCMC_MINB : 2) solve_kernel
                 if constexpr (STORE_W_MODE) {
                     if (store_w) {
 #pragma unroll
-                        for (int w = 0; w < M; ++w) st_tile(Wdst + w_off(wtile, chain, w, p.C, M), dwo[w]);
+                        for (int w = 0; w < M; ++w) {
+                            double *wd = Wdst + w_off(wtile, chain, w, p.C, M) + s0;
+                            if constexpr (SL == TILE) st_tile(wd, dwo[w]);
+                            else st_v4(wd, dwo[w][0], dwo[w][1], dwo[w][2], dwo[w][3]);
+                        }
                     }
                 }
+              }
             };
 #pragma unroll 1
             for (int half = 0; half < TS / TILE; ++half) {
                 const int kh = tl * TS + half * TILE;
-                if (kh + TILE <= N) eight(std::false_type{}, half);
+                // generic models: one copy of the eight-step body (the live test is CTA-uniform); two copies of the ~450
+                // instructions per step put the loop at 126 KB, far beyond the instruction cache (ncu: no_instruction 0.5
+                // warps per issue on Lorenz-63)
+                if (FAST && kh + TILE <= N) eight(std::false_type{}, half);
                 else if (kh < N) eight(std::true_type{}, half);
             }
         }
