@@ -244,4 +244,20 @@ function save_path!(gws::B200GlobalWorkspace)
     buf.next[] = mod1(buf.next[] + 1, length(buf.XX))
 end
 
+# ---- one long recording over the GPUs of a box (no counterpart in the reference; SURVEY 8e, INTEGRATION.md "Multi-GPU") ----
+# One process and one context per GPU; `id` = 128 bytes from comm_unique_id() on one rank, handed to the others by the
+# host's own means.  The collectives live in the library: nothing here needs CUDA.jl, NCCL.jl or MPI.
+comm_unique_id() = (id = Vector{UInt8}(undef, 128); ccall((:dmcmc_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("NCCL not available"); id)
+comm_init!(ctx, id::Vector{UInt8}, rank::Integer, world::Integer) =
+    check(ctx, ccall((:dmcmc_comm_init, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), ctx.h, id, rank, world))
+# end-point exchange over NVLink peer memory instead of ncclSend / ncclRecv (collective); true when every rank has it
+function comm_enable_p2p!(ctx, mailbox_bytes::Integer)
+    check(ctx, ccall((:dmcmc_comm_enable_p2p, LIB), Cint, (Ptr{Cvoid}, Int64), ctx.h, mailbox_bytes))
+    ccall((:dmcmc_comm_p2p_enabled, LIB), Cint, (Ptr{Cvoid},), ctx.h) != 0
+end
+halo_exchange!(ctx, after_pattern::Integer, n_first::Integer, n_halo::Integer, left_edge_steps::Integer) =
+    check(ctx, ccall((:dmcmc_halo_exchange, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Int32),
+                     ctx.h, after_pattern, n_first, n_halo, left_edge_steps))
+comm_destroy!(ctx) = check(ctx, ccall((:dmcmc_comm_destroy, LIB), Cint, (Ptr{Cvoid},), ctx.h))
+
 end # module
