@@ -257,10 +257,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     if constexpr (MODE != MODE_IMPUTE) {
                         z[w] = 0.0;
                     } else if constexpr (PHILOX) {
-                        float z4[4];
-                        philox_normal4f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w, (uint32_t)(k >> 2), z4);
-                        const int e = k & 3;
-                        z[w] = e == 0 ? z4[0] : (e == 1 ? z4[1] : (e == 2 ? z4[2] : z4[3]));
+                        z[w] = philox_normal1f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w, (uint32_t)k);
                     } else {
                         z[w] = live ? p.Z[w_off(wtile0 + (size_t)(k >> 3), chain, w, p.C, M) + (k & 7)] : 0.0;
                     }

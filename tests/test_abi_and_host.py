@@ -160,3 +160,17 @@ def test_parameter_updates_refuse_a_chain_batch(pkg):
     mcmc = pkg.MCMC([pkg.PathImputation(0.9), pkg.RandomWalkUpdate(0.1, [2])])
     with pytest.raises(ValueError, match="n_chains == 1"):
         pkg.run_(mcmc, 3, data, data["theta"])
+
+
+def test_table_fragment_order_of_the_tensor_core_kernel(tmp_path):
+    """The d = 40 table record stores H and Psi' in mma.m8n8k4 fragment order (big_frag): a bijection, and exactly the
+    element a lane of the Lorenz-96 kernel expects at the address it loads (host-only program, compiled with nvcc)."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = tmp_path / "frag_order_check"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "frag_order_check.cu")
+    subprocess.check_call(["nvcc", "-std=c++17", "-o", str(exe), src])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "fragment order ok" in out.stdout, out.stdout + out.stderr
