@@ -30,7 +30,24 @@ constexpr int CT = 32;  // Euler steps per tile = lanes
 // accepted noise under the proposal law, no mix, no accept -- per-unit ll deg and success flag out.
 // MODE_RELAYOUT / MODE_LOGLIK: the accepted path only -- recover its noise (RELAYOUT: store it) and its ll under the
 // current layout (update_workspaces!, src/workspaces.jl:467-471; init_ll!, :425-431): phase P alone, plus the serial sum.
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE>
+// MS: a tile may hold up to MS WHOLE consecutive intervals when they are short (<= 32 steps together): phase P costs the
+// same for 10 live lanes as for 32, and with 10-step intervals (BASELINE config 4) it was paid per interval.  MS = 1: every
+// tile is a 32-step chunk of one interval.  The tile sequence of a block follows from iv_N alone (fit_intervals), so the
+// table pipeline, the producer and the solver agree on it without talking.
+template <int MS>
+__device__ __forceinline__ int fit_intervals(const SolveParams &p, int j, int i2, int N0, int *b) {
+    int ns = 0, tot = 0;
+    for (int jj = j; jj <= i2 && ns < MS; ++jj) {
+        const int n = jj == j ? N0 : p.iv_N[jj];
+        if (n > CT - tot) break;
+        b[ns++] = tot;
+        tot += n;
+    }
+    b[ns] = tot;
+    return ns;
+}
+
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE, int MS>
 __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     constexpr bool PARAM = MODE == MODE_PARAM;
     constexpr bool ACC_ONLY = MODE == MODE_RELAYOUT || MODE == MODE_LOGLIK;
@@ -82,6 +99,26 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     int tj = i1, ttl = 0, tq = 0, tN = p.iv_N[i1], ttoff = p.iv_tile_off[i1];
     auto issue_table = [&]() {
         if (tj > i2) return;
+        if constexpr (MS > 1) {
+            if (ttl == 0 && tN <= CT) {  // whole short intervals: one bulk copy each, in lane order, on one barrier
+                int b[MS + 1];
+                const int ns = fit_intervals<MS>(p, tj, i2, tN, b);
+                if (ns > 1) {
+                    uint64_t *bar = &full[tq & (TD - 1)];
+                    double *dst = stab + (size_t)(tq & (TD - 1)) * CT * RS;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(bar, (uint32_t)(b[ns] * RS * sizeof(double)));
+                    for (int g = 0; g < ns; ++g) {
+                        const int toff = g == 0 ? ttoff : p.iv_tile_off[tj + g];
+                        bulk_g2s(dst + (size_t)b[g] * RS, p.table + (size_t)toff * TILE * RS, (uint32_t)((b[g + 1] - b[g]) * RS * sizeof(double)), bar);
+                    }
+                    ++tq;
+                    tj += ns;
+                    if (tj <= i2) { tN = p.iv_N[tj]; ttoff = p.iv_tile_off[tj]; }
+                    return;
+                }
+            }
+        }
         const int npad = ((tN + TILE - 1) >> 3) * TILE;  // records the table holds for this interval
         const int nrec = min(CT, npad - ttl * CT);
         const uint32_t bytes = (uint32_t)(nrec * RS * sizeof(double));
@@ -159,29 +196,46 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             if (threadIdx.x == 0) issue_table();
         }
     }
-    for (int j = i1; j <= i2; ++j) {
-        const int N = p.iv_N[j], nt = (N + CT - 1) / CT;
-        const int sx = p.selX_in[(size_t)j * p.C + chain], sw = p.selW_in[(size_t)j * p.C + chain];
-        double aB[FAST ? 1 : D * D], abeta[FAST ? 1 : D], aatil[MD::CONST_SIGMA ? 1 : D * D];
+    // context of one interval: selectors, containers, aux law, pCN memory.  Loaded per interval; in a tile of several
+    // short intervals every lane loads its own interval's for phase P, and phase S walks the intervals one after another
+    int sx = 0, sw = 0;
+    double aB[FAST ? 1 : D * D], abeta[FAST ? 1 : D], aatil[MD::CONST_SIGMA ? 1 : D * D];
+    double rho = 1.0, lam = 0.0;
+    const double *Xa = nullptr, *Wa = nullptr;
+    double *Xp = nullptr, *Wp = nullptr;
+    size_t wtile0 = 0;
+    auto load_iv = [&](int jj) {
+        sx = p.selX_in[(size_t)jj * p.C + chain];
+        sw = p.selW_in[(size_t)jj * p.C + chain];
         if constexpr (FAST) {
-            fk.set_interval(p.auxB + (size_t)j * D * D, p.auxbeta + (size_t)j * D);
+            fk.set_interval(p.auxB + (size_t)jj * D * D, p.auxbeta + (size_t)jj * D);
         } else {
 #pragma unroll
-            for (int i = 0; i < D * D; ++i) aB[i] = p.auxB[(size_t)j * D * D + i];
+            for (int i = 0; i < D * D; ++i) aB[i] = p.auxB[(size_t)jj * D * D + i];
 #pragma unroll
-            for (int i = 0; i < D; ++i) abeta[i] = p.auxbeta[(size_t)j * D + i];
+            for (int i = 0; i < D; ++i) abeta[i] = p.auxbeta[(size_t)jj * D + i];
         }
         if constexpr (!MD::CONST_SIGMA) {
 #pragma unroll
-            for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)j * D * D + i];
+            for (int i = 0; i < D * D; ++i) aatil[i] = p.auxatil[(size_t)jj * D * D + i];
         }
-        const double rho = MODE != MODE_IMPUTE ? 1.0 : p.rho[j], lam = MODE != MODE_IMPUTE ? 0.0 : sqrt(1.0 - rho * rho);
-        const double *Xa = p.X[sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];      // accepted record
-        double *Xp = p.X[1 - sx] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];        // proposal record
-        const double *Wa = p.W[sw];
-        double *Wp = p.W[1 - sw];
-        xp_end = Xp + (size_t)(N - 1) * D;
-        const size_t wtile0 = (size_t)p.iv_tile_off[j];
+        rho = MODE != MODE_IMPUTE ? 1.0 : p.rho[jj];
+        lam = MODE != MODE_IMPUTE ? 0.0 : sqrt(1.0 - rho * rho);
+        Xa = p.X[sx] + p.iv_xoff[jj] + (size_t)chain * p.iv_xs[jj];      // accepted record
+        Xp = p.X[1 - sx] + p.iv_xoff[jj] + (size_t)chain * p.iv_xs[jj];  // proposal record
+        Wa = p.W[sw];
+        Wp = p.W[1 - sw];
+        wtile0 = (size_t)p.iv_tile_off[jj];
+    };
+    for (int j = i1; j <= i2; ++j) {
+        const int N = p.iv_N[j], nt = (N + CT - 1) / CT;
+        load_iv(j);
+        // whole short intervals j .. j + ns - 1 in one tile (lanes bnd[g] .. bnd[g + 1] - 1 work on interval j + g)
+        int ns = 1, bnd[MS + 1];
+        bnd[0] = 0; bnd[1] = min(CT, N);
+        if constexpr (MS > 1) {
+            if (N <= CT) ns = fit_intervals<MS>(p, j, i2, N, bnd);
+        }
 
         for (int tl = 0; tl < nt; ++tl, ++q) {
             cta_sync();  // every warp is done with its previous tile: that table stage and staging buffer are free
@@ -189,9 +243,25 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             mbar_wait(&full[q & (TD - 1)], (uint32_t)((q / TD) & 1));
             const double *srec = stab + (size_t)(q & (TD - 1)) * CT * RS;
             double *sdw = sdw0 + (SPLIT ? (q & 1) * CT * SW : 0);
-            const int k = tl * CT + lane;  // this lane's Euler step in phase P
-            const int nlive = min(CT, N - tl * CT);
+            // this lane's interval and Euler step in phase P
+            const bool multi = MS > 1 && ns > 1;
+            int gl = 0;
+            if constexpr (MS > 1) {
+                if (multi) {
+#pragma unroll
+                    for (int i = 1; i < MS; ++i) gl += (i < ns && lane >= bnd[i]) ? 1 : 0;
+                    if (gl > 0) load_iv(j + gl);  // the lanes of the first interval hold its context already
+                }
+            }
+            int lane0 = 0;  // first lane of this lane's interval
+            if constexpr (MS > 1) {
+#pragma unroll
+                for (int i = 1; i < MS; ++i) lane0 = (multi && i < ns && lane >= bnd[i]) ? bnd[i] : lane0;
+            }
+            const int k = multi ? lane - lane0 : tl * CT + lane;
+            const int nlive = multi ? bnd[ns] : min(CT, N - tl * CT);
             const bool live = lane < nlive;
+            double *const Xp_l = Xp;  // phase S walks the intervals one after another: the tile's states go out from here
 
             // ================= phase P: lane = step =================
             if (do_P) {
@@ -257,7 +327,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                     if constexpr (MODE != MODE_IMPUTE) {
                         z[w] = 0.0;
                     } else if constexpr (PHILOX) {
-                        z[w] = philox_normal1f(pkeys, p.iter, (uint32_t)(j + p.interval_offset), gchain, (uint32_t)w, (uint32_t)k);
+                        z[w] = philox_normal1f(pkeys, p.iter, (uint32_t)(j + gl + p.interval_offset), gchain, (uint32_t)w, (uint32_t)k);
                     } else {
                         z[w] = live ? p.Z[w_off(wtile0 + (size_t)(k >> 3), chain, w, p.C, M) + (k & 7)] : 0.0;
                     }
@@ -330,8 +400,52 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             [[maybe_unused]] double rec1[AHEAD == 2 ? NREC : 1], sv1[AHEAD == 2 ? SW : 1];
             load_ops(0, rec, sv);
             if constexpr (AHEAD == 2) load_ops(1, rec1, sv1);
+            int s_beg = 0;
+            // aux law of the interval the recursion walks (uniform); the next interval's is fetched while this one runs
+            [[maybe_unused]] double aBn[FAST ? 2 : D * D], abn[FAST ? 1 : D], aan[MD::CONST_SIGMA ? 1 : D * D];
+            auto fetch_aux = [&](int jj) {
+                if constexpr (FAST) {
+                    aBn[0] = p.auxB[(size_t)jj * D * D];
+                    aBn[1] = p.auxbeta[(size_t)jj * D];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) aBn[i] = p.auxB[(size_t)jj * D * D + i];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) abn[i] = p.auxbeta[(size_t)jj * D + i];
+                }
+                if constexpr (!MD::CONST_SIGMA) {
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) aan[i] = p.auxatil[(size_t)jj * D * D + i];
+                }
+            };
+            auto take_aux = [&]() {
+                if constexpr (FAST) {
+                    fk.aB0 = aBn[0];
+                    fk.c2 = aBn[1] - fk.s * fk.ie;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) aB[i] = aBn[i];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) abeta[i] = abn[i];
+                }
+                if constexpr (!MD::CONST_SIGMA) {
+#pragma unroll
+                    for (int i = 0; i < D * D; ++i) aatil[i] = aan[i];
+                }
+            };
+            if constexpr (MS > 1) {
+                if (multi) fetch_aux(j);
+            }
+            for (int gs = 0; gs < (multi ? ns : 1); ++gs) {
+            if constexpr (MS > 1) {
+                if (multi) {
+                    take_aux();
+                    if (gs + 1 < ns) fetch_aux(j + gs + 1);
+                }
+            }
+            const int s_end = multi ? s_beg + p.iv_N[j + gs] : nlive;
 #pragma unroll 4
-            for (int s = 0; s < nlive; ++s) {
+            for (int s = s_beg; s < s_end; ++s) {
                 double recn[NREC], svn[SW];
                 load_ops(min(s + AHEAD, CT - 1), recn, svn);
                 if constexpr (FAST) {
@@ -370,9 +484,11 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                         asm volatile("st.shared.f64 [%0], %1;" ::"r"(sxk_a + (uint32_t)(s * D + c) * 8u), "d"(x[c]));
                 }
             }
+            s_beg = s_end;
+            }
             __syncwarp();
-            if (live && active) {  // the tile's states: one coalesced store
-                double *dst = Xp + (size_t)k * D;
+            if (live && active) {  // the tile's states: one coalesced store (per interval)
+                double *dst = Xp_l + (size_t)k * D;
                 if constexpr (D == 2) {
                     const double2 v = *reinterpret_cast<const double2 *>(sxk + lane * D);
                     st_v2(dst, v.x, v.y);
@@ -382,6 +498,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                 }
             }
         }
+        j += ns - 1;  // the tile has dealt with ns whole intervals
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if constexpr (SPLIT) {
@@ -398,6 +515,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
         return;
     }
     if (pinned && active && lane == 0) {  // pin the proposal's last point to x_b (glued paths stay continuous)
+        xp_end = p.X[1 - p.selX_in[(size_t)i2 * p.C + chain]] + p.iv_xoff[i2] + (size_t)chain * p.iv_xs[i2] + (size_t)(p.iv_N[i2] - 1) * D;
 #pragma unroll
         for (int c = 0; c < D; ++c) xp_end[c] = xb[c];
     }
@@ -438,15 +556,15 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     }
 }
 
-template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE>
-static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE, int MS>
+static cudaError_t launch_coop_ms(const SolveParams &p, cudaStream_t s) {
     constexpr int RS = Rec<MD::D, PSI>::SIZE;
     constexpr int TD = SPLIT ? 4 : 2, NB = SPLIT ? 2 : 1, SW = FAST ? 4 : MD::M + 2;
     const int wpc = std::min(4, (int)p.C);  // units of one block (consecutive chains) share the table stage
     const unsigned groups = (unsigned)((p.C + wpc - 1) / wpc);
     const unsigned grid = groups * (unsigned)p.nblk;
     const size_t smem = sizeof(double) * ((size_t)TD * CT * RS + (size_t)wpc * CT * (NB * SW + MD::D));
-    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE>;
+    auto kern = solve_coop_kernel<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE, MS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -464,6 +582,15 @@ static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+// short intervals (fewer than 16 Euler steps on average): up to four whole intervals per tile
+template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE>
+static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
+    static const int env_ms = getenv("DMCMC_COOP_MULTI") ? atoi(getenv("DMCMC_COOP_MULTI")) : -1;  // A/B override
+    const bool multi = env_ms >= 0 ? env_ms != 0 : p.mean_N <= 16;
+    return multi ? launch_coop_ms<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE, 4>(p, s)
+                 : launch_coop_ms<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE, 1>(p, s);
 }
 
 template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, int MODE = MODE_IMPUTE>
