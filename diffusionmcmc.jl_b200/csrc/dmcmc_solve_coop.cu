@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     const bool do_P = !SPLIT || warp_raw >= wpc, do_S = !SPLIT || warp_raw < wpc;  // producer / solver role of this warp
     const int warp = SPLIT && warp_raw >= wpc ? warp_raw - wpc : warp_raw;          // unit of the CTA
     double *stab = dsm;                                              // [TD][CT][RS]  table records of a tile
-    constexpr int SW = FAST ? 4 : M + 2;  // per step: mixed increments (FAST: e_k, R_k), two factors of the accepted G dt
+    // per step: mixed increments (FAST: e_k, R_k), two factors of the accepted G dt, and (generic) the guiding offset
+    // F = F0 + Psi x_b, which does not depend on the proposal state: phase P computes it lane-parallel, so that the serial
+    // phase neither multiplies by Psi nor loads it (the same arithmetic on the same inputs: bit-identical)
+    constexpr int SW = FAST ? 4 : M + 2 + D;
     double *sdw0 = dsm + TD * CT * RS + (size_t)warp * CT * (NB * SW + D);  // [NB][CT][SW]
     double *sxk = sdw0 + NB * CT * SW;                                       // [CT][D]   the tile's proposal states
     auto cta_sync = [&]() {
@@ -364,6 +367,13 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
 #pragma unroll
                     for (int w = 0; w < M; ++w) sdw[lane * SW + w] = dw[w];
                     if constexpr (REINV) { sdw[lane * SW + M] = ga; sdw[lane * SW + M + 1] = gb; }
+                    if constexpr (!ACC_ONLY) {
+                        double recf[RS], Fl[D];
+                        load_rec_smem<RS>(rp, recf);
+                        guiding_F<D, PSI>(recf, xb, Fl);
+#pragma unroll
+                        for (int c = 0; c < D; ++c) sdw[lane * SW + M + 2 + c] = Fl[c];
+                    }
                 }
             }
             if constexpr (!SPLIT) __syncwarp();
@@ -379,7 +389,8 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             // shared-memory loads are never moved above a shared store whose address they might alias, so in source
             // order their ~30-cycle latency would sit in the recurrence of every step.
             const uint32_t sxk_a = smem_u32(sxk);
-            constexpr int NREC = FAST ? 6 : RS;  // FAST: A1, B1, dt H11, dt H12, dt/eps, (sqrt dt) is all the recursion reads
+            // FAST: A1, B1, dt H11, dt H12, dt/eps, (sqrt dt) is all the recursion reads; generic: dt, sqrt dt and H
+            constexpr int NREC = FAST ? 6 : ((R::OFF_F + 1) & ~1);
             double rec[NREC], sv[SW];
             auto load_ops = [&](int s, double *r, double *v) {
                 load_rec_smem<NREC>(srec + s * RS, r);
@@ -454,7 +465,8 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
                 } else {
                     if constexpr (REINV) lsum_a = fma(sv[M], sv[M + 1], lsum_a);
                     double F[D], dr[D], sdwv[D], gg;
-                    guiding_F<D, PSI>(rec, xb, F);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) F[c] = sv[M + 2 + c];
                     guided_terms<MD, PSI>(p.th, rec, F, aB, abeta, aatil, x, rec[0], dr, gg);
                     lsum = fma(gg, rec[0], lsum);
                     MD::sigma_mul(p.th, x, sv, sdwv);
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
 template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE, int MS>
 static cudaError_t launch_coop_ms(const SolveParams &p, cudaStream_t s) {
     constexpr int RS = Rec<MD::D, PSI>::SIZE;
-    constexpr int TD = SPLIT ? 4 : 2, NB = SPLIT ? 2 : 1, SW = FAST ? 4 : MD::M + 2;
+    constexpr int TD = SPLIT ? 4 : 2, NB = SPLIT ? 2 : 1, SW = FAST ? 4 : MD::M + 2 + MD::D;
     const int wpc = std::min(4, (int)p.C);  // units of one block (consecutive chains) share the table stage
     const unsigned groups = (unsigned)((p.C + wpc - 1) / wpc);
     const unsigned grid = groups * (unsigned)p.nblk;
