@@ -599,7 +599,8 @@ static cudaError_t launch_coop_ms(const SolveParams &p, cudaStream_t s) {
 // short intervals (fewer than 16 Euler steps on average): up to four whole intervals per tile
 template <class MD, bool PSI, bool PHILOX, bool REINV, bool FAST, bool SPLIT, int MODE>
 static cudaError_t launch_coop_split(const SolveParams &p, cudaStream_t s) {
-    static const int env_ms = getenv("DMCMC_COOP_MULTI") ? atoi(getenv("DMCMC_COOP_MULTI")) : -1;  // A/B override
+    const char *env = getenv("DMCMC_COOP_MULTI");  // A/B override, read per launch (the tests switch it)
+    const int env_ms = env ? atoi(env) : -1;
     const bool multi = env_ms >= 0 ? env_ms != 0 : p.mean_N <= 16;
     return multi ? launch_coop_ms<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE, 4>(p, s)
                  : launch_coop_ms<MD, PSI, PHILOX, REINV, FAST, SPLIT, MODE, 1>(p, s);

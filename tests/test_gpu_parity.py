@@ -452,3 +452,34 @@ def test_warp_per_unit_kernel_is_bit_identical(pkg, monkeypatch, name, kw, half)
                                            "parameter-step X", "W after a layout switch")):
         assert np.array_equal(a, b), f"{what} differs between the two imputation kernels"
 
+
+
+@pytest.mark.parametrize("name,kw,half", [("l63", dict(n_obs=40, C=3, dt=1e-3), 3), ("lv", dict(n_obs=24, C=2, dt=0.01), 2),
+                                          ("fhn", dict(n_obs=30, C=2, dt=0.01), 5), ("lvm", dict(n_obs=12, C=4, dt=0.01), 1)])
+def test_tiles_of_several_short_intervals_are_bit_identical(pkg, monkeypatch, name, kw, half):
+    """Warp-per-unit kernel: a tile may hold up to four WHOLE short intervals (lanes of one tile then work on different
+    intervals; phase S walks them one after another).  Forced on and off (DMCMC_COOP_MULTI) it must never change a
+    sample: fused layout-switch sweeps, parameter-step solve, layout switch -- 10 Euler steps per interval, so three
+    intervals share a tile, blocks of 2-10 intervals."""
+    from diffusionmcmc_jl_b200.engine import Engine
+    spec = _mk(pkg, name, **kw)
+    assert max(spec["N"]) <= 16
+    monkeypatch.setenv("DMCMC_COOP", "1")
+    out = []
+    for multi in ("0", "1"):
+        monkeypatch.setenv("DMCMC_COOP_MULTI", multi)
+        e = Engine(spec, seed=21)
+        e.init_paths()
+        e.run_sweeps(0, 4, half)
+        X, W = e.download_state(0)
+        th = np.array(spec["theta"], float)
+        llp, ok = e.param_loglik(th * (1 + 1e-3), critical=True)
+        Xp, _ = e.download_state(1)
+        e.param_commit(False)
+        e.relayout(*pkg.problems.chequerboard_layout(e.rec_nobs, max(half - 1, 1), 1))
+        _, Wr = e.download_state(0)
+        out.append((X, W, e.get_ll().copy(), e.accept_counts()[0].copy(), llp, ok, Xp, Wr))
+        e.close()
+    for a, b, what in zip(out[0], out[1], ("X", "W", "ll", "accept counts", "parameter-step ll", "parameter-step success",
+                                           "parameter-step X", "W after a layout switch")):
+        assert np.array_equal(a, b), f"{what} differs between one interval per tile and several"
