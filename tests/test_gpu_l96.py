@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True, params=["auto_cta", "8_warps_per_cta"])
 def l96_mapping(request, monkeypatch):
     """Every Lorenz-96 test runs with the launcher's own CTA size (one or two warps for these chain counts) and with
-    eight warps per CTA (BASELINE C5's shape: the warps of a CTA share the table stages, the last one to finish with a
-    stage refills it; surplus warps shadow the last chain)."""
+    eight warps per CTA (BASELINE C5's shape: the warps of a CTA share the table stages behind full / empty mbarriers,
+    warp 0 refills a stage once every warp has released it; surplus warps shadow the last chain)."""
     if request.param == "8_warps_per_cta":
         monkeypatch.setenv("DMCMC_L96_WARPS", "8")
     else:
