@@ -366,7 +366,13 @@ def config_c4(pkg, K, W, local_rank, rank, world):
     dt_nccl = timed_iterations(0)
     p2p_on = os.environ.get("DMCMC_P2P", "1") != "0" and s.engine.comm_enable_p2p((s.h + 1) * s.N_max * s.engine.d * 8 * s.engine.C)
     halo.p2p = p2p_on
-    dt = timed_iterations(1000) if p2p_on else dt_nccl
+    halo.fused = False
+    dt_p2p = timed_iterations(1000) if p2p_on else dt_nccl
+    # third: the same stores and flags from inside the sweep kernels (dmcmc_impute_exchange_async)
+    fused_on = p2p_on and os.environ.get("DMCMC_P2P_FUSE", "1") != "0"
+    halo.fused = fused_on
+    dt = timed_iterations(2000) if fused_on else dt_p2p
+    halo.fused = False   # the part timings below call the exchange and the sweeps on their own
     # what the two parts cost on their own: the exchanges alone (same messages, nothing computed in between) and the
     # sweeps alone (no exchange; the halo goes stale, which does not change the work)
     e = s.engine
@@ -394,17 +400,20 @@ def config_c4(pkg, K, W, local_rank, rank, world):
     for i in range(20):
         halo.param_step(th * (1 + 1e-4 * (i + 2)), lambda llp, ll, ok: False)
     dtp = (time.perf_counter() - t1) / 20
-    tt = torch.tensor([dt, dtp, dt_x, dt_k, dt_nccl], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([dt, dtp, dt_x, dt_k, dt_nccl, dt_p2p], device="cuda", dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt, dtp, dt_x, dt_k, dt_nccl = (float(x) for x in tt)
+    dt, dtp, dt_x, dt_k, dt_nccl, dt_p2p = (float(x) for x in tt)
     out = {"workload": "C4: Lorenz-63 1 chain x 10^4 obs, chequerboard half_len=5, interval blocks sharded over the GPUs, "
                        "end-point / halo exchange after every sweep (inside the library)",
            "n_chains": 1, "n_obs": 10_000, "n_gpus": world, "scaling": "strong", "path_steps_per_sweep": steps,
            "value": 2 * steps * n / dt, "unit": UNIT, "ms_per_iteration": dt / n * 1e3,
            "parameter_step_ms": dtp * 1e3, "mcmc_iters_per_sec": 1.0 / (dt / n / 2 + dtp),
            "exchanges_alone_ms_per_iteration": dt_x * 1e3, "sweeps_alone_ms_per_iteration": dt_k * 1e3,
-           "halo": "peer memory (CUDA IPC mailboxes, NVLink stores + flags from the pack / unpack kernels)" if p2p_on else "ncclSend / ncclRecv",
+           "halo": ("peer memory, fused into the sweep kernels (the edge block's warps push after their accept decision and pull "
+                    "before they read)" if fused_on else
+                    "peer memory (CUDA IPC mailboxes, NVLink stores + flags from the exchange kernel)" if p2p_on else "ncclSend / ncclRecv"),
            "ms_per_iteration_with_nccl_halo": dt_nccl / n * 1e3,
+           "ms_per_iteration_with_peer_memory_halo_in_its_own_kernel": dt_p2p / n * 1e3,
            "what": "one imputation iteration = sweep A + exchange + sweep B + exchange; wall clock, MAX over ranks; parameter "
                    "step = relayout + backward filter + fixed-noise solve + all-reduce of per-block ll deg + commit; "
                    "mcmc_iters_per_sec counts one sweep + one parameter step per iteration like the N=1 entry"}

@@ -72,6 +72,7 @@ SYMBOLS = {
     "dmcmc_comm_destroy": (C.c_int, [C.c_void_p]),
     "dmcmc_halo_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmcmc_comm_enable_p2p": (C.c_int, [C.c_void_p, C.c_int64]),
+    "dmcmc_impute_exchange_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dmcmc_comm_p2p_enabled": (C.c_int, [C.c_void_p]),
     "dmcmc_param_loglik_sharded": (C.c_int, [C.c_void_p, _dp, C.c_int32, C.c_int32, C.c_int32, _ip, _dp, _dp, _bp]),
     "dmcmc_conjugate_dim": (C.c_int32, [C.c_void_p, _ip]),

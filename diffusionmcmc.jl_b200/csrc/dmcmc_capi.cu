@@ -182,8 +182,19 @@ struct dmcmc_ctx {
     unsigned long long p2p_sent[2] = {0, 0}, p2p_recvd[2] = {0, 0};   // per direction (0: leftwards, 1: rightwards)
     unsigned int *p2p_counter = nullptr;       // device: [4] CTA counters (push / pull per direction)
     int *p2p_err = nullptr, *p2p_err_dev = nullptr;  // host-mapped time-out flag
+    // exchange fused into the sweeps (dmcmc_impute_exchange_async): a message the neighbour pushes at the end of ITS sweep
+    // is taken out of my mailbox by my next fused sweep, or by flush_pending_pull before anything else touches the paths
+    bool pull_pending = false;
+    int pull_dir = 0, pull_j0 = 0, pull_j1 = 0;
+    size_t pull_lead = 0;
+    HaloFuse hf_next{};        // what the next imputation launch fuses (blk < 0: nothing)
+    bool hf_armed = false;
     DevBuf<int32_t> d_gl_ok, d_gidx;
 };
+
+// a message pushed by the neighbour's fused sweep waits in my mailbox: take it out (stand-alone kernel) before anything
+// but my own next fused sweep reads or writes the path containers
+static int flush_pending_pull(dmcmc_ctx *ctx);
 
 namespace {
 
@@ -403,6 +414,7 @@ int fill_params(dmcmc_ctx *ctx, SolveParams &sp, int slot) {
     if (!tb.valid && run_backward_filter(ctx, slot)) return -1;  // tables follow the layout lazily
     Law &law = ctx->law[slot];
     sp = SolveParams{};
+    sp.hf.blk = -1;
     sp.C = ctx->C; sp.nblk = lay.nblk; sp.J = ctx->J; sp.D = ctx->d; sp.chain_offset = ctx->cfg.chain_offset;
     sp.interval_offset = ctx->cfg.interval_offset;
     sp.blk_active = lay.has_mask ? lay.d_active.p : nullptr;
@@ -460,7 +472,15 @@ int timed_launch(dmcmc_ctx *ctx, int mode, const SolveParams &sp) {
         ctx->ev_used += 2;
         CK(cudaEventRecord(e0, ctx->stream));
     }
-    CK(launch_solve(ctx->cfg.model, mode, sp, ctx->threads, ctx->stream));
+    if (ctx->hf_armed && mode == MODE_IMPUTE) {  // dmcmc_impute_exchange_async: this launch carries the exchange
+        SolveParams spf = sp;
+        spf.hf = ctx->hf_next;
+        ctx->hf_armed = false;
+        CK(launch_solve(ctx->cfg.model, mode, spf, ctx->threads, ctx->stream));
+    } else {
+        if (flush_pending_pull(ctx)) return -1;
+        CK(launch_solve(ctx->cfg.model, mode, sp, ctx->threads, ctx->stream));
+    }
     if (timed) CK(cudaEventRecord(e1, ctx->stream));
     return 0;
 }
@@ -647,6 +667,7 @@ static void p2p_release(dmcmc_ctx *ctx) {
     if (ctx->p2p_err) cudaFreeHost(ctx->p2p_err);
     ctx->p2p_region = nullptr; ctx->p2p_counter = nullptr; ctx->p2p_err = nullptr; ctx->p2p_err_dev = nullptr;
     ctx->p2p_on = false; ctx->p2p_cap = 0;
+    ctx->pull_pending = false; ctx->hf_armed = false;
     ctx->p2p_sent[0] = ctx->p2p_sent[1] = ctx->p2p_recvd[0] = ctx->p2p_recvd[1] = 0;
 }
 
@@ -959,6 +980,7 @@ static int segment_copy(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *X, bool 
     g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
     g.selX = ctx->d_selX[ctx->sel_cur].p;
     g.packed = pk.p; g.upload = up; g.pk_stride = (int64_t)steps * ctx->d; g.c0 = c0; g.nc = nc;
+    if (flush_pending_pull(ctx)) return -1;  // a fused exchange's message may still sit in the mailbox
     CK(launch_segment(g, ctx->stream));
     if (!up) CK(cudaMemcpyAsync(X, pk.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (sync(ctx)) return -1;
@@ -982,6 +1004,7 @@ int dmcmc_segment_device(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *dev, in
     g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
     g.selX = ctx->d_selX[ctx->sel_cur].p;
     g.packed = dev; g.upload = upload_; g.pk_stride = chain_stride;
+    if (flush_pending_pull(ctx)) return -1;  // a fused exchange's message may still sit in the mailbox
     CK(launch_segment(g, ctx->stream));
     if (upload_) ctx->w_valid = false;
     return 0;
@@ -991,6 +1014,7 @@ int dmcmc_segment_device(dmcmc_ctx *ctx, int32_t j0, int32_t j1, double *dev, in
 int dmcmc_set_start_device(dmcmc_ctx *ctx, const double *dev, int64_t chain_stride) {
     REQUIRE(ctx && dev && ctx->have_start, "dmcmc_set_start_device: context not initialised");
     CK(cudaSetDevice(ctx->cfg.device));
+    if (flush_pending_pull(ctx)) return -1;  // a fused exchange's message may still sit in the mailbox
     CK(launch_set_start(ctx->d_x0.p, dev, chain_stride, ctx->C, ctx->R, ctx->d, ctx->stream));
     ctx->w_valid = false;
     return 0;
@@ -1589,6 +1613,7 @@ int dmcmc_download_state(dmcmc_ctx *ctx, int32_t which, double *X, double *W) {
     for (int b = 0; b < 2; ++b) { g.X[b] = ctx->d_X[b].p; g.W[b] = ctx->d_W[b].p; }
     g.selX = ctx->d_selX[ctx->sel_cur].p; g.selW = ctx->d_selW[ctx->sel_cur].p;
     g.x0 = ctx->d_x0.p; g.which = which; g.outX = oX.p; g.outW = oW.p;
+    if (flush_pending_pull(ctx)) return -1;  // a fused exchange's message may still sit in the mailbox
     CK(launch_gather(g, ctx->stream));
     CK(cudaMemcpyAsync(X, oX.p, nX * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(W, oW.p, nW * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1657,6 +1682,7 @@ int dmcmc_save_path_async(dmcmc_ctx *ctx, int32_t n_sel, const int32_t *chains, 
         g.X[0] = ctx->d_X[0].p; g.X[1] = ctx->d_X[1].p;
         g.selX = ctx->d_selX[ctx->sel_cur].p;
         g.packed = sv.d_buf.p + per * i + d; g.upload = 0; g.pk_stride = (int64_t)per; g.c0 = chains[i]; g.nc = 1;
+        if (flush_pending_pull(ctx)) return -1;  // a fused exchange's message may still sit in the mailbox
         CK(launch_segment(g, ctx->stream));
         // starting point x0[(rec * d + c) * C + chain] -> first d doubles of the glued path
         CK(cudaMemcpy2DAsync(sv.d_buf.p + per * i, sizeof(double), ctx->d_x0.p + (size_t)rec * d * ctx->C + chains[i],
@@ -1785,6 +1811,7 @@ extern "C" int dmcmc_conjugate_sums(dmcmc_ctx *ctx, double *mu, double *W) {
     c.selX = ctx->d_selX[ctx->sel_cur].p;
     c.x0 = ctx->d_x0.p; c.partial = partial.p;
     for (int i = 0; i < DMCMC_MAX_THETA; ++i) c.th.v[i] = ctx->law[ctx->law_cur].theta[i];
+    if (flush_pending_pull(ctx)) return -1;  // a fused exchange's message may still sit in the mailbox
     CK(launch_conjugate(ctx->cfg.model, c, out.p, ctx->stream));
     std::vector<double> h((size_t)ctx->C * nout);
     CK(cudaMemcpyAsync(h.data(), out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1963,6 +1990,7 @@ extern "C" int dmcmc_comm_init(dmcmc_ctx *ctx, const void *id128, int32_t rank, 
 extern "C" int dmcmc_comm_destroy(dmcmc_ctx *ctx) {
     REQUIRE(ctx, "dmcmc_comm_destroy: null context");
     CK(cudaSetDevice(ctx->cfg.device));
+    if (flush_pending_pull(ctx)) return -1;
     if (sync(ctx)) return -1;
     comm_release(ctx);
     ctx->comm_rank = 0;
@@ -2083,6 +2111,104 @@ static int halo_p2p(dmcmc_ctx *ctx, int dir, bool send, int sj0, int sj1, bool r
     return 0;
 }
 
+namespace {
+struct P2PAddr {
+    dmcmc_ctx *c;
+    unsigned long long *data_seq(char *region, int d) const { return reinterpret_cast<unsigned long long *>(region) + d; }
+    unsigned long long *ack_seq(char *region, int d) const { return reinterpret_cast<unsigned long long *>(region) + 2 + d; }
+    double *mailbox(char *region, int d) const { return reinterpret_cast<double *>(region + 256 + (size_t)d * c->p2p_cap); }
+};
+}  // namespace
+
+static int flush_pending_pull(dmcmc_ctx *ctx) {
+    if (!ctx->pull_pending) return 0;
+    const int dir = ctx->pull_dir;
+    ctx->pull_pending = false;
+    return halo_p2p(ctx, dir, false, 0, 0, true, ctx->pull_j0, ctx->pull_j1, ctx->pull_lead);
+}
+
+// One imputation sweep (Philox noise, current layout and block mask, enqueued like dmcmc_impute_async) WITH the end-point
+// exchange that follows it under `pattern` (the arguments of dmcmc_halo_exchange) fused into the sweep kernels: the edge
+// block's units push their accepted intervals into the neighbour's mailbox right after their accept decision, and the
+// neighbour's next fused sweep (or the first other call that touches the paths) takes them out.  Needs
+// dmcmc_comm_enable_p2p and a launch small enough for the warp-per-unit kernel; otherwise it is dmcmc_impute_async
+// followed by dmcmc_halo_exchange.  Results are identical either way.
+extern "C" int dmcmc_impute_exchange_async(dmcmc_ctx *ctx, uint32_t iter, int32_t pattern, int32_t n_first, int32_t n_halo,
+                                           int32_t left_edge_steps) {
+    REQUIRE(ctx && ctx->comm, "dmcmc_impute_exchange_async: call dmcmc_comm_init first");
+    REQUIRE(pattern == 0 || pattern == 1, "dmcmc_impute_exchange_async: pattern is 0 or 1");
+    REQUIRE(ctx->R == 1 && ctx->lay_cur >= 0, "dmcmc_impute_exchange_async: one recording, layout set");
+    const int r = ctx->comm_rank, w = ctx->comm_world, J = ctx->J, d = ctx->d;
+    REQUIRE(n_first > 0 && n_first <= J - n_halo && n_halo >= 0 && n_halo < J, "dmcmc_impute_exchange_async: bad interval counts");
+    const int n_own = J - n_halo;
+    const size_t C = (size_t)ctx->C;
+    // the messages of this pattern's exchange (as in dmcmc_halo_exchange)
+    int sj0, sj1, rj0, rj1;
+    size_t lead = 0;
+    bool send, recv;
+    if (pattern == 0) { send = r > 0; sj0 = 0; sj1 = n_first; recv = r < w - 1; rj0 = n_own; rj1 = J; }
+    else { send = r < w - 1; sj0 = n_own - 1; sj1 = J; recv = r > 0; rj0 = 0; rj1 = n_first; lead = (size_t)left_edge_steps * d; }
+    const size_t send_b = send ? C * (size_t)(ctx->st_off[sj1] - ctx->st_off[sj0]) * d * sizeof(double) : 0;
+    const size_t recv_b = recv ? C * ((size_t)(ctx->st_off[rj1] - ctx->st_off[rj0]) * d + lead) * sizeof(double) : 0;
+    Layout &lay = ctx->layout[ctx->lay_cur];
+    SolveParams probe{};
+    probe.C = ctx->C; probe.nblk = lay.nblk; probe.coop = ctx->coop;
+    const bool fuse = ctx->p2p_on && send_b <= ctx->p2p_cap && recv_b <= ctx->p2p_cap &&
+                      solve_uses_warp_per_unit(ctx->cfg.model, probe) && (pattern == 0 || left_edge_steps > 0 || r == 0) &&
+                      sj1 - sj0 <= 32 && rj1 - rj0 <= 32;  // a warp maps one interval of the message per lane
+    if (!fuse) {
+        if (dmcmc_impute_async(ctx, iter)) return -1;
+        return dmcmc_halo_exchange(ctx, pattern, n_first, n_halo, left_edge_steps);
+    }
+    REQUIRE(*ctx->p2p_err == 0, "dmcmc_impute_exchange_async: a wait on the neighbouring GPU timed out (peer gone?)");
+    // the block both messages belong to: the one that holds interval 0 (pattern 0) or the last interval (pattern 1)
+    const int target = pattern == 0 ? 0 : J - 1;
+    int eb = -1;
+    for (int b = 0; b < lay.nblk; ++b)
+        if (lay.i1[b] <= target && target <= lay.i2[b]) eb = b;
+    REQUIRE(eb >= 0, "dmcmc_impute_exchange_async: no block holds the edge interval");
+    // a pending message is this sweep's to take out only if it was sent under the OTHER pattern (it feeds the same block)
+    if (ctx->pull_pending && ctx->pull_dir == pattern) { if (flush_pending_pull(ctx)) return -1; }
+    const P2PAddr A{ctx};
+    char *mine = ctx->p2p_region;
+    HaloFuse h{};
+    h.blk = eb;
+    h.iv_st_off = ctx->d_st_off.p;
+    h.err = ctx->p2p_err_dev;
+    if (ctx->pull_pending) {
+        const int pd = ctx->pull_dir;                       // == 1 - pattern
+        char *sender = ctx->p2p_peer[pd == 0 ? 1 : 0];
+        REQUIRE(lay.i1[eb] <= ctx->pull_j0 && ctx->pull_j1 - 1 <= lay.i2[eb], "dmcmc_impute_exchange_async: the pending message is not the edge block's");
+        h.pull_box = A.mailbox(mine, pd);
+        h.pull_j0 = ctx->pull_j0; h.pull_j1 = ctx->pull_j1; h.pull_lead = (int32_t)ctx->pull_lead;
+        h.pull_stride = (int64_t)ctx->pull_lead + (int64_t)(ctx->st_off[ctx->pull_j1] - ctx->st_off[ctx->pull_j0]) * d;
+        h.pull_flag = A.data_seq(mine, pd); h.pull_val = ctx->p2p_recvd[pd] + 1;
+        h.pull_ack = A.ack_seq(sender, pd); h.pull_counter = ctx->p2p_counter + 2 + pd;
+        ++ctx->p2p_recvd[pd];
+        ctx->pull_pending = false;
+        ctx->w_valid = false;
+    }
+    if (send) {
+        REQUIRE(lay.i1[eb] <= sj0 && sj1 - 1 <= lay.i2[eb], "dmcmc_impute_exchange_async: the message is not the edge block's");
+        char *peer = ctx->p2p_peer[pattern == 0 ? 0 : 1];
+        h.push_box = A.mailbox(peer, pattern);
+        h.push_j0 = sj0; h.push_j1 = sj1;
+        h.push_stride = (int64_t)(ctx->st_off[sj1] - ctx->st_off[sj0]) * d;
+        h.push_wait = A.ack_seq(mine, pattern); h.push_wait_val = ctx->p2p_sent[pattern];
+        h.push_flag = A.data_seq(peer, pattern); h.push_val = ctx->p2p_sent[pattern] + 1;
+        h.push_counter = ctx->p2p_counter + pattern;
+        ++ctx->p2p_sent[pattern];
+    }
+    ctx->hf_next = h;
+    ctx->hf_armed = true;
+    if (dmcmc_impute_async(ctx, iter)) { ctx->hf_armed = false; return -1; }
+    if (recv) {  // my neighbour pushes at the end of its sweep: mine to take out next
+        ctx->pull_pending = true;
+        ctx->pull_dir = pattern; ctx->pull_j0 = rj0; ctx->pull_j1 = rj1; ctx->pull_lead = lead;
+    }
+    return 0;
+}
+
 static int seg_on_stream(dmcmc_ctx *ctx, int j0, int j1, double *dev, int64_t stride, int up) {
     const int steps = ctx->st_off[j1] - ctx->st_off[j0];
     SegmentParams g{};
@@ -2112,6 +2238,7 @@ extern "C" int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_
     REQUIRE(n_first > 0 && n_first <= J - n_halo && n_halo >= 0 && n_halo < J, "dmcmc_halo_exchange: bad interval counts");
     REQUIRE((r < w - 1) == (n_halo > 0) || w == 1, "dmcmc_halo_exchange: every rank but the last holds a halo");
     CK(cudaSetDevice(ctx->cfg.device));
+    if (flush_pending_pull(ctx)) return -1;
     std::string err;
     NcclApi *nc = nccl_api(err);
     REQUIRE(nc, "dmcmc_halo_exchange: " + err);

@@ -14,6 +14,34 @@ enum SolveMode {
     MODE_LOGLIK = 3     // init_ll!: ll of the accepted path only
 };
 
+// End-point exchange of a block-sharded recording FUSED into the imputation sweep (warp-per-unit kernel, peer memory):
+// the units of the layout's edge block pull the neighbour's message out of this GPU's mailbox before they read anything,
+// and push their freshly accepted intervals into the neighbour's mailbox right after their accept decision -- no kernel
+// boundary and no separate pack / unpack pass between a sweep and its exchange (dmcmc_impute_exchange_async).
+struct HaloFuse {
+    int32_t blk;                       // the edge block under this sweep's layout; -1: nothing is fused
+    const int32_t *iv_st_off;          // [J + 1] cumulative Euler steps
+    // pull: own mailbox -> accepted containers of intervals [pull_j0, pull_j1) (+ starting point: the last D of the
+    // pull_lead doubles that precede them in every chain's slice)
+    const double *pull_box;            // nullptr: no pull
+    int32_t pull_j0, pull_j1, pull_lead;
+    int64_t pull_stride;
+    const unsigned long long *pull_flag;   // this GPU's memory, raised by the sender
+    unsigned long long pull_val;
+    unsigned long long *pull_ack;          // the sender's memory
+    unsigned int *pull_counter;
+    // push: accepted path of intervals [push_j0, push_j1) after this sweep -> the neighbour's mailbox
+    double *push_box;                  // nullptr: no push
+    int32_t push_j0, push_j1;
+    int64_t push_stride;
+    const unsigned long long *push_wait;   // this GPU's memory: the neighbour's acknowledgement of the previous message
+    unsigned long long push_wait_val;
+    unsigned long long *push_flag;         // the neighbour's memory
+    unsigned long long push_val;
+    unsigned int *push_counter;
+    int *err;                          // host-mapped: 1 when a wait timed out
+};
+
 // Everything a solve kernel needs.  Pointers are device pointers.
 struct SolveParams {
     int32_t C, nblk, J, D;
@@ -66,10 +94,12 @@ struct SolveParams {
     uint8_t *out_acc;             // [C][nblk]  (MODE_PARAM: per-unit success)
     unsigned long long *acc_count, *prop_count;  // [nblk]
     Theta th;
+    HaloFuse hf;        // hf.blk < 0 unless the launch is dmcmc_impute_exchange_async's (warp-per-unit kernel only)
 };
 
 // launchers (dmcmc_solve.cu); return the CUDA error of the launch
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s);
+bool solve_uses_warp_per_unit(int model, const SolveParams &p);  // the kernel launch_solve will pick for p
 cudaError_t launch_solve_big(int d, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_l96.cu
 cudaError_t launch_solve_coop(int model, int mode, const SolveParams &p, cudaStream_t s);  // dmcmc_solve_coop.cu (MODE_IMPUTE, MODE_PARAM)
 cudaError_t launch_fhn_derive(const double *raw, double *out, long long nrec, int has_psi, const Theta &th, cudaStream_t s);

@@ -602,11 +602,13 @@ static cudaError_t launch_psi(int mode, const SolveParams &p, int threads, cudaS
 // critical path; above it the cooperative kernel's 32 x redundant recursion costs more than it hides
 constexpr long long COOP_MAX_UNITS = 2048;  // measured crossover on B200: ~3000 units (FitzHugh-Nagumo fused step), ~4000 (Lorenz-63)
 
+bool solve_uses_warp_per_unit(int model, const SolveParams &p) {
+    const long long units = (long long)p.C * p.nblk;
+    return model != 3 && (p.coop > 0 || (p.coop < 0 && units <= COOP_MAX_UNITS));
+}
+
 cudaError_t launch_solve(int model, int mode, const SolveParams &p, int threads, cudaStream_t s) {
-    if (model != 3) {
-        const long long units = (long long)p.C * p.nblk;
-        if (p.coop > 0 || (p.coop < 0 && units <= COOP_MAX_UNITS)) return launch_solve_coop(model, mode, p, s);
-    }
+    if (solve_uses_warp_per_unit(model, p)) return launch_solve_coop(model, mode, p, s);
     switch (model) {
     case 0: return p.fast_ok ? launch_psi<ModelFHN, true>(mode, p, threads, s)
                              : launch_psi<ModelFHN, false>(mode, p, threads, s);

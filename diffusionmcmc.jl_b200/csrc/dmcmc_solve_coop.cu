@@ -30,6 +30,111 @@ constexpr int CT = 32;  // Euler steps per tile = lanes
 // accepted noise under the proposal law, no mix, no accept -- per-unit ll deg and success flag out.
 // MODE_RELAYOUT / MODE_LOGLIK: the accepted path only -- recover its noise (RELAYOUT: store it) and its ll under the
 // current layout (update_workspaces!, src/workspaces.jl:467-471; init_ll!, :425-431): phase P alone, plus the serial sum.
+// ---- end-point exchange fused into the sweep (HaloFuse, dmcmc_internal.h) --------------------------------------------
+__device__ __forceinline__ unsigned long long hf_ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void hf_st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void hf_spin(const unsigned long long *flag, unsigned long long val, int *err) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (hf_ld_acquire_sys(flag) < val) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (t - t0 > 3000000000ULL) { *err = 1; break; }  // a dead peer must not hang the GPU
+    }
+}
+// A message holds at most 32 intervals (half_len + 1): lane i keeps interval j0 + i's first step within the message and
+// the address of the chain's record in the container to use (sel_flip: the accept decision of the sweep just done), so
+// that every global load the copy depends on is issued once, in one round, before the data moves
+struct HfMap {
+    int off;          // first Euler step of this lane's interval within the message (INT_MAX beyond the message)
+    double *rec;      // the chain's record of this lane's interval in the accepted container
+};
+__device__ __forceinline__ HfMap hf_map(const SolveParams &p, int j0, int j1, int chain, int lane, int sel_flip) {
+    HfMap m;
+    m.off = 0x7fffffff;
+    m.rec = nullptr;
+    const int j = j0 + lane;
+    if (j < j1) {
+        m.off = p.hf.iv_st_off[j] - p.hf.iv_st_off[j0];
+        m.rec = p.X[p.selX_in[(size_t)j * p.C + chain] ^ sel_flip] + p.iv_xoff[j] + (size_t)chain * p.iv_xs[j];
+    }
+    return m;
+}
+// element e of the chain's slice -> its address in the containers (the owning lane's record, found by shuffles)
+__device__ __forceinline__ double *hf_addr(const HfMap &m, int nj, int e, int D) {
+    const int step = e / D, c = e - step * D;
+    int off = __shfl_sync(0xffffffffu, m.off, 0);
+    unsigned long long rec = __shfl_sync(0xffffffffu, (unsigned long long)m.rec, 0);
+    for (int i = 1; i < nj; ++i) {
+        const int oi = __shfl_sync(0xffffffffu, m.off, i);
+        const unsigned long long ri = __shfl_sync(0xffffffffu, (unsigned long long)m.rec, i);
+        if (oi <= step) { off = oi; rec = ri; }
+    }
+    return reinterpret_cast<double *>(rec) + (size_t)(step - off) * D + c;
+}
+// one warp, its chain: the neighbour's message out of this GPU's mailbox into the accepted containers (and the starting
+// point); the last unit of the block to finish acknowledges in the sender's memory.  One chain: no counter, no fence
+// beyond the release store (a gpu-scope fence costs more than the hand-over: tools/micro/p2p_latency.cu)
+__device__ __forceinline__ void hf_pull_unit(const SolveParams &p, int chain, int lane, int D) {
+    const HaloFuse &h = p.hf;
+    const int nj = h.pull_j1 - h.pull_j0;
+    const HfMap m = hf_map(p, h.pull_j0, h.pull_j1, chain, lane, 0);
+    const int n = (h.iv_st_off[h.pull_j1] - h.iv_st_off[h.pull_j0]) * D;
+    if (lane == 0) hf_spin(h.pull_flag, h.pull_val, h.err);
+    __syncwarp();
+    const double *src = h.pull_box + (size_t)chain * h.pull_stride;
+    if (h.pull_lead > 0 && lane < D)
+        const_cast<double *>(p.x0)[(size_t)lane * p.C + chain] = __ldcg(src + h.pull_lead - D + lane);  // R = 1: record 0
+    for (int e0 = 0; e0 < n; e0 += 32) {  // uniform trip count: the address look-up shuffles
+        const int e = e0 + lane;
+        double *dst = hf_addr(m, nj, min(e, n - 1), D);
+        if (e < n) *dst = __ldcg(src + h.pull_lead + e);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        bool last = true;
+        if (p.C > 1) {
+            __threadfence();
+            last = atomicAdd(h.pull_counter, 1u) == (unsigned)p.C - 1u;
+            if (last) { *h.pull_counter = 0; __threadfence(); }
+        }
+        if (last) hf_st_release_sys(h.pull_ack, h.pull_val);
+    }
+}
+// one warp, its chain, after the accept decision: the accepted path of the message's intervals straight into the
+// neighbour's mailbox (stores over NVLink); the last unit of the block raises the neighbour's data flag
+__device__ __forceinline__ void hf_push_unit(const SolveParams &p, int chain, int lane, int D, bool acc) {
+    const HaloFuse &h = p.hf;
+    const int nj = h.push_j1 - h.push_j0;
+    const HfMap m = hf_map(p, h.push_j0, h.push_j1, chain, lane, acc ? 1 : 0);
+    const int n = (h.iv_st_off[h.push_j1] - h.iv_st_off[h.push_j0]) * D;
+    if (lane == 0) hf_spin(h.push_wait, h.push_wait_val, h.err);  // the previous message has been taken out
+    __threadfence_block();  // this warp's proposal stores are what is read back below (from L2)
+    __syncwarp();
+    double *dst = h.push_box + (size_t)chain * h.push_stride;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        const double *src = hf_addr(m, nj, min(e, n - 1), D);
+        if (e < n) dst[e] = __ldcg(src);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        bool last = true;
+        if (p.C > 1) {
+            __threadfence();
+            last = atomicAdd(h.push_counter, 1u) == (unsigned)p.C - 1u;
+            if (last) { *h.push_counter = 0; __threadfence(); }
+        }
+        if (last) hf_st_release_sys(h.push_flag, h.push_val);
+    }
+}
+
 // MS: a tile may hold up to MS WHOLE consecutive intervals when they are short (<= 32 steps together): phase P costs the
 // same for 10 live lanes as for 32, and with 10-step intervals (BASELINE config 4) it was paid per interval.  MS = 1: every
 // tile is a 32-step chunk of one interval.  The tile sequence of a block follows from iv_N alone (fit_intervals), so the
@@ -97,6 +202,13 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if constexpr (MODE == MODE_IMPUTE) {
+        if (p.hf.blk == blk && p.hf.pull_box) {  // CTA-uniform: this is the edge block and a message is due
+            if (do_S && in_range) hf_pull_unit(p, chain, lane, D);
+            __syncthreads();  // producer warps read the accepted path too
+        }
+    }
 
     // ---- table pipeline (thread 0): one bulk copy per 32-step tile, one tile ahead ----
     int tj = i1, ttl = 0, tq = 0, tN = p.iv_N[i1], ttoff = p.iv_tile_off[i1];
@@ -549,6 +661,7 @@ __global__ void __launch_bounds__(256) solve_coop_kernel(const SolveParams p) {
             p.selX_out[o] = p.selX_in[o] ^ (uint8_t)acc;
             p.selW_out[o] = p.selW_in[o] ^ (uint8_t)(acc && STORE_W);
         }
+        if (p.hf.blk == blk && p.hf.push_box) hf_push_unit(p, chain, lane, D, acc);  // the neighbour's halo / start point
     }
     if (lane == 0) {
         if (p.acc_count && acc) atomicAdd(p.acc_count + blk, 1ull);

@@ -275,6 +275,11 @@ class Engine:
         self._ck(self.lib.dmcmc_comm_enable_p2p(self.h, int(mailbox_bytes)))
         return bool(self.lib.dmcmc_comm_p2p_enabled(self.h))
 
+    def impute_exchange_async(self, it, pattern, n_first, n_halo, left_edge_steps):
+        """impute_async + the halo_exchange that follows it under `pattern`, fused into the sweep kernels when peer memory
+        is on and the launch goes to the warp-per-unit kernel (else the two calls one after the other)."""
+        self._ck(self.lib.dmcmc_impute_exchange_async(self.h, int(it), int(pattern), int(n_first), int(n_halo), int(left_edge_steps)))
+
     def comm_destroy(self):
         self._ck(self.lib.dmcmc_comm_destroy(self.h))
 

@@ -286,8 +286,9 @@ class LibHalo:
     what a host without torch.distributed, i.e. the Julia plugin, calls.  `unique_id` comes from
     Engine.comm_unique_id() on one rank and is handed to the others by the host."""
 
-    def __init__(self, sampler, unique_id, p2p=None):
+    def __init__(self, sampler, unique_id, p2p=None, fused=None):
         s = self.s = sampler
+        self.fused = (os.environ.get("DMCMC_P2P_FUSE", "1") != "0") if fused is None else bool(fused)
         s.engine.comm_init(unique_id, s.rank, s.world)
         n_own = s.b - s.a
         self.n_first = min(s.h, n_own)
@@ -304,6 +305,15 @@ class LibHalo:
 
     def iterate(self, it):
         s, e = self.s, self.s.engine
+        if s.world > 1 and self.p2p and self.fused:
+            # sweep + exchange in one call: the edge block's warps push / pull inside the sweep kernels
+            for pat in (0, 1):
+                i1, i2, pin, act = s.lays[pat]
+                e.set_layout(i1, i2, pin)
+                e.set_block_mask(act)
+                e.impute_exchange_async(2 * it + pat, pat, self.n_first, self.n_halo, self.left_edge_steps)
+                s.sweeps += 1
+            return
         s.sweep_async(0, 2 * it)
         if s.world > 1:
             e.halo_exchange(0, self.n_first, self.n_halo, self.left_edge_steps)

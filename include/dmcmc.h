@@ -251,6 +251,16 @@ int dmcmc_halo_exchange(dmcmc_ctx *ctx, int32_t after_pattern, int32_t n_first, 
  * and every exchange when IPC is unavailable on any rank, still go through NCCL; results are identical either way.
  * dmcmc_comm_p2p_enabled: 1 when peer memory is in use. */
 int dmcmc_comm_enable_p2p(dmcmc_ctx *ctx, int64_t mailbox_bytes);
+/* dmcmc_impute_async + the dmcmc_halo_exchange that follows it under `pattern`, FUSED: with peer memory on and a launch
+ * small enough for the warp-per-unit kernel (a single chain, or a few), the units of the layout's edge block store their
+ * freshly accepted intervals into the neighbour's mailbox right after their accept decision, inside the sweep kernel, and
+ * the neighbour's next such sweep takes the message out of its mailbox before that block's units read anything -- no
+ * kernel boundary and no pack / unpack pass between a sweep and its exchange.  A message still in the mailbox when
+ * anything else touches the paths (read-outs, parameter step, layout switch, dmcmc_halo_exchange, dmcmc_comm_destroy) is
+ * taken out first.  Otherwise (no peer memory, many chains, d = 40) it is the two calls one after the other; results
+ * are bit-identical either way. */
+int dmcmc_impute_exchange_async(dmcmc_ctx *ctx, uint32_t iter, int32_t pattern, int32_t n_first, int32_t n_halo,
+                                int32_t left_edge_steps);
 int dmcmc_comm_p2p_enabled(const dmcmc_ctx *ctx);
 /* a9 on a block-sharded recording (set_proposal!, src/run!_alterations.jl:177-211; ONE accept decision
  * for all blocks, :367): every rank solves its blocks, the per-block ll deg / ll are all-reduced over the

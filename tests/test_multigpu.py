@@ -39,7 +39,7 @@ def _thetas(spec):
     return th1, th2
 
 
-def _worker(rank, world, uid, q, p2p):
+def _worker(rank, world, uid, q, p2p, fused):
     sys.path.insert(0, ROOT)
     import dmcmc_pkg
     pkg = dmcmc_pkg.load()
@@ -49,7 +49,7 @@ def _worker(rank, world, uid, q, p2p):
     mk = lambda sp, off: Engine(sp, device=rank, seed=SEED, interval_offset=off)
     full0 = parallel.initial_full_path(spec, mk)
     s = parallel.BlockShardedSampler(spec, rank, world, H, mk, full0)
-    halo = parallel.LibHalo(s, uid, p2p=p2p)
+    halo = parallel.LibHalo(s, uid, p2p=p2p, fused=fused)
     th1, th2 = _thetas(spec)
     for it in range(ITERS):
         halo.iterate(it)
@@ -98,11 +98,13 @@ def _unsharded(pkg):
     return X, p1, p2
 
 
-@pytest.mark.parametrize("halo", ["nccl", "peer_memory"])
+@pytest.mark.parametrize("halo", ["nccl", "peer_memory", "peer_memory_fused"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_block_sharded_sweeps_and_parameter_step_in_library_nccl(pkg, world, halo):
     """halo = nccl: end-point exchange by ncclSend / ncclRecv; peer_memory: by stores into the neighbour's CUDA-IPC mailbox
-    and sequence flags (dmcmc_comm_enable_p2p).  Both must reproduce one GPU bit for bit."""
+    and sequence flags (dmcmc_comm_enable_p2p), in a kernel of its own; peer_memory_fused: the same stores and flags from
+    inside the sweep kernels (dmcmc_impute_exchange_async: the edge block's warps push after their accept decision and
+    pull before they read).  All three must reproduce one GPU bit for bit."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -111,14 +113,14 @@ def test_block_sharded_sweeps_and_parameter_step_in_library_nccl(pkg, world, hal
     uid = Engine.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, uid, q, halo == "peer_memory")) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, uid, q, halo != "nccl", halo == "peer_memory_fused")) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert all(r[4] == (halo == "peer_memory") for r in res), "peer-memory mailboxes could not be set up (CUDA IPC)"
+    assert all(r[4] == (halo != "nccl") for r in res), "peer-memory mailboxes could not be set up (CUDA IPC)"
     X = np.concatenate([r[1] for r in res], axis=1)
     assert np.array_equal(X, Xref), f"sharded over {world} GPUs != unsharded: max diff {np.abs(X - Xref).max()}"
     for rank, _, p1, p2, _ in res:
