@@ -258,6 +258,10 @@ end
 halo_exchange!(ctx, after_pattern::Integer, n_first::Integer, n_halo::Integer, left_edge_steps::Integer) =
     check(ctx, ccall((:dmcmc_halo_exchange, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Int32),
                      ctx.h, after_pattern, n_first, n_halo, left_edge_steps))
+# the sweep and the exchange that follows it in one call (fused into the sweep kernels when peer memory is on)
+impute_exchange!(ctx, iter::Integer, pattern::Integer, n_first::Integer, n_halo::Integer, left_edge_steps::Integer) =
+    check(ctx, ccall((:dmcmc_impute_exchange_async, LIB), Cint, (Ptr{Cvoid}, UInt32, Int32, Int32, Int32, Int32),
+                     ctx.h, iter, pattern, n_first, n_halo, left_edge_steps))
 comm_destroy!(ctx) = check(ctx, ccall((:dmcmc_comm_destroy, LIB), Cint, (Ptr{Cvoid},), ctx.h))
 
 end # module
