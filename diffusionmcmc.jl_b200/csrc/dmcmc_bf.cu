@@ -465,12 +465,20 @@ struct Coop {
     __device__ double lu(double *A, int *piv) const {
         double lad = 0.0;
         for (int k = 0; k < D; ++k) {
-            if (tid == 0) {
+            if (tid < 32) {  // first maximum of |A[i][k]|, i >= k (the oracle's rule), by one warp: strided scan + reduction
                 int p = k;
-                double best = fabs(A[k * D + k]);
-                for (int i = k + 1; i < D; ++i)
-                    if (fabs(A[i * D + k]) > best) { best = fabs(A[i * D + k]); p = i; }
-                piv[k] = p;
+                double best = -1.0;
+                for (int i = k + tid; i < D; i += 32) {
+                    const double v = fabs(A[i * D + k]);
+                    if (v > best) { best = v; p = i; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ob = __shfl_down_sync(0xffffffffu, best, off);
+                    const int op = __shfl_down_sync(0xffffffffu, p, off);
+                    if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+                }
+                if (tid == 0) piv[k] = p;
             }
             __syncthreads();
             const int p = piv[k];
@@ -495,21 +503,32 @@ struct Coop {
         }
         return lad;
     }
-    // solve A X = Bm for NR columns (Bm row-major D x NR, overwritten): one thread per column
-    __device__ void solve(const double *LU, const int *piv, double *Bm, int NR) const {
-        for (int j = tid; j < NR; j += nt) {
-            for (int k = 0; k < D; ++k) {
-                const int p = piv[k];
-                if (p != k) { const double t = Bm[k * NR + j]; Bm[k * NR + j] = Bm[p * NR + j]; Bm[p * NR + j] = t; }
-                const double bk = Bm[k * NR + j];
-                for (int i = k + 1; i < D; ++i) Bm[i * NR + j] -= LU[i * D + k] * bk;
-            }
-            for (int k = D - 1; k >= 0; --k) {
-                double sacc = Bm[k * NR + j];
-                for (int i = k + 1; i < D; ++i) sacc -= LU[k * D + i] * Bm[i * NR + j];
-                Bm[k * NR + j] = sacc * (1.0 / LU[k * D + k]);
-            }
+    // column j of A X = Bm (Bm row-major D x NR, overwritten) by one thread
+    __device__ void solve_col(const double *LU, const int *piv, double *Bm, int NR, int j) const {
+        for (int k = 0; k < D; ++k) {
+            const int p = piv[k];
+            if (p != k) { const double t = Bm[k * NR + j]; Bm[k * NR + j] = Bm[p * NR + j]; Bm[p * NR + j] = t; }
+            const double bk = Bm[k * NR + j];
+            for (int i = k + 1; i < D; ++i) Bm[i * NR + j] -= LU[i * D + k] * bk;
         }
+        for (int k = D - 1; k >= 0; --k) {
+            double sacc = Bm[k * NR + j];
+            for (int i = k + 1; i < D; ++i) sacc -= LU[k * D + i] * Bm[i * NR + j];
+            Bm[k * NR + j] = sacc * (1.0 / LU[k * D + k]);
+        }
+    }
+    // solve A X = Bm for NR columns: one thread per column
+    __device__ void solve(const double *LU, const int *piv, double *Bm, int NR) const {
+        for (int j = tid; j < NR; j += nt) solve_col(LU, piv, Bm, NR, j);
+        __syncthreads();
+    }
+    // the step's three right-hand sides (H: D columns, F: one, Psi: D columns when the block is pinned) in ONE pass, a
+    // thread per column in separate warps -- each column's arithmetic is what solve() does, so the tables do not change;
+    // one after the other the three passes were about half of a backward step (a column is 3200 serial multiply-subtracts)
+    __device__ void solve3(const double *LU, const int *piv, double *Hm, double *Fv, double *Pm) const {
+        if (tid < D) solve_col(LU, piv, Hm, D, tid);
+        else if (tid == 64) solve_col(LU, piv, Fv, 1, 0);
+        else if (Pm && tid >= 96 && tid < 96 + D) solve_col(LU, piv, Pm, D, tid - 96);
         __syncthreads();
     }
 };
@@ -625,18 +644,16 @@ __global__ void __launch_bounds__(256) bf_big_kernel(const BFParams b) {
             __syncthreads();
             const double lad = co.lu(A, piv);
             co.copy(Hs, H, DD);
-            co.solve(A, piv, Hs, D);
-            co.sym(Hs);
             co.copy(Fs, F0, D);
-            co.solve(A, piv, Fs, 1);
+            if (pinned) co.copy(Psis, Psi, DD);
+            co.solve3(A, piv, Hs, Fs, pinned ? Psis : nullptr);
+            co.sym(Hs);
             co.mv(Hs, mvec, tv);
             co.mv(Q, Fs, tv2);
             if (tid == 0)
                 c0s = c0s + 0.5 * lad + 0.5 * co.dot(mvec, tv) - co.dot(mvec, Fs) - 0.5 * co.dot(F0, tv2);
             __syncthreads();
             if (pinned) {
-                co.copy(Psis, Psi, DD);
-                co.solve(A, piv, Psis, D);
                 co.mTv(Psis, mvec, a1);
                 co.mTv(Psi, tv2, a2);
                 for (int i = tid; i < D; i += nt) g[i] = g[i] - a1[i] - a2[i];
