@@ -348,7 +348,7 @@ def config_c4(pkg, K, W, local_rank, rank, world):
     uid = [Engine.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     halo = parallel.LibHalo(s, uid[0], p2p=False)
-    n = max(K, 100)
+    n = max(K, 1000)   # 100 iterations (7 ms) scattered by +-5 us from run to run
 
     def timed_iterations(first):
         for it in range(first, first + max(W, 3)):
@@ -367,11 +367,11 @@ def config_c4(pkg, K, W, local_rank, rank, world):
     p2p_on = os.environ.get("DMCMC_P2P", "1") != "0" and s.engine.comm_enable_p2p((s.h + 1) * s.N_max * s.engine.d * 8 * s.engine.C)
     halo.p2p = p2p_on
     halo.fused = False
-    dt_p2p = timed_iterations(1000) if p2p_on else dt_nccl
+    dt_p2p = timed_iterations(10_000) if p2p_on else dt_nccl
     # third: the same stores and flags from inside the sweep kernels (dmcmc_impute_exchange_async)
     fused_on = p2p_on and os.environ.get("DMCMC_P2P_FUSE", "1") != "0"
     halo.fused = fused_on
-    dt = timed_iterations(2000) if fused_on else dt_p2p
+    dt = timed_iterations(20_000) if fused_on else dt_p2p
     halo.fused = False   # the part timings below call the exchange and the sweeps on their own
     # what the two parts cost on their own: the exchanges alone (same messages, nothing computed in between) and the
     # sweeps alone (no exchange; the halo goes stale, which does not change the work)
