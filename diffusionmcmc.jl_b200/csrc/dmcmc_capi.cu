@@ -2140,6 +2140,7 @@ extern "C" int dmcmc_impute_exchange_async(dmcmc_ctx *ctx, uint32_t iter, int32_
     REQUIRE(ctx->R == 1 && ctx->lay_cur >= 0, "dmcmc_impute_exchange_async: one recording, layout set");
     const int r = ctx->comm_rank, w = ctx->comm_world, J = ctx->J, d = ctx->d;
     REQUIRE(n_first > 0 && n_first <= J - n_halo && n_halo >= 0 && n_halo < J, "dmcmc_impute_exchange_async: bad interval counts");
+    REQUIRE((r < w - 1) == (n_halo > 0) || w == 1, "dmcmc_impute_exchange_async: every rank but the last holds a halo");
     const int n_own = J - n_halo;
     const size_t C = (size_t)ctx->C;
     // the messages of this pattern's exchange (as in dmcmc_halo_exchange)
