@@ -29,6 +29,42 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
 
 
+def test_ctypes_mirror_matches_the_header_prototypes(lib):
+    """The hand-written ctypes table (_lib.SYMBOLS) against the prototypes of include/dmcmc.h: same number of parameters,
+    and pointer / 64-bit / 32-bit / double kinds in the same positions (a mismatch would pass the symbol-name test and
+    corrupt arguments at run time)."""
+    hdr = open(os.path.join(ROOT, "include", "dmcmc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"\b([A-Za-z_][A-Za-z0-9_ \*]*?)\b(dmcmc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)
+    assert len(protos) >= 40
+
+    def kind(decl):
+        d = decl.strip()
+        if "*" in d or "[" in d:   # array parameters decay to pointers
+            return "ptr"
+        if re.search(r"\b(int64_t|uint64_t|size_t|long long)\b", d):
+            return "i64"
+        if re.search(r"\bdouble\b", d):
+            return "f64"
+        return "i32"
+
+    C = C_ = ctypes
+    ck = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int64: "i64", C.c_uint64: "i64", C.c_size_t: "i64", C.c_double: "f64",
+          C.c_int: "i32", C.c_int32: "i32", C.c_uint32: "i32", C.c_uint8: "i32"}
+    seen = 0
+    for ret, name, args in protos:
+        if name not in lib.SYMBOLS:
+            continue
+        params = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        restype, argtypes = lib.SYMBOLS[name]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, ctypes mirror {len(argtypes)}"
+        for i, (a, t) in enumerate(zip(params, argtypes)):
+            tk = "ptr" if (isinstance(t, type) and issubclass(t, C_._Pointer)) or t in (C.c_void_p, C.c_char_p) else ck.get(t)
+            assert tk == kind(a), f"{name}: parameter {i} is `{a}` in the header, {t} in the ctypes mirror"
+        seen += 1
+    assert seen == len(lib.SYMBOLS)
+
+
 def test_layout_helper_matches_host_mirror(lib, pkg):
     l = lib.load()
     for nobs in ([100], [5, 8, 3], [1]):
