@@ -44,6 +44,11 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     subprocess.check_call(["nvcc", "-shared", "-o", LIB_PATH] + objs +
                           ["-gencode", "arch=compute_100a,code=sm_100a"], cwd=CSRC)
+    for obj in objs:  # every build compiles every source: the objects are not reused, and they would double what travels
+        try:          # to the GPU box with the snapshot
+            os.remove(obj)
+        except OSError:
+            pass
     return LIB_PATH
 
 
